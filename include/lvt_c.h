@@ -1,0 +1,135 @@
+/*
+ * lvt_c.h -- public C ABI of the B200-native LVT front end.
+ *
+ * The first five entry points are the reference's C interface, unchanged in
+ * name, argument order and meaning (reference: lvt/src/lvt_c.h:55-62,
+ * behaviour: lvt/src/lvt_c.cpp:33-148).  A C caller or FFI binding written
+ * against the reference's liblvt_c links against this library unmodified.
+ *
+ * Everything below the "additive extensions" banner is new and does not
+ * alter the five reference entry points.
+ *
+ * Two libraries export this ABI:
+ *   - lvt_b200/lib/liblvt_b200.so : the product (CUDA, sm_100a).  No CPU path.
+ *   - oracle/_build/liblvt_oracle.so : the CPU oracle (test infrastructure).
+ */
+#ifndef LVT_B200_C_INTERFACE_H__
+#define LVT_B200_C_INTERFACE_H__
+
+#if defined(LVT_EXPORT_FUNCTIONS) && defined(__GNUC__)
+#define LVT_API __attribute__((visibility("default")))
+#else
+#define LVT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *lvt_handle;
+
+/* ---- reference ABI (lvt/src/lvt_c.h:55-62) -------------------------------------------- */
+
+/* sensor_type: 1 = stereo, 2 = RGB-D.  NULL on unreadable YAML / bad sensor / any failure
+ * (lvt/src/lvt_c.cpp:33-48).  The YAML must carry fx,fy,cx,cy,baseline,img_width,img_height. */
+LVT_API lvt_handle lvt_create(const char *config_file_name, int sensor_type);
+/* lvt/src/lvt_c.cpp:50-61 */
+LVT_API void lvt_destroy(lvt_handle vo_system);
+/* 8-bit single-channel tightly packed images, borrowed for the call.  R = camera->world
+ * rotation (row-major), t = camera position in the frame-0 world.  Outputs are left
+ * untouched on an internal failure (lvt/src/lvt_c.cpp:63-88). */
+LVT_API void lvt_track(lvt_handle vo_system, unsigned char *left_img, unsigned char *right_img,
+                       int n_rows, int n_cols, double R[3][3], double t[3]);
+/* lvt/src/lvt_c.cpp:90-134 */
+LVT_API void lvt_track_with_external_corners(lvt_handle vo_system, unsigned char *left_img,
+                                             unsigned char *right_img, int n_rows, int n_cols,
+                                             double corners_left[][2], int n_corners_left,
+                                             double corners_right[][2], int n_corners_right,
+                                             double R[3][3], double t[3]);
+/* 1 = not initialised, 2 = tracking, 3 = lost, -1 on failure (lvt/src/lvt_c.cpp:136-148) */
+LVT_API int lvt_get_status(lvt_handle vo_system);
+
+/* ---- additive extensions ------------------------------------------------------------ */
+
+/* Plain-C mirror of struct lvt_parameters (lvt/src/lvt_parameters.h:29-64), same field
+ * meaning and defaults (lvt/src/lvt_parameters.cpp:29-52).  bools are ints. */
+typedef struct lvt_params_c
+{
+    float fx, fy, cx, cy;
+    float baseline;
+    int img_width, img_height;
+    float k1, k2, p1, p2, k3;
+    float near_plane_distance, far_plane_distance;
+    float triangulation_ratio_test_threshold;
+    float tracking_ratio_test_threshold;
+    float descriptor_matching_threshold;
+    int min_num_matches_for_tracking;
+    int tracking_radius;
+    int detection_cell_size;
+    int max_keypoints_per_cell;
+    int agast_threshold;
+    int untracked_threshold;
+    int staged_threshold;
+    int enable_logging;
+    int enable_visualization;
+    int triangulation_policy; /* 1 decreasing matches, 2 always, 3 map size */
+    float viewer_camera_size;
+    int viewer_point_size;
+} lvt_params_c;
+
+/* fill with the reference defaults (lvt/src/lvt_parameters.cpp:29-52) */
+LVT_API void lvt_params_default(lvt_params_c *p);
+/* flat OpenCV-FileStorage YAML reader (lvt/src/lvt_parameters.cpp:54-93): missing keys read
+ * as 0, exactly as cv::FileNode does.  Returns 1 on success, 0 if the file cannot be opened. */
+LVT_API int lvt_params_from_file(lvt_params_c *p, const char *config_file_name);
+/* lvt_system::create (lvt/src/lvt_system.cpp:70-127) from a struct, so that calibration can
+ * arrive by broadcast rather than by file. */
+LVT_API lvt_handle lvt_create_from_params(const lvt_params_c *p, int sensor_type);
+/* lvt_system::reset (lvt/src/lvt_system.cpp:44-68) */
+LVT_API void lvt_reset(lvt_handle vo_system);
+/* RGB-D frame: gray u8 + depth in metres as float32 (lvt/src/lvt_system.cpp:179-183); the
+ * reference's C ABI cannot carry a float image (lvt/src/lvt_c.cpp:69-70). */
+LVT_API void lvt_track_rgbd(lvt_handle vo_system, const unsigned char *gray_img, const float *depth_m,
+                            int n_rows, int n_cols, double R[3][3], double t[3]);
+
+/* Per-frame bookkeeping numbers: the series the reference's value recorder registers
+ * (lvt/src/lvt_system.cpp:336-350) plus what a parity test needs. */
+typedef struct lvt_frame_info
+{
+    int frame_number;      /* as lvt_system::m_frame_number after the call */
+    int state;             /* 1/2/3 */
+    int n_features_left;   /* "image keypoints" */
+    int n_features_right;
+    int map_points_before; /* "map points count" at perform_tracking entry */
+    int staged_before;     /* "staged points count" */
+    int tracked;           /* "tracked map points" (matches fed to the pose solve) */
+    int inliers;           /* "inlier count" */
+    int map_points_after;
+    int staged_after;
+    int triangulated;      /* 1 if update_with_new_triangulation ran this frame */
+    int new_points;        /* points it produced */
+    int retried_matching;  /* 1 if the <50 matches, radius x2 pass ran */
+} lvt_frame_info;
+
+LVT_API int lvt_get_frame_info(lvt_handle vo_system, lvt_frame_info *out);
+/* quaternion (w,x,y,z) + position of the last returned pose */
+LVT_API int lvt_get_last_pose(lvt_handle vo_system, double q_wxyz[4], double t[3]);
+
+/* Debug read-back of the state after the last track call (parity tests).
+ * which: 0 = left/gray features, 1 = right features.  kps_xy: n x 2 float, desc: n x 32 bytes.
+ * Returns the count (and copies min(count,cap) entries), <0 on error. */
+LVT_API int lvt_debug_get_features(lvt_handle vo_system, int which, float *kps_xy, unsigned char *desc, int cap);
+/* which: 0 = map points, 1 = staged points.  xyz: n x 3 double, counters/ages/match_idx: n int. */
+LVT_API int lvt_debug_get_points(lvt_handle vo_system, int which, double *xyz, unsigned char *desc,
+                                 int *counters, int *ages, int *match_idx, int cap);
+
+/* Replace the 256 BRIEF test pairs (process-wide; call before lvt_create).
+ * pairs[i] = {dy1, dx1, dy2, dx2}, |offset| <= 24, in the order of opencv_contrib's
+ * generated_32.i.  NULL restores the built-in table.  Returns 0 on success. */
+LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4]);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LVT_B200_C_INTERFACE_H__ */
