@@ -1,0 +1,255 @@
+// Common device/host helpers for the sm_100a LVT front end.
+#pragma once
+
+#include "../../include/lvt_kernels.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lvtb
+{
+
+// ---------------------------------------------------------------------------------------------
+// error handling: every CUDA call is checked; the C ABI turns failures into LVTK_ERR_CUDA.
+// ---------------------------------------------------------------------------------------------
+void set_last_error(const char *file, int line, const char *what);
+const char *last_error();
+
+#define LVT_CUDA_TRY(expr)                                                                                            \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess)                                                                                        \
+        {                                                                                                             \
+            lvtb::set_last_error(__FILE__, __LINE__, cudaGetErrorString(_e));                                         \
+            return LVTK_ERR_CUDA;                                                                                     \
+        }                                                                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// reference constants (lvt/src/lvt_definitions.h:29-34)
+// ---------------------------------------------------------------------------------------------
+constexpr double kReprojectionTh2 = 5.991; // LVT_REPROJECTION_TH2
+constexpr int kNMapPoints = 250;           // LVT_N_MAP_POINTS
+constexpr int kRowSearchRadius = 2;        // LVT_ROW_MATCHING_VERTICAL_SEARCH_RADIUS
+constexpr int kHashCell = 25;              // LVT_HASHING_CELL_SIZE
+constexpr int kCornersLowTh = 200;         // LVT_CORNERS_LOW_TH
+constexpr int kNMatchesTh = 50;            // LVT_N_MATCHES_TH
+constexpr int kBriefBorder = 28;           // PATCH_SIZE/2 + KERNEL_SIZE/2 (opencv_contrib brief.cpp)
+
+// ---------------------------------------------------------------------------------------------
+// fp64 pose math on the device (Eigen formulas, see lvt/src/lvt_pose.h:34-79)
+// ---------------------------------------------------------------------------------------------
+struct Quat
+{
+    double w, x, y, z;
+};
+struct PoseD
+{
+    Quat q;
+    double t[3];
+};
+
+__host__ __device__ inline Quat quat_mul(const Quat &a, const Quat &b)
+{
+    Quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+__host__ __device__ inline double quat_dot(const Quat &a, const Quat &b)
+{
+    return a.w * b.w + a.x * b.x + a.y * b.y + a.z * b.z;
+}
+__host__ __device__ inline Quat quat_normalized(const Quat &q)
+{
+    const double n = sqrt(quat_dot(q, q));
+    Quat r;
+    r.w = q.w / n;
+    r.x = q.x / n;
+    r.y = q.y / n;
+    r.z = q.z / n;
+    return r;
+}
+__host__ __device__ inline Quat quat_inverse(const Quat &q)
+{
+    const double n2 = quat_dot(q, q);
+    Quat r;
+    if (n2 > 0)
+    {
+        r.w = q.w / n2;
+        r.x = -q.x / n2;
+        r.y = -q.y / n2;
+        r.z = -q.z / n2;
+    }
+    else
+    {
+        r.w = r.x = r.y = r.z = 0;
+    }
+    return r;
+}
+// rotation matrix, row-major R[3*i+j]
+__host__ __device__ inline void quat_to_mat(const Quat &q, double R[9])
+{
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    R[0] = 1 - (tyy + tzz);
+    R[1] = txy - twz;
+    R[2] = txz + twy;
+    R[3] = txy + twz;
+    R[4] = 1 - (txx + tzz);
+    R[5] = tyz - twx;
+    R[6] = txz - twy;
+    R[7] = tyz + twx;
+    R[8] = 1 - (txx + tyy);
+}
+// world -> camera 3x4, row-major W[4*i+j]: [R^T | -R^T t]  (lvt/src/lvt_pose.cpp:36-43)
+__host__ __device__ inline void world_to_camera(const PoseD &p, double W[12])
+{
+    double R[9];
+    quat_to_mat(p.q, R);
+    for (int i = 0; i < 3; i++)
+    {
+        const double a = R[0 + i], b = R[3 + i], c = R[6 + i]; // row i of R^T
+        W[4 * i + 0] = a;
+        W[4 * i + 1] = b;
+        W[4 * i + 2] = c;
+        W[4 * i + 3] = (-a) * p.t[0] + (-b) * p.t[1] + (-c) * p.t[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera / matching parameters handed to kernels by value
+// ---------------------------------------------------------------------------------------------
+struct CamParams
+{
+    float fx, fy, cx, cy, baseline;
+    float near_plane, far_plane;
+    float min_x, max_x, min_y, max_y; // image bounds (lvt/src/lvt_local_map.cpp:84-123), per instance
+    int img_w, img_h;
+    int cells_x, cells_y;     // 25-px hash grid
+    int cell_search_radius;   // lvt/src/lvt_image_features_struct.cpp:53
+    int tracking_radius;
+    float tracking_ratio_th, triangulation_ratio_th, desc_dist_th;
+};
+
+// is_point_visible (lvt/src/lvt_local_map.cpp:62-82)
+__device__ inline bool point_visible(const double W[12], const CamParams &c, double x, double y, double z, double *u,
+                                     double *v)
+{
+    const double xc = W[0] * x + W[1] * y + W[2] * z + W[3];
+    const double yc = W[4] * x + W[5] * y + W[6] * z + W[7];
+    const double zc = W[8] * x + W[9] * y + W[10] * z + W[11];
+    if (zc < (double)c.near_plane || zc > (double)c.far_plane)
+        return false;
+    const double inv_z = 1.0 / zc;
+    const double uu = (double)c.fx * xc * inv_z + (double)c.cx;
+    const double vv = (double)c.fy * yc * inv_z + (double)c.cy;
+    if (uu < (double)c.min_x || uu > (double)c.max_x || vv < (double)c.min_y || vv > (double)c.max_y)
+        return false;
+    *u = uu;
+    *v = vv;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp / block primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// exclusive prefix sum of one int per thread over the block; returns the exclusive value and the
+// block total through *total.  scratch: >= 33 ints of shared memory.  All threads must call.
+__device__ inline int block_exclusive_scan(int v, int *scratch, int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += n;
+    }
+    __syncthreads(); // scratch may still be read from a previous call
+    if (lane == 31)
+        scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        int w = lane < nwarps ? scratch[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o)
+                wi += n;
+        }
+        scratch[lane] = wi - w; // exclusive per-warp offset
+        if (lane == 31)
+            scratch[32] = wi;
+    }
+    __syncthreads();
+    *total = scratch[32];
+    return scratch[warp] + incl - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) + mbarrier, hand-written PTX
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// bounded wait: a TMA that never lands traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24))
+            __trap();
+}
+// 3-D tiled load: tensor (x, y, image) -> dense box in shared memory
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+                 "l"((uint64_t)map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+} // namespace lvtb

@@ -1,0 +1,1165 @@
+// Host side of liblvt_b200.so: the per-sequence context, the seam ABI (include/lvt_kernels.h),
+// the lvt_system mirror and the public C ABI (include/lvt_c.h).
+//
+// lvt_system's control flow (lvt/src/lvt_system.cpp:157-207) is kept on the host only as far as
+// the C ABI needs it (LOST short-circuit, frame counter, returning the pose); everything
+// perform_tracking does runs on the device (track.cu).  There is no CPU implementation of any
+// stage in this library: without a CUDA device lvt_create returns NULL and the seam calls
+// return LVTK_ERR_NO_DEVICE.
+#define LVT_EXPORT_FUNCTIONS
+#include "context.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+
+namespace lvtb
+{
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char *file, int line, const char *what)
+{
+    std::snprintf(g_err, sizeof(g_err), "%s:%d: %s", file, line, what);
+    if (std::getenv("LVT_B200_VERBOSE"))
+        std::fprintf(stderr, "[lvt_b200] %s\n", g_err);
+}
+const char *last_error() { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// parameters (lvt/src/lvt_parameters.cpp:29-93)
+// ---------------------------------------------------------------------------------------------
+static void params_default(lvt_params_c *p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->fx = p->fy = p->cx = p->cy = 0.5f;
+    p->near_plane_distance = 0.1f;
+    p->far_plane_distance = 500.0f;
+    p->triangulation_ratio_test_threshold = 0.60f;
+    p->tracking_ratio_test_threshold = 0.80f;
+    p->descriptor_matching_threshold = 30.0f;
+    p->min_num_matches_for_tracking = 10;
+    p->tracking_radius = 25;
+    p->agast_threshold = 25;
+    p->untracked_threshold = 10;
+    p->staged_threshold = 2;
+    p->detection_cell_size = 250;
+    p->max_keypoints_per_cell = 150;
+    p->triangulation_policy = 1;
+    p->enable_logging = 1;
+    p->enable_visualization = 0;
+    p->viewer_camera_size = 0.6f;
+    p->viewer_point_size = 5;
+}
+
+// flat "key: value" reader for OpenCV FileStorage YAML 1.0; absent keys read as 0 like cv::FileNode
+static int params_from_file(lvt_params_c *p, const char *file)
+{
+    FILE *f = file ? std::fopen(file, "r") : nullptr;
+    if (!f)
+        return 0;
+    std::map<std::string, double> kv;
+    char line[1024];
+    while (std::fgets(line, sizeof(line), f))
+    {
+        char *hash = std::strchr(line, '#');
+        if (hash)
+            *hash = 0;
+        if (line[0] == '%' || line[0] == '-')
+            continue;
+        char *colon = std::strchr(line, ':');
+        if (!colon)
+            continue;
+        *colon = 0;
+        std::string key(line);
+        const size_t b = key.find_first_not_of(" \t"), e = key.find_last_not_of(" \t\r\n");
+        if (b == std::string::npos)
+            continue;
+        key = key.substr(b, e - b + 1);
+        char *end = nullptr;
+        const double v = std::strtod(colon + 1, &end);
+        if (end == colon + 1)
+            continue;
+        kv[key] = v;
+    }
+    std::fclose(f);
+    auto num = [&kv](const char *k) {
+        auto it = kv.find(k);
+        return it == kv.end() ? 0.0 : it->second;
+    };
+    auto integer = [&num](const char *k) { return (int)std::lrint(num(k)); };
+    std::memset(p, 0, sizeof(*p));
+    p->fx = (float)num("fx");
+    p->fy = (float)num("fy");
+    p->cx = (float)num("cx");
+    p->cy = (float)num("cy");
+    p->k1 = (float)num("k1");
+    p->k2 = (float)num("k2");
+    p->p1 = (float)num("p1");
+    p->p2 = (float)num("p2");
+    p->k3 = (float)num("k3");
+    p->baseline = (float)num("baseline");
+    p->img_width = integer("img_width");
+    p->img_height = integer("img_height");
+    p->near_plane_distance = (float)num("near_plane_distance");
+    p->far_plane_distance = (float)num("far_plane_distance");
+    p->triangulation_ratio_test_threshold = (float)num("triangulation_ratio_test_threshold");
+    p->tracking_ratio_test_threshold = (float)num("tracking_ratio_test_threshold");
+    p->min_num_matches_for_tracking = integer("min_num_matches_for_tracking");
+    p->tracking_radius = integer("tracking_radius");
+    p->agast_threshold = integer("agast_threshold");
+    p->untracked_threshold = integer("untracked_threshold");
+    p->staged_threshold = integer("staged_threshold");
+    p->descriptor_matching_threshold = (float)num("descriptor_matching_threshold");
+    p->detection_cell_size = integer("detection_cell_size");
+    p->max_keypoints_per_cell = integer("max_keypoints_per_cell");
+    p->enable_logging = integer("enable_logging") != 0;
+    p->enable_visualization = integer("enable_visualization") != 0;
+    p->triangulation_policy = integer("triangulation_policy");
+    p->viewer_camera_size = (float)num("viewer_camera_size");
+    p->viewer_point_size = integer("viewer_point_size");
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_pool_map(CUtensorMap *map, const ImagePool &pool, int box_w, int box_h)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode)
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LVT_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+        {
+            set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available");
+            return LVTK_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)pool.cols, (cuuint64_t)pool.rows, (cuuint64_t)pool.n_slots};
+    const cuuint64_t gstride[2] = {(cuuint64_t)pool.pitch, (cuuint64_t)pool.pitch * pool.rows};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pool.data, gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+    {
+        set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled failed");
+        return LVTK_ERR_CUDA;
+    }
+    return LVTK_OK;
+}
+
+int make_image_pool(ImagePool *pool, DeviceArena &arena, int rows, int cols, int n_slots)
+{
+    pool->rows = rows;
+    pool->cols = cols;
+    pool->pitch = (cols + 127) / 128 * 128;
+    pool->n_slots = n_slots;
+    if (int rc = arena.alloc(&pool->data, pool->slot_bytes() * n_slots))
+        return rc;
+    if (int rc = encode_pool_map(&pool->tmap_score, *pool, kScoreBoxW, kScoreBoxH))
+        return rc;
+    return encode_pool_map(&pool->tmap_patch, *pool, kPatchW, kPatchH);
+}
+
+TileGrid make_tile_grid(int img_w, int img_h, int cell)
+{
+    TileGrid g;
+    g.cell = cell;
+    g.img_w = img_w;
+    g.img_h = img_h;
+    g.ny = 1 + ((img_h - 1) / cell);
+    g.nx = 1 + ((img_w - 1) / cell);
+    return g;
+}
+
+int make_detect_workspace(DetectWorkspace *ws, DeviceArena &arena, const TileGrid &grid, int rows, int pitch, int batch)
+{
+    ws->batch = batch;
+    ws->n_tiles = grid.count();
+    const long tw = std::min(grid.cell, grid.img_w), th = std::min(grid.cell, grid.img_h);
+    long cap = 1;
+    while (cap < (tw * th) / 2 + 2)
+        cap <<= 1; // no two survivors are 4-adjacent: at most half the pixels, rounded to a power of two
+    ws->tile_cap = (int)cap;
+    const size_t nt = (size_t)batch * ws->n_tiles;
+    int rc = arena.alloc(&ws->score, (size_t)batch * rows * pitch);
+    rc = rc ? rc : arena.alloc(&ws->parent, (size_t)batch * rows * pitch);
+    rc = rc ? rc : arena.alloc(&ws->tile_list, nt * cap);
+    rc = rc ? rc : arena.alloc(&ws->tile_aux, nt * cap * 2);
+    rc = rc ? rc : arena.alloc(&ws->tile_out, nt * cap);
+    rc = rc ? rc : arena.alloc(&ws->tile_count, nt);
+    rc = rc ? rc : arena.alloc(&ws->tile_overflow, nt);
+    rc = rc ? rc : arena.alloc(&ws->tile_out_count, nt);
+    rc = rc ? rc : arena.alloc(&ws->retry, (size_t)batch);
+    rc = rc ? rc : arena.alloc(&ws->error, 1);
+    return rc;
+}
+
+int make_feat(FeatDev *f, DeviceArena &arena, int cap, int n_cells, int rows)
+{
+    f->cap = cap;
+    int rc = arena.alloc(&f->n, 1);
+    rc = rc ? rc : arena.alloc(&f->xy, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&f->resp, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&f->desc, (size_t)cap * 8);
+    rc = rc ? rc : arena.alloc(&f->matched, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&f->depth, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&f->cell_start, (size_t)n_cells + 1);
+    rc = rc ? rc : arena.alloc(&f->cell_items, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&f->row_start, (size_t)rows + 2);
+    rc = rc ? rc : arena.alloc(&f->row_items, (size_t)cap);
+    return rc;
+}
+
+int make_points(PointStore *p, DeviceArena &arena, int cap)
+{
+    p->cap = cap;
+    int rc = arena.alloc(&p->xyz, (size_t)cap * 3);
+    rc = rc ? rc : arena.alloc(&p->desc, (size_t)cap * 8);
+    rc = rc ? rc : arena.alloc(&p->counter, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&p->age, (size_t)cap);
+    rc = rc ? rc : arena.alloc(&p->match_idx, (size_t)cap);
+    return rc;
+}
+
+// cv::undistortPoints for one point (host; image bounds only, lvt/src/lvt_local_map.cpp:95-122)
+static void undistort_host(const lvt_params_c &p, float u, float v, float *ou, float *ov)
+{
+    const double fx = p.fx, fy = p.fy, cx = p.cx, cy = p.cy;
+    double x = ((double)u - cx) / fx, y = ((double)v - cy) / fy;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++)
+    {
+        const double r2 = x * x + y * y;
+        const double icdist = 1.0 / (1 + (((double)p.k3 * r2 + (double)p.k2) * r2 + (double)p.k1) * r2);
+        const double dX = 2 * (double)p.p1 * x * y + (double)p.p2 * (r2 + 2 * x * x);
+        const double dY = (double)p.p1 * (r2 + 2 * y * y) + 2 * (double)p.p2 * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    *ou = (float)(x * fx + cx);
+    *ov = (float)(y * fy + cy);
+}
+
+CamParams make_cam_params(const lvt_params_c &p)
+{
+    CamParams c;
+    c.fx = p.fx;
+    c.fy = p.fy;
+    c.cx = p.cx;
+    c.cy = p.cy;
+    c.baseline = p.baseline;
+    c.near_plane = p.near_plane_distance;
+    c.far_plane = p.far_plane_distance;
+    if (std::fabs((double)p.k1) < 1e-5)
+    {
+        c.min_x = 0.0f;
+        c.max_x = (float)p.img_width;
+        c.min_y = 0.0f;
+        c.max_y = (float)p.img_height;
+    }
+    else
+    {
+        float x[4], y[4];
+        undistort_host(p, 0.0f, 0.0f, &x[0], &y[0]);
+        undistort_host(p, (float)p.img_width, 0.0f, &x[1], &y[1]);
+        undistort_host(p, 0.0f, (float)p.img_height, &x[2], &y[2]);
+        undistort_host(p, (float)p.img_width, (float)p.img_height, &x[3], &y[3]);
+        c.min_x = std::min(x[0], x[2]);
+        c.max_x = std::max(x[1], x[3]);
+        c.min_y = std::min(y[0], y[1]);
+        c.max_y = std::max(y[2], y[3]);
+    }
+    c.img_w = p.img_width;
+    c.img_h = p.img_height;
+    const float k_cell = (float)kHashCell;
+    c.cells_x = (int)std::ceil(p.img_width / k_cell);
+    c.cells_y = (int)std::ceil(p.img_height / k_cell);
+    c.tracking_radius = p.tracking_radius;
+    c.cell_search_radius = (p.tracking_radius == kHashCell) ? 1 : (int)std::ceil((float)p.tracking_radius / k_cell);
+    c.tracking_ratio_th = p.tracking_ratio_test_threshold;
+    c.triangulation_ratio_th = p.triangulation_ratio_test_threshold;
+    c.desc_dist_th = p.descriptor_matching_threshold;
+    return c;
+}
+
+static bool g_pairs_uploaded = false;
+static signed char g_pairs[256][4];
+static bool g_pairs_custom = false;
+
+} // namespace lvtb
+
+using namespace lvtb;
+
+// ---------------------------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------------------------
+struct lvtk_ctx
+{
+    lvt_params_c params;
+    CamParams cam;
+    TrackParams tp;
+    DetectParams dp;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DeviceArena arena;
+    ImagePool pool;
+    DetectWorkspace ws;
+    int fcap = 0, pcap = 0;
+    FeatDev feats_h[2];
+    FeatDev *feats_d = nullptr;
+    int *d_slots = nullptr;
+    uint8_t *h_stage = nullptr; // pinned, 2 tightly packed images
+    float *d_depth = nullptr, *h_depth = nullptr;
+    // seam inputs
+    float2 *d_in_xy = nullptr;
+    float *d_in_resp = nullptr;
+    int *d_in_n = nullptr;
+    int *d_int_a = nullptr, *d_int_b = nullptr; // [pcap] generic int outputs
+    float *d_f_a = nullptr, *d_f_b = nullptr;   // [pcap]
+    PoseD *d_pose_out = nullptr;
+    // tracking
+    TrackState *d_state = nullptr;
+    FrameResult *d_result = nullptr, *h_result = nullptr;
+    PointStore map, staged;
+    TrackScratch sc;
+};
+
+static int ctx_check_error(lvtk_ctx *c)
+{
+    int e = 0;
+    LVT_CUDA_TRY(cudaMemcpyAsync(&e, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (e)
+    {
+        int z = 0;
+        cudaMemcpy(c->ws.error, &z, sizeof(int), cudaMemcpyHostToDevice);
+        set_last_error(__FILE__, __LINE__, "device-side capacity error");
+    }
+    return e;
+}
+
+static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        set_last_error(__FILE__, __LINE__, "no CUDA device");
+        return LVTK_ERR_NO_DEVICE;
+    }
+    if (p.img_width <= 0 || p.img_height <= 0 || p.img_width > 4095 || p.img_height > 4095 || p.detection_cell_size <= 0 ||
+        p.max_keypoints_per_cell <= 0 || p.tracking_radius <= 0 || p.agast_threshold <= 0 || p.agast_threshold > 254)
+    {
+        set_last_error(__FILE__, __LINE__, "parameters out of range");
+        return LVTK_ERR_ARG;
+    }
+    if (device >= 0)
+        LVT_CUDA_TRY(cudaSetDevice(device));
+    LVT_CUDA_TRY(cudaGetDevice(&c->device));
+    c->params = p;
+    c->cam = make_cam_params(p);
+    if (c->cam.cells_x * c->cam.cells_y + p.img_height + 3 > 12000)
+    {
+        set_last_error(__FILE__, __LINE__, "image too large for the shared-memory hash grid");
+        return LVTK_ERR_ARG;
+    }
+    c->tp.cam = c->cam;
+    c->tp.sensor = 1;
+    c->tp.min_matches = p.min_num_matches_for_tracking;
+    c->tp.untracked_threshold = p.untracked_threshold;
+    c->tp.staged_threshold = p.staged_threshold;
+    c->tp.triangulation_policy = p.triangulation_policy;
+    LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
+        return rc;
+    c->dp.grid = make_tile_grid(p.img_width, p.img_height, p.detection_cell_size);
+    c->dp.threshold = p.agast_threshold;
+    c->dp.threshold_low = (int)((double)p.agast_threshold * 0.5 + 0.5);
+    c->dp.max_per_cell = p.max_keypoints_per_cell;
+    c->dp.pitch = c->pool.pitch;
+    c->dp.rows = p.img_height;
+    c->dp.cols = p.img_width;
+    if (c->dp.grid.count() > 1024)
+    {
+        set_last_error(__FILE__, __LINE__, "more than 1024 detection tiles");
+        return LVTK_ERR_ARG;
+    }
+    if (int rc = make_detect_workspace(&c->ws, c->arena, c->dp.grid, p.img_height, c->pool.pitch, 2))
+        return rc;
+
+    // capacities: ANMS keeps >= k+1 per tile (ties add a few); 2x headroom, at least 4096
+    long want = 2L * c->dp.grid.count() * (p.max_keypoints_per_cell + 1);
+    long fcap = 4096;
+    while (fcap < want)
+        fcap <<= 1;
+    if (fcap > 24576)
+        fcap = 24576; // two owner arrays must fit in 227 KB of shared memory
+    c->fcap = (int)fcap;
+    c->pcap = std::max(32768, 8 * c->fcap);
+    const int n_cells = c->cam.cells_x * c->cam.cells_y;
+    for (int i = 0; i < 2; i++)
+        if (int rc = make_feat(&c->feats_h[i], c->arena, c->fcap, n_cells, p.img_height))
+            return rc;
+    int rc = c->arena.alloc(&c->feats_d, 2);
+    rc = rc ? rc : c->arena.alloc(&c->d_slots, 2);
+    rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)p.img_width * p.img_height);
+    rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_in_resp, (size_t)2 * c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_in_n, 2);
+    rc = rc ? rc : c->arena.alloc(&c->d_int_a, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_int_b, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_f_a, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_f_b, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_pose_out, 1);
+    rc = rc ? rc : c->arena.alloc(&c->d_state, 1);
+    rc = rc ? rc : c->arena.alloc(&c->d_result, 1);
+    rc = rc ? rc : make_points(&c->map, c->arena, c->pcap);
+    rc = rc ? rc : make_points(&c->staged, c->arena, c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.ms.proj, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.ms.vis, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.ms.choice, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.sol_xyz, (size_t)c->pcap * 3);
+    rc = rc ? rc : c->arena.alloc(&c->sc.sol_uv, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.level, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.inlier, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.e2, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.row_choice, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.pair_query, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.pair_train, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.tri_xyz, (size_t)c->pcap * 3);
+    rc = rc ? rc : c->arena.alloc(&c->sc.tri_ok, (size_t)c->pcap);
+    if (rc)
+        return rc;
+    LVT_CUDA_TRY(cudaMemcpy(c->feats_d, c->feats_h, sizeof(c->feats_h), cudaMemcpyHostToDevice));
+    const int slots[2] = {0, 1};
+    LVT_CUDA_TRY(cudaMemcpy(c->d_slots, slots, sizeof(slots), cudaMemcpyHostToDevice));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_stage, (size_t)2 * p.img_width * p.img_height));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_depth, sizeof(float) * (size_t)p.img_width * p.img_height));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_result, sizeof(FrameResult)));
+    if (!g_pairs_uploaded)
+    {
+        if (int r2 = upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr))
+            return r2;
+        g_pairs_uploaded = true;
+    }
+    LVT_CUDA_TRY(cudaDeviceSynchronize()); // the arena's memsets ran on the default stream
+    if (int r3 = launch_reset_state(c->d_state, c->stream))
+        return r3;
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LVTK_OK;
+}
+
+static void ctx_free(lvtk_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+    {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    c->arena.release();
+    if (c->h_stage)
+        cudaFreeHost(c->h_stage);
+    if (c->h_depth)
+        cudaFreeHost(c->h_depth);
+    if (c->h_result)
+        cudaFreeHost(c->h_result);
+    delete c;
+}
+
+// host image (any stride) -> pinned staging -> pitched pool slot
+static int ctx_upload_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows, int cols, int stride)
+{
+    uint8_t *stage = c->h_stage + (size_t)slot * rows * cols;
+    if (stride == cols)
+        std::memcpy(stage, img, (size_t)rows * cols);
+    else
+        for (int y = 0; y < rows; y++)
+            std::memcpy(stage + (size_t)y * cols, img + (size_t)y * stride, cols);
+    LVT_CUDA_TRY(cudaMemcpy2DAsync(c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, stage, cols, cols, rows,
+                                   cudaMemcpyHostToDevice, c->stream));
+    return LVTK_OK;
+}
+
+static int ctx_download_features(lvtk_ctx *c, int which, lvtk_keypoint *out_kps, uint8_t *out_desc, int cap, int *n_out)
+{
+    const FeatDev &f = c->feats_h[which];
+    int n = 0;
+    LVT_CUDA_TRY(cudaMemcpyAsync(&n, f.n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    if (n > cap)
+        return LVTK_ERR_CAPACITY;
+    if (n == 0)
+        return LVTK_OK;
+    std::vector<float2> xy(n);
+    std::vector<float> resp(n);
+    LVT_CUDA_TRY(cudaMemcpyAsync(xy.data(), f.xy, sizeof(float2) * n, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaMemcpyAsync(resp.data(), f.resp, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_desc)
+        LVT_CUDA_TRY(cudaMemcpyAsync(out_desc, f.desc, (size_t)32 * n, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (out_kps)
+        for (int i = 0; i < n; i++)
+            out_kps[i] = lvtk_keypoint{xy[i].x, xy[i].y, resp[i]};
+    return LVTK_OK;
+}
+
+// keypoints + descriptors + marks of a seam call -> feature set `which`, indexed
+static int ctx_upload_features(lvtk_ctx *c, int which, const lvtk_keypoint *kps, const uint8_t *desc, int n,
+                               const uint8_t *marks)
+{
+    if (n > c->fcap)
+        return LVTK_ERR_CAPACITY;
+    const FeatDev &f = c->feats_h[which];
+    std::vector<float2> xy(n);
+    std::vector<float> resp(n);
+    for (int i = 0; i < n; i++)
+    {
+        xy[i] = make_float2(kps[i].x, kps[i].y);
+        resp[i] = kps[i].response;
+    }
+    LVT_CUDA_TRY(cudaMemcpyAsync(f.n, &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (n)
+    {
+        LVT_CUDA_TRY(cudaMemcpyAsync(f.xy, xy.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(f.resp, resp.data(), sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(f.desc, desc, (size_t)32 * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+    if (int rc = launch_index(c->feats_d + which, 1, c->cam, c->stream))
+        return rc;
+    if (marks && n)
+        LVT_CUDA_TRY(cudaMemcpyAsync(f.matched, marks, n, cudaMemcpyHostToDevice, c->stream));
+    return LVTK_OK;
+}
+
+static PoseD make_pose(const double q[4], const double t[3])
+{
+    PoseD p;
+    p.q = Quat{q[0], q[1], q[2], q[3]};
+    p.t[0] = t[0];
+    p.t[1] = t[1];
+    p.t[2] = t[2];
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lvt_system mirror
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+struct System
+{
+    lvtk_ctx *ctx = nullptr;
+    int sensor = 1;
+    int state = 1;
+    int frame_number = 0;
+    PoseD last_pose;
+    lvt_frame_info info;
+
+    System()
+    {
+        last_pose.q = Quat{1, 0, 0, 0};
+        last_pose.t[0] = last_pose.t[1] = last_pose.t[2] = 0;
+        std::memset(&info, 0, sizeof(info));
+        info.state = 1;
+    }
+
+    // the LOST short-circuit of lvt_system::track (lvt/src/lvt_system.cpp:159-166)
+    bool lost_shortcut(PoseD *out)
+    {
+        frame_number++;
+        if (state != 3)
+            return false;
+        std::memset(&info, 0, sizeof(info));
+        info.frame_number = frame_number;
+        info.state = 3;
+        *out = last_pose;
+        return true;
+    }
+
+    // features of this frame are in ctx->feats[0..1]: run perform_tracking on the device
+    int run_tracking(PoseD *out)
+    {
+        lvtk_ctx *c = ctx;
+        if (int rc = launch_index(c->feats_d, sensor == 1 ? 2 : 1, c->cam, c->stream))
+            return rc;
+        if (int rc = launch_track_frame(c->d_state, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc, c->fcap,
+                                        c->stream))
+            return rc;
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, c->stream));
+        LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (int e = ctx_check_error(c))
+            return e;
+        info = c->h_result->info;
+        info.frame_number = frame_number;
+        state = info.state;
+        *out = c->h_result->pose;
+        return LVTK_OK;
+    }
+
+    int track_stereo(const uint8_t *left, const uint8_t *right, int rows, int cols, PoseD *out)
+    {
+        lvtk_ctx *c = ctx;
+        if (rows != c->params.img_height || cols != c->params.img_width)
+            return LVTK_ERR_ARG;
+        if (lost_shortcut(out))
+            return LVTK_OK;
+        if (int rc = ctx_upload_image(c, 0, left, rows, cols, cols))
+            return rc;
+        if (int rc = ctx_upload_image(c, 1, right, rows, cols, cols))
+            return rc;
+        if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 2, c->feats_d, kBriefBorder, 1, c->stream))
+            return rc;
+        if (int rc = launch_brief(c->pool, c->d_slots, 2, c->feats_d, c->stream))
+            return rc;
+        return finish(out);
+    }
+
+    int track_external(const uint8_t *left, const uint8_t *right, int rows, int cols, const double (*cl)[2], int nl,
+                       const double (*cr)[2], int nr, PoseD *out)
+    {
+        lvtk_ctx *c = ctx;
+        if (rows != c->params.img_height || cols != c->params.img_width || nl < 0 || nr < 0)
+            return LVTK_ERR_ARG;
+        if (nl > c->pcap || nr > c->pcap)
+            return LVTK_ERR_CAPACITY;
+        if (lost_shortcut(out))
+            return LVTK_OK;
+        if (int rc = ctx_upload_image(c, 0, left, rows, cols, cols))
+            return rc;
+        if (int rc = ctx_upload_image(c, 1, right, rows, cols, cols))
+            return rc;
+        std::vector<float2> xy((size_t)2 * c->pcap);
+        for (int i = 0; i < nl; i++)
+            xy[i] = make_float2((float)cl[i][0], (float)cl[i][1]);
+        for (int i = 0; i < nr; i++)
+            xy[c->pcap + i] = make_float2((float)cr[i][0], (float)cr[i][1]);
+        const int n_in[2] = {nl, nr};
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_xy, xy.data(), sizeof(float2) * xy.size(), cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_n, n_in, sizeof(n_in), cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (int rc = launch_border_filter(c->d_in_xy, nullptr, c->d_in_n, c->pcap, c->feats_d, 2, rows, cols, c->ws.error,
+                                          c->stream))
+            return rc;
+        if (int rc = launch_brief(c->pool, c->d_slots, 2, c->feats_d, c->stream))
+            return rc;
+        return finish(out);
+    }
+
+    int track_rgbd(const uint8_t *gray, const float *depth, int rows, int cols, PoseD *out)
+    {
+        lvtk_ctx *c = ctx;
+        if (rows != c->params.img_height || cols != c->params.img_width)
+            return LVTK_ERR_ARG;
+        if (lost_shortcut(out))
+            return LVTK_OK;
+        if (int rc = ctx_upload_image(c, 0, gray, rows, cols, cols))
+            return rc;
+        std::memcpy(c->h_depth, depth, sizeof(float) * (size_t)rows * cols);
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->d_depth, c->h_depth, sizeof(float) * (size_t)rows * cols, cudaMemcpyHostToDevice,
+                                     c->stream));
+        if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, c->stream))
+            return rc;
+        if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
+            return rc;
+        if (int rc = launch_depth_gate(c->feats_h[0], c->d_depth, c->params, c->stream))
+            return rc;
+        return finish(out);
+    }
+
+    int finish(PoseD *out)
+    {
+        const bool first_frame = state == 1;
+        PoseD pose;
+        if (int rc = run_tracking(&pose))
+            return rc;
+        if (!first_frame && state == 2)
+            last_pose = pose; // m_last_pose = computed_pose (lvt_system.cpp:205); not on the first frame
+        *out = pose;
+        return LVTK_OK;
+    }
+};
+
+void write_pose(const PoseD &pose, double R[3][3], double t[3])
+{
+    double m[9];
+    quat_to_mat(pose.q, m);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            R[i][j] = m[3 * i + j];
+    t[0] = pose.t[0];
+    t[1] = pose.t[1];
+    t[2] = pose.t[2];
+}
+} // namespace
+
+extern "C"
+{
+
+// ---- reference ABI (lvt/src/lvt_c.cpp:33-148) -------------------------------------------------
+LVT_API lvt_handle lvt_create_from_params(const lvt_params_c *p, int sensor_type)
+{
+    if (!p || !(sensor_type == 1 || sensor_type == 2))
+        return nullptr;
+    System *vo = new System();
+    vo->sensor = sensor_type;
+    vo->ctx = new lvtk_ctx();
+    if (ctx_build(vo->ctx, *p, -1, 2) != LVTK_OK)
+    {
+        ctx_free(vo->ctx);
+        delete vo;
+        return nullptr;
+    }
+    vo->ctx->tp.sensor = sensor_type;
+    return vo;
+}
+
+LVT_API lvt_handle lvt_create(const char *config_file_name, int sensor_type)
+{
+    lvt_params_c p;
+    if (!params_from_file(&p, config_file_name))
+        return nullptr;
+    return lvt_create_from_params(&p, sensor_type);
+}
+
+LVT_API void lvt_destroy(lvt_handle h)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return;
+    ctx_free(vo->ctx);
+    delete vo;
+}
+
+LVT_API void lvt_reset(lvt_handle h)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return;
+    cudaSetDevice(vo->ctx->device);
+    launch_reset_state(vo->ctx->d_state, vo->ctx->stream);
+    cudaStreamSynchronize(vo->ctx->stream);
+    lvtk_ctx *c = vo->ctx;
+    const int sensor = vo->sensor;
+    *vo = System();
+    vo->ctx = c;
+    vo->sensor = sensor;
+}
+
+LVT_API void lvt_track(lvt_handle h, unsigned char *left, unsigned char *right, int n_rows, int n_cols, double R[3][3],
+                       double t[3])
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || !left || !right)
+        return;
+    cudaSetDevice(vo->ctx->device);
+    PoseD pose;
+    if (vo->track_stereo(left, right, n_rows, n_cols, &pose) == LVTK_OK)
+        write_pose(pose, R, t);
+}
+
+LVT_API void lvt_track_rgbd(lvt_handle h, const unsigned char *gray, const float *depth_m, int n_rows, int n_cols,
+                            double R[3][3], double t[3])
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || !gray || !depth_m)
+        return;
+    cudaSetDevice(vo->ctx->device);
+    PoseD pose;
+    if (vo->track_rgbd(gray, depth_m, n_rows, n_cols, &pose) == LVTK_OK)
+        write_pose(pose, R, t);
+}
+
+LVT_API void lvt_track_with_external_corners(lvt_handle h, unsigned char *left, unsigned char *right, int n_rows,
+                                             int n_cols, double corners_left[][2], int n_left,
+                                             double corners_right[][2], int n_right, double R[3][3], double t[3])
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || !left || !right)
+        return;
+    cudaSetDevice(vo->ctx->device);
+    PoseD pose;
+    if (vo->track_external(left, right, n_rows, n_cols, corners_left, n_left, corners_right, n_right, &pose) == LVTK_OK)
+        write_pose(pose, R, t);
+}
+
+LVT_API int lvt_get_status(lvt_handle h)
+{
+    System *vo = static_cast<System *>(h);
+    return vo ? vo->state : -1;
+}
+
+// ---- extensions --------------------------------------------------------------------------------
+LVT_API void lvt_params_default(lvt_params_c *p) { params_default(p); }
+LVT_API int lvt_params_from_file(lvt_params_c *p, const char *f) { return params_from_file(p, f); }
+
+LVT_API int lvt_get_frame_info(lvt_handle h, lvt_frame_info *out)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || !out)
+        return -1;
+    *out = vo->info;
+    return 0;
+}
+
+LVT_API int lvt_get_last_pose(lvt_handle h, double q[4], double t[3])
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return -1;
+    q[0] = vo->last_pose.q.w;
+    q[1] = vo->last_pose.q.x;
+    q[2] = vo->last_pose.q.y;
+    q[3] = vo->last_pose.q.z;
+    t[0] = vo->last_pose.t[0];
+    t[1] = vo->last_pose.t[1];
+    t[2] = vo->last_pose.t[2];
+    return 0;
+}
+
+LVT_API int lvt_debug_get_features(lvt_handle h, int which, float *kps_xy, unsigned char *desc, int cap)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || which < 0 || which > 1)
+        return -1;
+    lvtk_ctx *c = vo->ctx;
+    cudaSetDevice(c->device);
+    const FeatDev &f = c->feats_h[which];
+    int n = 0;
+    if (cudaMemcpy(&n, f.n, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    if (vo->frame_number == 0 || (which == 1 && vo->sensor != 1))
+        n = 0;
+    const int m = std::min(n, cap);
+    if (m > 0 && kps_xy)
+        cudaMemcpy(kps_xy, f.xy, sizeof(float2) * m, cudaMemcpyDeviceToHost);
+    if (m > 0 && desc)
+        cudaMemcpy(desc, f.desc, (size_t)32 * m, cudaMemcpyDeviceToHost);
+    return n;
+}
+
+LVT_API int lvt_debug_get_points(lvt_handle h, int which, double *xyz, unsigned char *desc, int *counters, int *ages,
+                                 int *match_idx, int cap)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || which < 0 || which > 1)
+        return -1;
+    lvtk_ctx *c = vo->ctx;
+    cudaSetDevice(c->device);
+    TrackState st;
+    if (cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    const PointStore &p = which ? c->staged : c->map;
+    const int n = which ? st.staged_n : st.map_n;
+    const int m = std::min(n, cap);
+    if (m > 0)
+    {
+        if (xyz)
+            cudaMemcpy(xyz, p.xyz, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost);
+        if (desc)
+            cudaMemcpy(desc, p.desc, (size_t)32 * m, cudaMemcpyDeviceToHost);
+        if (counters)
+            cudaMemcpy(counters, p.counter, sizeof(int) * m, cudaMemcpyDeviceToHost);
+        if (ages)
+            cudaMemcpy(ages, p.age, sizeof(int) * m, cudaMemcpyDeviceToHost);
+        if (match_idx)
+            cudaMemcpy(match_idx, p.match_idx, sizeof(int) * m, cudaMemcpyDeviceToHost);
+    }
+    return n;
+}
+
+LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
+{
+    if (pairs)
+    {
+        for (int i = 0; i < 256; i++)
+            for (int j = 0; j < 4; j++)
+                if (pairs[i][j] < -24 || pairs[i][j] > 24)
+                    return -1;
+        std::memcpy(g_pairs, pairs, sizeof(g_pairs));
+    }
+    g_pairs_custom = pairs != nullptr;
+    if (g_pairs_uploaded) // a device is already in use: refresh its table
+        return upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr);
+    return 0;
+}
+
+LVT_API const char *lvtk_last_error(void) { return last_error(); }
+
+// ---- seam ABI (include/lvt_kernels.h) ------------------------------------------------------------
+LVT_API lvtk_ctx *lvtk_ctx_create(const lvt_params_c *p, int device)
+{
+    if (!p)
+        return nullptr;
+    lvtk_ctx *c = new lvtk_ctx();
+    if (ctx_build(c, *p, device, 2) != LVTK_OK)
+    {
+        ctx_free(c);
+        return nullptr;
+    }
+    return c;
+}
+LVT_API void lvtk_ctx_destroy(lvtk_ctx *c) { ctx_free(c); }
+LVT_API int lvtk_is_gpu(void) { return 1; }
+
+LVT_API int lvtk_agast(lvtk_ctx *ctx, const uint8_t *img, int rows, int cols, int stride, int threshold, int nonmax,
+                       lvtk_keypoint *out, int cap, int *n_out)
+{
+    if (!ctx || !img || !n_out || rows <= 0 || cols <= 0 || stride < cols || threshold <= 0 || threshold > 254 ||
+        rows > 4095 || cols > 4095)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    // one image == one tile of arbitrary size: a throw-away pool / workspace of that shape
+    DeviceArena arena;
+    ImagePool pool;
+    DetectWorkspace ws;
+    FeatDev f, *d_f = nullptr;
+    int *d_slot = nullptr;
+    DetectParams dp;
+    dp.grid = make_tile_grid(cols, rows, std::max(rows, cols));
+    dp.threshold = dp.threshold_low = threshold;
+    dp.max_per_cell = 0x7FFFFFFF;
+    int rc = make_image_pool(&pool, arena, rows, cols, 1);
+    dp.pitch = pool.pitch;
+    dp.rows = rows;
+    dp.cols = cols;
+    rc = rc ? rc : make_detect_workspace(&ws, arena, dp.grid, rows, pool.pitch, 1);
+    rc = rc ? rc : make_feat(&f, arena, std::max(cap, 1), 1, rows);
+    rc = rc ? rc : arena.alloc(&d_f, 1);
+    rc = rc ? rc : arena.alloc(&d_slot, 1);
+    auto body = [&]() -> int {
+        if (rc)
+            return rc;
+        LVT_CUDA_TRY(cudaMemcpy(d_f, &f, sizeof(f), cudaMemcpyHostToDevice));
+        LVT_CUDA_TRY(cudaDeviceSynchronize());
+        LVT_CUDA_TRY(cudaMemcpy2D(pool.data, pool.pitch, img, stride, cols, rows, cudaMemcpyHostToDevice));
+        if (int r = launch_detect(pool, ws, dp, d_slot, 1, d_f, 0, nonmax ? 1 : 0, ctx->stream))
+            return r;
+        LVT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        int n = 0, err = 0;
+        LVT_CUDA_TRY(cudaMemcpy(&n, f.n, sizeof(int), cudaMemcpyDeviceToHost));
+        LVT_CUDA_TRY(cudaMemcpy(&err, ws.error, sizeof(int), cudaMemcpyDeviceToHost));
+        *n_out = n;
+        if (err)
+            return err;
+        std::vector<float2> xy(std::max(n, 1));
+        std::vector<float> resp(std::max(n, 1));
+        if (n)
+        {
+            LVT_CUDA_TRY(cudaMemcpy(xy.data(), f.xy, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+            LVT_CUDA_TRY(cudaMemcpy(resp.data(), f.resp, sizeof(float) * n, cudaMemcpyDeviceToHost));
+        }
+        for (int i = 0; i < n; i++)
+            out[i] = lvtk_keypoint{xy[i].x, xy[i].y, resp[i]};
+        return LVTK_OK;
+    };
+    rc = body();
+    arena.release();
+    return rc;
+}
+
+LVT_API int lvtk_detect(lvtk_ctx *c, const uint8_t *img, int rows, int cols, int stride, lvtk_keypoint *out, int cap,
+                        int *n_out)
+{
+    if (!c || !img || !n_out || rows != c->params.img_height || cols != c->params.img_width || stride < cols)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = ctx_upload_image(c, 0, img, rows, cols, stride))
+        return rc;
+    if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 1, c->feats_d, 0, 1, c->stream))
+        return rc;
+    if (int e = ctx_check_error(c))
+        return e;
+    return ctx_download_features(c, 0, out, nullptr, cap, n_out);
+}
+
+LVT_API int lvtk_brief(lvtk_ctx *c, const uint8_t *img, int rows, int cols, int stride, const lvtk_keypoint *in,
+                       int n_in, lvtk_keypoint *out_kps, uint8_t *out_desc, int *n_out)
+{
+    if (!c || !img || !n_out || n_in < 0 || rows != c->params.img_height || cols != c->params.img_width || stride < cols)
+        return LVTK_ERR_ARG;
+    if (n_in > c->fcap)
+        return LVTK_ERR_CAPACITY;
+    cudaSetDevice(c->device);
+    if (int rc = ctx_upload_image(c, 0, img, rows, cols, stride))
+        return rc;
+    std::vector<float2> xy(std::max(n_in, 1));
+    std::vector<float> resp(std::max(n_in, 1));
+    for (int i = 0; i < n_in; i++)
+    {
+        xy[i] = make_float2(in[i].x, in[i].y);
+        resp[i] = in[i].response;
+    }
+    LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_xy, xy.data(), sizeof(float2) * std::max(n_in, 1), cudaMemcpyHostToDevice, c->stream));
+    LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_resp, resp.data(), sizeof(float) * std::max(n_in, 1), cudaMemcpyHostToDevice, c->stream));
+    LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_n, &n_in, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (int rc = launch_border_filter(c->d_in_xy, c->d_in_resp, c->d_in_n, c->pcap, c->feats_d, 1, rows, cols, c->ws.error,
+                                      c->stream))
+        return rc;
+    if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
+        return rc;
+    if (int e = ctx_check_error(c))
+        return e;
+    return ctx_download_features(c, 0, out_kps, out_desc, n_in, n_out);
+}
+
+LVT_API int lvtk_extract(lvtk_ctx *c, const uint8_t *img, int rows, int cols, int stride, lvtk_keypoint *out_kps,
+                         uint8_t *out_desc, int cap, int *n_out)
+{
+    if (!c || !img || !n_out || rows != c->params.img_height || cols != c->params.img_width || stride < cols)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = ctx_upload_image(c, 0, img, rows, cols, stride))
+        return rc;
+    if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, c->stream))
+        return rc;
+    if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
+        return rc;
+    if (int e = ctx_check_error(c))
+        return e;
+    return ctx_download_features(c, 0, out_kps, out_desc, cap, n_out);
+}
+
+LVT_API int lvtk_match_projected(lvtk_ctx *c, const double *pts_xyz, const uint8_t *pts_desc, int m, const double q[4],
+                                 const double t[3], const lvtk_keypoint *kps, const uint8_t *desc, int n,
+                                 uint8_t *matched_flags, int retry_below, int *out_match_idx, float *out_d1,
+                                 float *out_d2, int *out_count, int *retried)
+{
+    if (!c || m < 0 || n < 0 || !out_match_idx || !q || !t)
+        return LVTK_ERR_ARG;
+    if (m > c->pcap || n > c->fcap)
+        return LVTK_ERR_CAPACITY;
+    cudaSetDevice(c->device);
+    if (int rc = ctx_upload_features(c, 0, kps, desc, n, matched_flags))
+        return rc;
+    if (m)
+    {
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->map.xyz, pts_xyz, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->map.desc, pts_desc, (size_t)32 * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (int rc = launch_match_seam(c->map.xyz, c->map.desc, m, make_pose(q, t), c->feats_d, c->cam, retry_below, c->sc.ms,
+                                   c->d_int_a, c->d_f_a, c->d_f_b, c->d_int_b, c->fcap, c->stream))
+        return rc;
+    int cr[2] = {0, 0};
+    if (m)
+    {
+        LVT_CUDA_TRY(cudaMemcpyAsync(out_match_idx, c->d_int_a, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+        if (out_d1)
+            LVT_CUDA_TRY(cudaMemcpyAsync(out_d1, c->d_f_a, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+        if (out_d2)
+            LVT_CUDA_TRY(cudaMemcpyAsync(out_d2, c->d_f_b, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (matched_flags && n)
+        LVT_CUDA_TRY(cudaMemcpyAsync(matched_flags, c->feats_h[0].matched, n, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaMemcpyAsync(cr, c->d_int_b, sizeof(cr), cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (out_count)
+        *out_count = cr[0];
+    if (retried)
+        *retried = cr[1];
+    return LVTK_OK;
+}
+
+LVT_API int lvtk_row_match(lvtk_ctx *c, const lvtk_keypoint *kl, const uint8_t *dl, int nl, uint8_t *ml,
+                           const lvtk_keypoint *kr, const uint8_t *dr, int nr, uint8_t *mr, int *out_query,
+                           int *out_train, int *n_matches)
+{
+    if (!c || nl < 0 || nr < 0 || !n_matches)
+        return LVTK_ERR_ARG;
+    if (nl > c->fcap || nr > c->fcap)
+        return LVTK_ERR_CAPACITY;
+    cudaSetDevice(c->device);
+    if (int rc = ctx_upload_features(c, 0, kl, dl, nl, ml))
+        return rc;
+    if (int rc = ctx_upload_features(c, 1, kr, dr, nr, mr))
+        return rc;
+    if (int rc = launch_row_seam(c->feats_d, c->cam, c->sc.row_choice, c->sc.pair_query, c->sc.pair_train, c->d_int_b,
+                                 c->fcap, c->stream))
+        return rc;
+    int np = 0;
+    LVT_CUDA_TRY(cudaMemcpyAsync(&np, c->d_int_b, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_matches = np;
+    if (np)
+    {
+        LVT_CUDA_TRY(cudaMemcpyAsync(out_query, c->sc.pair_query, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(out_train, c->sc.pair_train, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (ml && nl)
+        LVT_CUDA_TRY(cudaMemcpyAsync(ml, c->feats_h[0].matched, nl, cudaMemcpyDeviceToHost, c->stream));
+    if (mr && nr)
+        LVT_CUDA_TRY(cudaMemcpyAsync(mr, c->feats_h[1].matched, nr, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LVTK_OK;
+}
+
+LVT_API int lvtk_solve_pose(lvtk_ctx *c, const double *pts_xyz, const float *uv, int m, const double q_in[4],
+                            const double t_in[3], double q_out[4], double t_out[3], uint8_t *inlier_marks)
+{
+    if (!c || m < 0 || !q_in || !t_in || !q_out || !t_out)
+        return LVTK_ERR_ARG;
+    if (m > c->pcap)
+        return LVTK_ERR_CAPACITY;
+    cudaSetDevice(c->device);
+    if (m)
+    {
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->sc.sol_xyz, pts_xyz, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->sc.sol_uv, uv, sizeof(float) * 2 * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (int rc = launch_pose_seam(c->sc.sol_xyz, c->sc.sol_uv, m, make_pose(q_in, t_in), c->cam, c->sc.level, c->sc.inlier,
+                                  c->sc.e2, c->d_pose_out, c->stream))
+        return rc;
+    PoseD out;
+    LVT_CUDA_TRY(cudaMemcpyAsync(&out, c->d_pose_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
+    if (inlier_marks && m)
+        LVT_CUDA_TRY(cudaMemcpyAsync(inlier_marks, c->sc.inlier, m, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    q_out[0] = out.q.w;
+    q_out[1] = out.q.x;
+    q_out[2] = out.q.y;
+    q_out[3] = out.q.z;
+    t_out[0] = out.t[0];
+    t_out[1] = out.t[1];
+    t_out[2] = out.t[2];
+    return LVTK_OK;
+}
+
+LVT_API int lvtk_triangulate(lvtk_ctx *c, const double q[4], const double t[3], const float *uv_left,
+                             const float *uv_right, int n, double *out_xyz, uint8_t *out_valid)
+{
+    if (!c || n < 0 || !q || !t)
+        return LVTK_ERR_ARG;
+    if (n > c->pcap)
+        return LVTK_ERR_CAPACITY;
+    if (n == 0)
+        return LVTK_OK;
+    cudaSetDevice(c->device);
+    LVT_CUDA_TRY(cudaMemcpyAsync(c->sc.sol_uv, uv_left, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    LVT_CUDA_TRY(cudaMemcpyAsync(c->sc.ms.proj, uv_right, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_tri_seam(make_pose(q, t), c->cam, c->sc.sol_uv, c->sc.ms.proj, n, c->sc.tri_xyz, c->sc.tri_ok,
+                                 c->stream))
+        return rc;
+    LVT_CUDA_TRY(cudaMemcpyAsync(out_xyz, c->sc.tri_xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaMemcpyAsync(out_valid, c->sc.tri_ok, n, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LVTK_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,62 @@
+// Host-side context of one sequence: device buffers, stream, tensor maps and the launch glue.
+#pragma once
+#include "track.cuh"
+#include <vector>
+
+namespace lvtb
+{
+
+int launch_border_filter(const float2 *src_xy, const float *src_resp, const int *src_n, int src_stride,
+                         const FeatDev *d_feats, int n_images, int rows, int cols, int *error, cudaStream_t stream);
+int launch_depth_gate(const FeatDev &f, const float *d_depth, const lvt_params_c &p, cudaStream_t stream);
+int launch_track_frame(TrackState *st, FrameResult *result, const PointStore &map, const PointStore &staged,
+                       const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, int owner_cap,
+                       cudaStream_t stream);
+int launch_reset_state(TrackState *st, cudaStream_t stream);
+int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const PoseD &pose, const FeatDev *d_feat,
+                      const CamParams &cam, int retry_below, const MatchScratch &ms, int *d_match_idx, float *d_d1,
+                      float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream);
+int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, int *d_choice, int *d_query, int *d_train, int *d_count,
+                    int owner_cap, cudaStream_t stream);
+int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD &init, const CamParams &cam,
+                     uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, cudaStream_t stream);
+int launch_tri_seam(const PoseD &pose, const CamParams &cam, const float2 *d_uvl, const float2 *d_uvr, int n,
+                    double *d_xyz, uint8_t *d_ok, cudaStream_t stream);
+
+// owns every cudaMalloc of a context; freed together
+struct DeviceArena
+{
+    std::vector<void *> blocks;
+    size_t total = 0;
+    template <class T>
+    int alloc(T **p, size_t count)
+    {
+        void *q = nullptr;
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        if (cudaMalloc(&q, bytes) != cudaSuccess)
+        {
+            set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+            return LVTK_ERR_CUDA;
+        }
+        cudaMemset(q, 0, bytes);
+        blocks.push_back(q);
+        total += bytes;
+        *p = static_cast<T *>(q);
+        return LVTK_OK;
+    }
+    void release()
+    {
+        for (void *q : blocks)
+            cudaFree(q);
+        blocks.clear();
+    }
+};
+
+int make_image_pool(ImagePool *pool, DeviceArena &arena, int rows, int cols, int n_slots);
+int make_detect_workspace(DetectWorkspace *ws, DeviceArena &arena, const TileGrid &grid, int rows, int pitch, int batch);
+int make_feat(FeatDev *f, DeviceArena &arena, int cap, int n_cells, int rows);
+int make_points(PointStore *p, DeviceArena &arena, int cap);
+CamParams make_cam_params(const lvt_params_c &p);
+TileGrid make_tile_grid(int img_w, int img_h, int cell);
+
+} // namespace lvtb

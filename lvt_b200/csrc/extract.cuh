@@ -1,0 +1,84 @@
+// Device-side data layout of the feature front end (detect -> NMS -> ANMS -> BRIEF -> index).
+#pragma once
+#include "common.cuh"
+
+namespace lvtb
+{
+
+// Pool of pitched 8-bit images in HBM: image i starts at data + i * pitch * rows.  One 3-D
+// tensor map (x, y, image) per box shape covers the whole pool, so a kernel addresses any
+// resident frame by its slot index.  pitch is a multiple of 128 B (TMA needs 16).
+struct ImagePool
+{
+    uint8_t *data = nullptr;
+    int rows = 0, cols = 0, pitch = 0, n_slots = 0;
+    CUtensorMap tmap_score; // box 80 x 38 x 1  (64x32 output tile + 3 px halo)
+    CUtensorMap tmap_patch; // box 64 x 57 x 1  (BRIEF patch)
+    size_t slot_bytes() const { return (size_t)pitch * rows; }
+};
+
+constexpr int kScoreTileW = 64, kScoreTileH = 32;
+constexpr int kScoreBoxW = 80, kScoreBoxH = kScoreTileH + 6;
+constexpr int kPatchW = 64, kPatchH = 57;
+
+// detection tile grid (lvt/src/lvt_image_features_handler.cpp:95-114)
+struct TileGrid
+{
+    int cell, nx, ny, img_w, img_h;
+    __host__ __device__ int count() const { return nx * ny; }
+    __host__ __device__ int tile_w(int tx) const { return (tx == nx - 1 && (tx + 1) * cell > img_w) ? img_w - tx * cell : cell; }
+    __host__ __device__ int tile_h(int ty) const { return (ty == ny - 1 && (ty + 1) * cell > img_h) ? img_h - ty * cell : cell; }
+};
+
+// One image's features as the matcher consumes them.  All pointers are device memory.
+struct FeatDev
+{
+    int *n;            // count N' after the BRIEF border filter
+    float2 *xy;        // [cap]
+    float *resp;       // [cap] AGAST response (0 for external corners)
+    uint32_t *desc;    // [cap][8]  256-bit BRIEF
+    uint8_t *matched;  // [cap] lvt_image_features_struct::m_matched_marks
+    float *depth;      // [cap] RGB-D only
+    int *cell_start;   // [cells+1] CSR over the 25-px hash grid (struct.cpp:58-61)
+    int *cell_items;   // [cap] feature indices grouped by cell
+    int *row_start;    // [rows+2] CSR over floor(y) (row matching band, struct.cpp:124-137)
+    int *row_items;    // [cap]
+    int cap;
+};
+
+// Scratch for `batch` images in flight through the detector.  Index [b] = image in batch.
+struct DetectWorkspace
+{
+    int batch = 0;
+    int n_tiles = 0;
+    int tile_cap = 0;       // entries per tile list (power of two, >= worst-case survivors)
+    uint8_t *score = nullptr;   // [batch][rows][pitch]   corner score, 0 = none
+    int *parent = nullptr;      // [batch][rows][pitch]   union-find scratch of the NMS fallback
+    uint32_t *tile_list = nullptr;   // [batch][n_tiles][tile_cap]  survivors, (raster << 8 | response)
+    uint32_t *tile_aux = nullptr;    // [batch][n_tiles][2*tile_cap] large-tile scratch (radii, permutation)
+    uint32_t *tile_out = nullptr;    // [batch][n_tiles][tile_cap]  ordered output, (y << 20 | x << 8 | response)
+    int *tile_count = nullptr;       // [batch][n_tiles]
+    int *tile_overflow = nullptr;    // [batch][n_tiles]  component larger than the in-register cap
+    int *tile_out_count = nullptr;   // [batch][n_tiles]
+    int *retry = nullptr;            // [batch] fewer than 200 corners: redo at the lowered threshold
+    int *error = nullptr;            // [1] sticky capacity error flag
+};
+
+struct DetectParams
+{
+    TileGrid grid;
+    int threshold;     // agast_threshold
+    int threshold_low; // (int)(threshold * 0.5 + 0.5)
+    int max_per_cell;  // max_keypoints_per_cell
+    int pitch, rows, cols;
+};
+
+// host launchers (detect.cu / brief.cu / index in match.cu)
+int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const DetectParams &dp, const int *d_slots,
+                  int n_images, FeatDev *d_feats /* device array [n_images] */, int border, int single_tile_nms,
+                  cudaStream_t stream);
+int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream);
+int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cudaStream_t stream);
+int upload_brief_pairs(const signed char pairs[256][4]);
+
+} // namespace lvtb

@@ -1,0 +1,178 @@
+// Feature container build-up: the 25-px hash grid of lvt_image_features_struct::init
+// (lvt/src/lvt_image_features_struct.cpp:35-66, .h:82-85) as a CSR, a row CSR for the stereo band
+// search (:124-137), cleared match marks (:62), and the RGB-D depth gate
+// (lvt/src/lvt_image_features_handler.cpp:249-294).
+#include "extract.cuh"
+
+namespace lvtb
+{
+
+struct IndexArgs
+{
+    const FeatDev *feats;
+    CamParams cam;
+};
+
+// exclusive scan of arr[0..len) in shared memory, in place; arr[len] = total
+__device__ void block_scan_array(int *arr, int len, int *s_scan)
+{
+    const int per = (len + blockDim.x - 1) / blockDim.x;
+    const int lo = min((int)threadIdx.x * per, len), hi = min(lo + per, len);
+    int sum = 0;
+    for (int i = lo; i < hi; i++)
+        sum += arr[i];
+    int total;
+    int off = block_exclusive_scan(sum, s_scan, &total);
+    for (int i = lo; i < hi; i++)
+    {
+        const int v = arr[i];
+        arr[i] = off;
+        off += v;
+    }
+    if (threadIdx.x == 0)
+        arr[len] = total;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) index_kernel(IndexArgs a)
+{
+    extern __shared__ int s_dyn[];
+    __shared__ int s_scan[34];
+    const CamParams &cam = a.cam;
+    const int n_cells = cam.cells_x * cam.cells_y, n_rows = cam.img_h + 1; // bins 0..img_h
+    int *s_cell = s_dyn, *s_row = s_dyn + n_cells + 1;
+    const FeatDev f = a.feats[blockIdx.x];
+    const int n = *f.n;
+
+    for (int i = threadIdx.x; i < n_cells + 1 + n_rows + 1; i += blockDim.x)
+        s_dyn[i] = 0;
+    __syncthreads();
+    const float cell = (float)kHashCell;
+    auto cell_of = [&](float2 p) {
+        // compute_hashed_index (struct.h:82-85); positions outside the grid (possible only for
+        // undistorted RGB-D keypoints, undefined in the reference) are clamped
+        const int hy = min(max((int)floorf(__fdiv_rn(p.y, cell)), 0), cam.cells_y - 1);
+        const int hx = min(max((int)floorf(__fdiv_rn(p.x, cell)), 0), cam.cells_x - 1);
+        return hy * cam.cells_x + hx;
+    };
+    auto row_of = [&](float2 p) { return min(max((int)floorf(p.y), 0), cam.img_h); };
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const float2 p = f.xy[i];
+        atomicAdd(&s_cell[cell_of(p)], 1);
+        atomicAdd(&s_row[row_of(p)], 1);
+        f.matched[i] = 0;
+    }
+    __syncthreads();
+    block_scan_array(s_cell, n_cells, s_scan);
+    block_scan_array(s_row, n_rows, s_scan);
+    for (int i = threadIdx.x; i <= n_cells; i += blockDim.x)
+        f.cell_start[i] = s_cell[i];
+    for (int i = threadIdx.x; i <= n_rows; i += blockDim.x)
+        f.row_start[i] = s_row[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const float2 p = f.xy[i];
+        f.cell_items[atomicAdd(&s_cell[cell_of(p)], 1)] = i;
+        f.row_items[atomicAdd(&s_row[row_of(p)], 1)] = i;
+    }
+}
+
+int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cudaStream_t stream)
+{
+    const int bytes = (cam.cells_x * cam.cells_y + 1 + cam.img_h + 2) * (int)sizeof(int);
+    static int configured = 0;
+    if (bytes > configured)
+    {
+        LVT_CUDA_TRY(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        configured = bytes;
+    }
+    IndexArgs ia{d_feats, cam};
+    index_kernel<<<n_images, 1024, bytes, stream>>>(ia);
+    LVT_CUDA_TRY(cudaGetLastError());
+    return LVTK_OK;
+}
+
+// ---- RGB-D: keep corners with a valid depth, attach it, undistort the survivors ----------------
+struct DepthArgs
+{
+    FeatDev f;
+    const float *depth; // rows x cols metres
+    int cols;
+    float near_plane, far_plane;
+    int undistort;
+    float fx, fy, cx, cy, k1, k2, p1, p2, k3;
+};
+
+// cv::undistortPoints(src, dst, K, dist, noArray(), K): 5 fixed-point iterations in fp64
+__device__ float2 undistort_point(const DepthArgs &a, float2 p)
+{
+    const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
+    double x = ((double)p.x - cx) / fx, y = ((double)p.y - cy) / fy;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++)
+    {
+        const double r2 = x * x + y * y;
+        const double icdist = 1.0 / (1 + (((double)a.k3 * r2 + (double)a.k2) * r2 + (double)a.k1) * r2);
+        const double dX = 2 * (double)a.p1 * x * y + (double)a.p2 * (r2 + 2 * x * x);
+        const double dY = (double)a.p1 * (r2 + 2 * y * y) + 2 * (double)a.p2 * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    return make_float2((float)(x * fx + cx), (float)(y * fy + cy));
+}
+
+__global__ void __launch_bounds__(1024) depth_gate_kernel(DepthArgs a)
+{
+    __shared__ int s_scan[34];
+    const FeatDev &f = a.f;
+    const int n = *f.n;
+    int running = 0;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x)
+    {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        float2 p = make_float2(0, 0);
+        float r = 0, d = 0;
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        if (i < n)
+        {
+            p = f.xy[i];
+            d = a.depth[(size_t)(int)p.y * a.cols + (int)p.x]; // Mat::at<float>(kp.pt.y, kp.pt.x): truncation
+            keep = d >= a.near_plane && d <= a.far_plane;
+            if (keep)
+            {
+                r = f.resp[i];
+                d0 = *reinterpret_cast<const uint4 *>(f.desc + 8 * (size_t)i);
+                d1 = *reinterpret_cast<const uint4 *>(f.desc + 8 * (size_t)i + 4);
+            }
+        }
+        int total;
+        const int pos = block_exclusive_scan(keep, s_scan, &total);
+        if (keep)
+        {
+            const int o = running + pos;
+            f.xy[o] = a.undistort ? undistort_point(a, p) : p;
+            f.resp[o] = r;
+            f.depth[o] = d;
+            *reinterpret_cast<uint4 *>(f.desc + 8 * (size_t)o) = d0;
+            *reinterpret_cast<uint4 *>(f.desc + 8 * (size_t)o + 4) = d1;
+        }
+        running += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        *f.n = running;
+}
+
+int launch_depth_gate(const FeatDev &f, const float *d_depth, const lvt_params_c &p, cudaStream_t stream)
+{
+    DepthArgs a{f, d_depth, p.img_width, p.near_plane_distance, p.far_plane_distance, fabsf(p.k1) > 1e-5f ? 1 : 0,
+                p.fx, p.fy, p.cx, p.cy, p.k1, p.k2, p.p1, p.p2, p.k3};
+    depth_gate_kernel<<<1, 1024, 0, stream>>>(a);
+    LVT_CUDA_TRY(cudaGetLastError());
+    return LVTK_OK;
+}
+
+} // namespace lvtb

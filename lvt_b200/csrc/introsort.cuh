@@ -1,0 +1,211 @@
+// Replay of libstdc++'s std::sort (introsort: median-of-3 quicksort to depth 2*lg(n), heapsort
+// fallback, threshold-16 final insertion sort) on 32-bit packed elements.
+//
+// Why: the reference orders a tile's corners with std::sort on the response alone
+// (lvt/src/lvt_image_features_handler.cpp:38-41).  Responses are small integers, ties are
+// everywhere, std::sort is unstable, and the resulting permutation is the order in which the
+// survivors are emitted (:72-80) -- i.e. it fixes every feature index downstream.  To be
+// index-exact the GPU path has to walk the same comparison sequence, so this is the same
+// algorithm (GCC 13 bits/stl_algo.h, bits/stl_heap.h) on elements (response << 24 | payload)
+// compared by the response byte only, "greater" first.
+//
+// Sequential by nature: one thread runs it per tile while the rest of the CTA computes the
+// suppression radii.  __host__ __device__ so that tests can check it against std::sort.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LVT_HD __host__ __device__
+#else
+#define LVT_HD
+#endif
+
+namespace lvtb
+{
+namespace isort
+{
+
+// comp(a, b): a sorts before b  <=>  response(a) > response(b)
+LVT_HD inline bool before(uint32_t a, uint32_t b) { return (a >> 24) > (b >> 24); }
+
+LVT_HD inline void swap_el(uint32_t *a, uint32_t *b)
+{
+    const uint32_t t = *a;
+    *a = *b;
+    *b = t;
+}
+
+LVT_HD inline void move_median_to_first(uint32_t *result, uint32_t *a, uint32_t *b, uint32_t *c)
+{
+    if (before(*a, *b))
+    {
+        if (before(*b, *c))
+            swap_el(result, b);
+        else if (before(*a, *c))
+            swap_el(result, c);
+        else
+            swap_el(result, a);
+    }
+    else if (before(*a, *c))
+        swap_el(result, a);
+    else if (before(*b, *c))
+        swap_el(result, c);
+    else
+        swap_el(result, b);
+}
+
+LVT_HD inline uint32_t *unguarded_partition(uint32_t *first, uint32_t *last, uint32_t *pivot)
+{
+    while (true)
+    {
+        while (before(*first, *pivot))
+            ++first;
+        --last;
+        while (before(*pivot, *last))
+            --last;
+        if (!(first < last))
+            return first;
+        swap_el(first, last);
+        ++first;
+    }
+}
+
+LVT_HD inline void push_heap(uint32_t *first, long hole, long top, uint32_t value)
+{
+    long parent = (hole - 1) / 2;
+    while (hole > top && before(first[parent], value))
+    {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+LVT_HD inline void adjust_heap(uint32_t *first, long hole, long len, uint32_t value)
+{
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2)
+    {
+        child = 2 * (child + 1);
+        if (before(first[child], first[child - 1]))
+            child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2)
+    {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    push_heap(first, hole, top, value);
+}
+
+// std::__partial_sort(first, last, last): make_heap + sort_heap
+LVT_HD inline void heap_sort(uint32_t *first, uint32_t *last)
+{
+    const long len = last - first;
+    if (len >= 2)
+    {
+        long parent = (len - 2) / 2;
+        while (true)
+        {
+            const uint32_t v = first[parent];
+            adjust_heap(first, parent, len, v);
+            if (parent == 0)
+                break;
+            parent--;
+        }
+    }
+    while (last - first > 1)
+    {
+        --last;
+        const uint32_t v = *last;
+        *last = *first;
+        adjust_heap(first, 0, last - first, v);
+    }
+}
+
+LVT_HD inline void unguarded_linear_insert(uint32_t *last)
+{
+    const uint32_t val = *last;
+    uint32_t *next = last - 1;
+    while (before(val, *next))
+    {
+        *last = *next;
+        last = next;
+        --next;
+    }
+    *last = val;
+}
+
+LVT_HD inline void insertion_sort(uint32_t *first, uint32_t *last)
+{
+    if (first == last)
+        return;
+    for (uint32_t *i = first + 1; i != last; ++i)
+    {
+        if (before(*i, *first))
+        {
+            const uint32_t val = *i;
+            for (uint32_t *p = i; p != first; --p)
+                *p = *(p - 1);
+            *first = val;
+        }
+        else
+            unguarded_linear_insert(i);
+    }
+}
+
+// std::sort(first, first + n, before)
+LVT_HD inline void sort(uint32_t *first, long n)
+{
+    if (n <= 0)
+        return;
+    uint32_t *last = first + n;
+    int lg = 0;
+    for (long v = n; v > 1; v >>= 1)
+        lg++;
+    // explicit stack replaces the recursion on the right-hand part; sub-ranges are disjoint,
+    // so the order in which they are processed does not change the result
+    struct Range
+    {
+        uint32_t *first, *last;
+        int depth;
+    };
+    Range stack[64];
+    int sp = 0;
+    stack[sp++] = Range{first, last, 2 * lg};
+    while (sp > 0)
+    {
+        Range r = stack[--sp];
+        while (r.last - r.first > 16)
+        {
+            if (r.depth == 0)
+            {
+                heap_sort(r.first, r.last);
+                break;
+            }
+            --r.depth;
+            uint32_t *mid = r.first + (r.last - r.first) / 2;
+            move_median_to_first(r.first, r.first + 1, mid, r.last - 1);
+            uint32_t *cut = unguarded_partition(r.first + 1, r.last, r.first);
+            stack[sp++] = Range{cut, r.last, r.depth};
+            r.last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16)
+    {
+        insertion_sort(first, first + 16);
+        for (uint32_t *i = first + 16; i != last; ++i)
+            unguarded_linear_insert(i);
+    }
+    else
+        insertion_sort(first, last);
+}
+
+} // namespace isort
+} // namespace lvtb

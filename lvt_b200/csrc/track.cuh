@@ -1,0 +1,306 @@
+// Device-resident tracking state of one sequence and the block-level map maintenance steps.
+// Header-only device code; the kernels are in track.cu.
+//
+// The reference keeps the local map in host vectors (lvt/src/lvt_local_map.h:64-85) and walks
+// them with scalar loops.  Here the map lives in HBM as structure-of-arrays and the whole of
+// lvt_system::perform_tracking (lvt/src/lvt_system.cpp:252-306) runs as ONE persistent CTA per
+// frame: projection matching, pose solve, culling, staging, triangulation -- no host round trip
+// between the stages, only the pose and the per-frame counters leave the GPU.
+#pragma once
+#include "match.cuh"
+#include "pose.cuh"
+
+namespace lvtb
+{
+
+// map points or staged points (lvt_local_map::lvt_map_point, lvt/src/lvt_local_map.h:64-73)
+struct PointStore
+{
+    double *xyz;    // [cap][3] world position
+    uint32_t *desc; // [cap][8]
+    int *counter;   // staged: frames tracked while staged; map: frames it failed tracking
+    int *age;
+    int *match_idx;
+    int cap;
+};
+
+struct MotionState // lvt/src/lvt_motion_model.h:41-45
+{
+    Quat last_q, ang_vel;
+    double last_pos[3], lin_vel[3];
+};
+
+struct TrackState
+{
+    int state;        // lvt_system::eState 1/2/3
+    int frame_number; // lvt_system::m_frame_number
+    int map_n, staged_n;
+    int last_matches[3]; // lvt/src/lvt_system.cpp:37, N_MATCHES_WINDOWS = 3
+    int error;           // sticky LVTK_ERR_*
+    PoseD last_pose;
+    MotionState motion;
+};
+
+struct FrameResult
+{
+    PoseD pose;
+    lvt_frame_info info;
+};
+
+struct TrackParams
+{
+    CamParams cam;
+    int sensor;              // 1 stereo, 2 rgbd
+    int min_matches;         // min_num_matches_for_tracking
+    int untracked_threshold; // untracked_threshold
+    int staged_threshold;
+    int triangulation_policy;
+};
+
+// scratch for one tracking CTA (global memory, sized for the point / feature capacities)
+struct TrackScratch
+{
+    MatchScratch ms;   // [pcap]
+    double *sol_xyz;   // [pcap][3]  matched map points, in map order
+    float2 *sol_uv;    // [pcap]     their matched keypoints
+    uint8_t *level;    // [pcap]
+    uint8_t *inlier;   // [pcap]
+    double *e2;        // [pcap]
+    int *row_choice;   // [fcap]
+    int *pair_query;   // [fcap]
+    int *pair_train;   // [fcap]
+    double *tri_xyz;   // [fcap][3]
+    uint8_t *tri_ok;   // [fcap]
+};
+
+// ---- motion model (lvt/src/lvt_motion_model.cpp:34-65), one thread -----------------------------
+__device__ inline Quat quat_slerp(const Quat &a, double t, const Quat &b)
+{
+    const double one = 1.0 - 2.220446049250313e-16;
+    const double d = quat_dot(a, b), abs_d = fabs(d);
+    double s0, s1;
+    if (abs_d >= one)
+    {
+        s0 = 1.0 - t;
+        s1 = t;
+    }
+    else
+    {
+        const double theta = acos(abs_d), sin_theta = sin(theta);
+        s0 = sin((1.0 - t) * theta) / sin_theta;
+        s1 = sin(t * theta) / sin_theta;
+    }
+    if (d < 0)
+        s1 = -s1;
+    Quat r;
+    r.w = s0 * a.w + s1 * b.w;
+    r.x = s0 * a.x + s1 * b.x;
+    r.y = s0 * a.y + s1 * b.y;
+    r.z = s0 * a.z + s1 * b.z;
+    return r;
+}
+
+__device__ inline void motion_reset(MotionState &m)
+{
+    m.last_q = Quat{1, 0, 0, 0};
+    m.ang_vel = Quat{1, 0, 0, 0};
+    for (int i = 0; i < 3; i++)
+        m.last_pos[i] = m.lin_vel[i] = 0.0;
+}
+
+__device__ inline PoseD motion_predict(MotionState &m, const PoseD &cur)
+{
+    double nl[3];
+    for (int i = 0; i < 3; i++)
+        nl[i] = ((cur.t[i] - m.last_pos[i]) + m.lin_vel[i]) * 0.5;
+    const Quat diff = quat_mul(cur.q, quat_inverse(m.last_q));
+    const Quat nav = quat_normalized(quat_slerp(diff, 0.5, m.ang_vel));
+    m.last_q = cur.q;
+    m.ang_vel = nav;
+    PoseD out;
+    for (int i = 0; i < 3; i++)
+    {
+        m.last_pos[i] = cur.t[i];
+        m.lin_vel[i] = nl[i];
+        out.t[i] = m.last_pos[i] + m.lin_vel[i];
+    }
+    out.q = quat_normalized(quat_mul(cur.q, nav));
+    return out;
+}
+
+// ---- triangulation (lvt/src/lvt_local_map.cpp:258-329), one thread per row match ---------------
+// minimum-norm least squares of A[:, 0:3] x = -A[:, 3] by one-sided Jacobi SVD (stands in for
+// Eigen::JacobiSVD(...).solve at :292)
+__device__ inline void solve_ls_4x3(const double Ain[4][4], double x[3])
+{
+    double a[4][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, b[4];
+    for (int i = 0; i < 4; i++)
+    {
+        for (int j = 0; j < 3; j++)
+            a[i][j] = Ain[i][j];
+        b[i] = -Ain[i][3];
+    }
+    for (int sweep = 0; sweep < 30; sweep++)
+    {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; pq++)
+        {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2; // (0,1) (0,2) (1,2)
+            double alpha = 0, beta = 0, gamma = 0;
+            for (int i = 0; i < 4; i++)
+            {
+                alpha += a[i][p] * a[i][p];
+                beta += a[i][q] * a[i][q];
+                gamma += a[i][p] * a[i][q];
+            }
+            if (gamma == 0.0 || fabs(gamma) <= 1e-15 * sqrt(alpha * beta))
+                continue;
+            rotated = true;
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+            for (int i = 0; i < 4; i++)
+            {
+                const double ap = a[i][p], aq = a[i][q];
+                a[i][p] = c * ap - s * aq;
+                a[i][q] = s * ap + c * aq;
+            }
+            for (int i = 0; i < 3; i++)
+            {
+                const double vp = V[i][p], vq = V[i][q];
+                V[i][p] = c * vp - s * vq;
+                V[i][q] = s * vp + c * vq;
+            }
+        }
+        if (!rotated)
+            break;
+    }
+    double s2[3], ab[3], s2max = 0;
+    for (int j = 0; j < 3; j++)
+    {
+        s2[j] = 0;
+        ab[j] = 0;
+        for (int i = 0; i < 4; i++)
+        {
+            s2[j] += a[i][j] * a[i][j];
+            ab[j] += a[i][j] * b[i];
+        }
+        s2max = fmax(s2max, s2[j]);
+    }
+    x[0] = x[1] = x[2] = 0;
+    const double thr = 4.0 * 2.220446049250313e-16;
+    for (int j = 0; j < 3; j++)
+    {
+        if (s2[j] <= thr * thr * s2max)
+            continue;
+        const double w = ab[j] / s2[j];
+        for (int i = 0; i < 3; i++)
+            x[i] += V[i][j] * w;
+    }
+}
+
+// Wl, Wr: world->camera of the left / right camera (12 doubles each)
+__device__ inline bool triangulate_pair(const double *Wl, const double *Wr, const CamParams &cam, float2 u1, float2 u2,
+                                        double out[3])
+{
+    const double cx = cam.cx, cy = cam.cy, inv_fx = 1.0 / (double)cam.fx, inv_fy = 1.0 / (double)cam.fy;
+    const double u1x = ((double)u1.x - cx) * inv_fx, u1y = ((double)u1.y - cy) * inv_fy;
+    const double u2x = ((double)u2.x - cx) * inv_fx, u2y = ((double)u2.y - cy) * inv_fy;
+    double A[4][4];
+    for (int c = 0; c < 4; c++)
+    {
+        A[0][c] = u1x * Wl[8 + c] - Wl[c];
+        A[1][c] = u1y * Wl[8 + c] - Wl[4 + c];
+        A[2][c] = u2x * Wr[8 + c] - Wr[c];
+        A[3][c] = u2y * Wr[8 + c] - Wr[4 + c];
+    }
+    solve_ls_4x3(A, out);
+    double ul, vl, ur, vr;
+    if (!point_visible(Wl, cam, out[0], out[1], out[2], &ul, &vl) ||
+        !point_visible(Wr, cam, out[0], out[1], out[2], &ur, &vr))
+        return false;
+    {
+        const double ex = ul - (double)u1.x, ey = vl - (double)u1.y;
+        if ((ex * ex + ey * ey) > kReprojectionTh2)
+            return false;
+    }
+    {
+        const double ex = ur - (double)u2.x, ey = vr - (double)u2.y;
+        if ((ex * ex + ey * ey) > kReprojectionTh2)
+            return false;
+    }
+    return true;
+}
+
+// right camera pose (lvt/src/lvt_pose.cpp:28-34)
+__device__ inline PoseD right_pose(const PoseD &l, double baseline)
+{
+    double R[9];
+    quat_to_mat(l.q, R);
+    PoseD r = l;
+    r.t[0] = R[0] * baseline + l.t[0];
+    r.t[1] = R[3] * baseline + l.t[1];
+    r.t[2] = R[6] * baseline + l.t[2];
+    return r;
+}
+
+__device__ inline void copy_point(const PointStore &dst, int d, const double *xyz, const uint32_t *desc, int counter,
+                                  int age, int match_idx)
+{
+    dst.xyz[3 * d] = xyz[0];
+    dst.xyz[3 * d + 1] = xyz[1];
+    dst.xyz[3 * d + 2] = xyz[2];
+    const uint4 a = *reinterpret_cast<const uint4 *>(desc), b = *reinterpret_cast<const uint4 *>(desc + 4);
+    *reinterpret_cast<uint4 *>(dst.desc + 8 * (size_t)d) = a;
+    *reinterpret_cast<uint4 *>(dst.desc + 8 * (size_t)d + 4) = b;
+    dst.counter[d] = counter;
+    dst.age[d] = age;
+    dst.match_idx[d] = match_idx;
+}
+
+// In-place, order-preserving compaction of a PointStore by keep(i).  Chunks are read into
+// registers, synchronised, then written: destinations never run ahead of the sources.
+template <class Keep>
+__device__ inline int block_compact_points(const PointStore &ps, int n, Keep keep, int *s_scan)
+{
+    int running = 0;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x)
+    {
+        const int i = i0 + threadIdx.x;
+        const bool k = i < n && keep(i);
+        double xyz[3] = {0, 0, 0};
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        int cnt = 0, age = 0, mi = 0;
+        if (k)
+        {
+            xyz[0] = ps.xyz[3 * i];
+            xyz[1] = ps.xyz[3 * i + 1];
+            xyz[2] = ps.xyz[3 * i + 2];
+            d0 = *reinterpret_cast<const uint4 *>(ps.desc + 8 * (size_t)i);
+            d1 = *reinterpret_cast<const uint4 *>(ps.desc + 8 * (size_t)i + 4);
+            cnt = ps.counter[i];
+            age = ps.age[i];
+            mi = ps.match_idx[i];
+        }
+        int total;
+        const int pos = block_exclusive_scan(k ? 1 : 0, s_scan, &total); // syncs: all reads done
+        if (k)
+        {
+            const int d = running + pos;
+            ps.xyz[3 * d] = xyz[0];
+            ps.xyz[3 * d + 1] = xyz[1];
+            ps.xyz[3 * d + 2] = xyz[2];
+            *reinterpret_cast<uint4 *>(ps.desc + 8 * (size_t)d) = d0;
+            *reinterpret_cast<uint4 *>(ps.desc + 8 * (size_t)d + 4) = d1;
+            ps.counter[d] = cnt;
+            ps.age[d] = age;
+            ps.match_idx[d] = mi;
+        }
+        running += total;
+        __syncthreads();
+    }
+    return running;
+}
+
+} // namespace lvtb
