@@ -3,8 +3,8 @@
 // Replaces cv::xfeatures2d::BriefDescriptorExtractor::compute as called at
 // lvt/src/lvt_image_features_handler.cpp:172 (also :190, :247): 32 bytes, no orientation.
 //
-// One warp per keypoint.  TMA stages the keypoint's 57x57 support (a 64x57 box at an arbitrary
-// byte offset) into shared memory; the warp turns it into a 58x58 integral image held in u16
+// One warp per keypoint.  TMA stages the keypoint's 57x57 support (an 80x57 box starting at the
+// 16-byte aligned column left of it) into shared memory; the warp turns it into a 58x58 integral image held in u16
 // -- arithmetic modulo 2^16 is exact because every 9x9 box sum is <= 81*255 = 20655 -- and
 // each lane then evaluates 8 tests.  The 32 outcomes of a group of tests are packed with one
 // __ballot_sync per 32-bit descriptor word; the lane -> test mapping is chosen so that the
@@ -94,11 +94,12 @@ __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_co
         *X = min((int)((double)p.x + 0.5), a.cols - kBriefBorder - 1);
         *Y = min((int)((double)p.y + 0.5), a.rows - kBriefBorder - 1);
     };
+    // the box starts at the 16-byte aligned column at or left of X-28 (TMA alignment rule)
     auto issue = [&](int k) {
         int X, Y;
         centre(k, &X, &Y);
         mbar_arrive_expect_tx(bar, kPatchBytes);
-        tma_load_3d(patch, &tmap, X - kBriefBorder, Y - kBriefBorder, slot, bar);
+        tma_load_3d(patch, &tmap, (X - kBriefBorder) & ~15, Y - kBriefBorder, slot, bar);
     };
 
     uint32_t phase = 0;
@@ -106,6 +107,9 @@ __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_co
         issue(kp);
     for (; kp < n; kp += stride)
     {
+        int Xc, Yc;
+        centre(kp, &Xc, &Yc);
+        const int xoff = (Xc - kBriefBorder) & 15; // column of the support inside the box
         mbar_wait(bar, phase);
         phase ^= 1;
         // pass 1: running column sums, lane = column (bytes of a row are consecutive: no conflicts)
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_co
 #pragma unroll 19
                 for (int r = 0; r < 57; r++)
                 {
-                    acc += patch[r * kPatchW + c];
+                    acc += patch[r * kPatchW + xoff + c];
                     integ[(r + 1) * kIntegStride + c + 1] = (uint16_t)acc;
                 }
             }
@@ -223,7 +227,7 @@ int launch_border_filter(const float2 *src_xy, const float *src_resp, const int 
 {
     FilterArgs fa{src_xy, src_resp, src_n, src_stride, d_feats, error, rows, cols};
     border_filter_kernel<<<n_images, 1024, 0, stream>>>(fa);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "border_filter_kernel");
     return LVTK_OK;
 }
 
@@ -238,7 +242,7 @@ int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const 
     BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols};
     // persistent-style: 148 SMs x 4 CTAs of 4 warps per image; warps stride over the keypoints
     brief_kernel<<<dim3(148 * 2, n_images), kBriefWarps * 32, kBriefSmem, stream>>>(pool.tmap_patch, ba);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "brief_kernel");
     return LVTK_OK;
 }
 

@@ -26,6 +26,21 @@ const char *last_error();
         }                                                                                                             \
     } while (0)
 
+// LVT_B200_SYNC=1: synchronise and check after every kernel launch (debug aid)
+bool debug_sync_enabled();
+#define LVT_LAUNCH_CHECK(stream, name)                                                                                \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                                                          \
+        if (_e == cudaSuccess && lvtb::debug_sync_enabled())                                                          \
+            _e = cudaStreamSynchronize(stream);                                                                       \
+        if (_e != cudaSuccess)                                                                                        \
+        {                                                                                                             \
+            lvtb::set_last_error(name, __LINE__, cudaGetErrorString(_e));                                             \
+            return LVTK_ERR_CUDA;                                                                                     \
+        }                                                                                                             \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // reference constants (lvt/src/lvt_definitions.h:29-34)
 // ---------------------------------------------------------------------------------------------

@@ -26,6 +26,11 @@ void set_last_error(const char *file, int line, const char *what)
         std::fprintf(stderr, "[lvt_b200] %s\n", g_err);
 }
 const char *last_error() { return g_err; }
+bool debug_sync_enabled()
+{
+    static const bool on = std::getenv("LVT_B200_SYNC") != nullptr;
+    return on;
+}
 
 // ---------------------------------------------------------------------------------------------
 // parameters (lvt/src/lvt_parameters.cpp:29-93)
@@ -343,8 +348,7 @@ static int ctx_check_error(lvtk_ctx *c)
     LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (e)
     {
-        int z = 0;
-        cudaMemcpy(c->ws.error, &z, sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemsetAsync(c->ws.error, 0, sizeof(int), c->stream);
         set_last_error(__FILE__, __LINE__, "device-side capacity error");
     }
     return e;
@@ -896,7 +900,11 @@ LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
     }
     g_pairs_custom = pairs != nullptr;
     if (g_pairs_uploaded) // a device is already in use: refresh its table
-        return upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr);
+    {
+        const int rc = upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr);
+        cudaDeviceSynchronize();
+        return rc;
+    }
     return 0;
 }
 
@@ -948,7 +956,9 @@ LVT_API int lvtk_agast(lvtk_ctx *ctx, const uint8_t *img, int rows, int cols, in
             return rc;
         LVT_CUDA_TRY(cudaMemcpy(d_f, &f, sizeof(f), cudaMemcpyHostToDevice));
         LVT_CUDA_TRY(cudaDeviceSynchronize());
-        LVT_CUDA_TRY(cudaMemcpy2D(pool.data, pool.pitch, img, stride, cols, rows, cudaMemcpyHostToDevice));
+        // stream-ordered: a synchronous copy from pageable memory may return before its DMA lands,
+        // and the kernels below run on a non-blocking stream
+        LVT_CUDA_TRY(cudaMemcpy2DAsync(pool.data, pool.pitch, img, stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
         if (int r = launch_detect(pool, ws, dp, d_slot, 1, d_f, 0, nonmax ? 1 : 0, ctx->stream))
             return r;
         LVT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

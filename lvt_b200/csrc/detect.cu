@@ -5,7 +5,7 @@
 // :146-152 (tile offset + concatenation), :161-169 (low-corner retry) and the border filter
 // that BriefDescriptorExtractor::compute applies at :172.
 //
-//   K1 score_kernel  : TMA stages a 70x38 (80x38 box) halo tile into shared memory; every pixel's
+//   K1 score_kernel  : TMA stages a 70x38 halo tile (96x38 box, 16-B aligned start) into shared memory; every pixel's
 //                      exact AGAST score (max threshold for which it is a 9-of-16 segment-test
 //                      corner) is computed branch-free with packed 2 x s16 min/max; the dense
 //                      u8 score map goes to HBM (stays in L2).
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) score_kernel(const __grid_constant__ CUte
     if (threadIdx.x == 0)
     {
         mbar_arrive_expect_tx(&bar, kScoreBoxH * kScoreBoxW);
-        tma_load_3d(&tile[0][0], &tmap, x0 - 3, y0 - 3, a.slots[b], &bar); // out-of-bounds -> 0
+        tma_load_3d(&tile[0][0], &tmap, x0 - kScoreBoxX, y0 - 3, a.slots[b], &bar); // out-of-bounds -> 0
     }
     mbar_wait(&bar, 0);
 
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) score_kernel(const __grid_constant__ CUte
             if (gx >= a.cols)
                 continue;
             const int tx = gx / a.grid.cell, lx = gx - tx * a.grid.cell, tw = a.grid.tile_w(tx);
-            int s = agast_score<kScoreBoxW>(&tile[r + 3][lx0 + 3]);
+            int s = agast_score<kScoreBoxW>(&tile[r + 3][lx0 + kScoreBoxX]);
             if (!(row_ok && lx >= 3 && lx <= tw - 4) || s < a.min_score)
                 s = 0;
             out[(size_t)gy * a.pitch + gx] = (uint8_t)s;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(128) nms_kernel(NmsArgs a)
     for (int k = 0; k < 4; k++)
     {
         const int s = (word >> (8 * k)) & 0xFF;
-        if (s >= a.threshold && s != 0)
+        if (s >= a.threshold && s != 0 && xw * 4 + k < a.cols)
             nms_pixel(a, b, sm, xw * 4 + k, y, s);
     }
 }
@@ -748,6 +748,7 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold};
     dim3 sgrid((dp.cols + kScoreTileW - 1) / kScoreTileW, (dp.rows + kScoreTileH - 1) / kScoreTileH, n_images);
     score_kernel<<<sgrid, 256, 0, stream>>>(pool.tmap_score, sa);
+    LVT_LAUNCH_CHECK(stream, "score_kernel");
 
     for (int pass = 0; pass < (allow_retry ? 2 : 1); pass++)
     {
@@ -759,14 +760,20 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
                    dp.pitch, dp.rows,     dp.cols,       ws.tile_cap,      nt,       th,    nonmax};
         dim3 ngrid(((dp.cols + 3) / 4 + 127) / 128, dp.rows, n_images);
         nms_kernel<<<ngrid, 128, 0, stream>>>(na);
+        LVT_LAUNCH_CHECK(stream, "nms_kernel");
         if (nonmax)
+        {
             nms_fallback_kernel<<<dim3(nt, n_images), 32, 0, stream>>>(na, ws.parent);
+            LVT_LAUNCH_CHECK(stream, "nms_fallback_kernel");
+        }
         TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count, ws.tile_out_count, retry,
                     dp.grid,      ws.tile_cap, nt,          dp.max_per_cell};
         tile_kernel<<<dim3(nt, n_images), kTileThreads, kTileSmemBytes, stream>>>(ta);
+        LVT_LAUNCH_CHECK(stream, "tile_kernel");
         GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, d_feats, nt, ws.tile_cap,
                       dp.rows,     dp.cols,           border,   pass,     allow_retry ? kCornersLowTh : 0};
         gather_kernel<<<n_images, 1024, 0, stream>>>(ga);
+        LVT_LAUNCH_CHECK(stream, "gather_kernel");
     }
     LVT_CUDA_TRY(cudaGetLastError());
     return LVTK_OK;

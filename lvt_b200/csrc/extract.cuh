@@ -12,14 +12,16 @@ struct ImagePool
 {
     uint8_t *data = nullptr;
     int rows = 0, cols = 0, pitch = 0, n_slots = 0;
-    CUtensorMap tmap_score; // box 80 x 38 x 1  (64x32 output tile + 3 px halo)
-    CUtensorMap tmap_patch; // box 64 x 57 x 1  (BRIEF patch)
+    // TMA needs the innermost box coordinate 16-byte aligned (measured: an unaligned x raises an
+    // illegal-instruction fault), so boxes start at an aligned x and are wide enough for any offset
+    CUtensorMap tmap_score; // box 96 x 38 x 1  (64x32 output tile, halo 3, start x0-16)
+    CUtensorMap tmap_patch; // box 80 x 57 x 1  (57-px BRIEF support at byte offset 0..15)
     size_t slot_bytes() const { return (size_t)pitch * rows; }
 };
 
 constexpr int kScoreTileW = 64, kScoreTileH = 32;
-constexpr int kScoreBoxW = 80, kScoreBoxH = kScoreTileH + 6;
-constexpr int kPatchW = 64, kPatchH = 57;
+constexpr int kScoreBoxW = 96, kScoreBoxH = kScoreTileH + 6, kScoreBoxX = 16;
+constexpr int kPatchW = 80, kPatchH = 57;
 
 // detection tile grid (lvt/src/lvt_image_features_handler.cpp:95-114)
 struct TileGrid

@@ -90,7 +90,7 @@ int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cud
     }
     IndexArgs ia{d_feats, cam};
     index_kernel<<<n_images, 1024, bytes, stream>>>(ia);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "index_kernel");
     return LVTK_OK;
 }
 
@@ -171,7 +171,7 @@ int launch_depth_gate(const FeatDev &f, const float *d_depth, const lvt_params_c
     DepthArgs a{f, d_depth, p.img_width, p.near_plane_distance, p.far_plane_distance, fabsf(p.k1) > 1e-5f ? 1 : 0,
                 p.fx, p.fy, p.cx, p.cy, p.k1, p.k2, p.p1, p.p2, p.k3};
     depth_gate_kernel<<<1, 1024, 0, stream>>>(a);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "depth_gate_kernel");
     return LVTK_OK;
 }
 

@@ -534,14 +534,14 @@ int launch_track_frame(TrackState *st, FrameResult *result, const PointStore &ma
         return rc;
     TrackArgs a{st, result, map, staged, d_feats, tp, sc, owner_cap};
     track_frame_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "track_frame_kernel");
     return LVTK_OK;
 }
 
 int launch_reset_state(TrackState *st, cudaStream_t stream)
 {
     reset_state_kernel<<<1, 1, 0, stream>>>(st);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "reset_state_kernel");
     return LVTK_OK;
 }
 
@@ -553,7 +553,7 @@ int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const
         return rc;
     MatchSeamArgs a{d_xyz, d_pdesc, m, pose, d_feat, cam, retry_below, ms, d_match_idx, d_d1, d_d2, d_count_retried, owner_cap};
     match_seam_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "match_seam_kernel");
     return LVTK_OK;
 }
 
@@ -564,7 +564,7 @@ int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, int *d_choice,
         return rc;
     RowSeamArgs a{d_feats, cam, d_choice, d_query, d_train, d_count, owner_cap};
     row_seam_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "row_seam_kernel");
     return LVTK_OK;
 }
 
@@ -573,7 +573,7 @@ int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD
 {
     PoseSeamArgs a{d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out};
     pose_seam_kernel<<<1, kTrackThreads, 0, stream>>>(a);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "pose_seam_kernel");
     return LVTK_OK;
 }
 
@@ -584,7 +584,7 @@ int launch_tri_seam(const PoseD &pose, const CamParams &cam, const float2 *d_uvl
         return LVTK_OK;
     TriSeamArgs a{pose, cam, d_uvl, d_uvr, n, d_xyz, d_ok};
     tri_seam_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a);
-    LVT_CUDA_TRY(cudaGetLastError());
+    LVT_LAUNCH_CHECK(stream, "tri_seam_kernel");
     return LVTK_OK;
 }
 
