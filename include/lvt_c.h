@@ -128,6 +128,30 @@ LVT_API int lvt_debug_get_points(lvt_handle vo_system, int which, double *xyz, u
  * generated_32.i.  NULL restores the built-in table.  Returns 0 on success. */
 LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4]);
 
+/* ---- resident-frame streaming (new; throughput path) -------------------------------------
+ * The reference processes one frame per call and blocks (lvt/src/lvt_c.cpp:63-88).  When the
+ * frames are already in device memory the same per-frame pipeline can run back to back with the
+ * feature extraction of frame t+1 overlapped with the tracking of frame t (compute_features is
+ * state-free, lvt/src/lvt_image_features_handler.cpp:196-209).  Results are identical to calling
+ * lvt_track on the same frames in the same order.  Stereo only. */
+LVT_API int lvt_pool_reserve(lvt_handle vo_system, int n_frames);
+/* copy one stereo pair (tightly packed u8) into pool slot `frame` */
+LVT_API int lvt_pool_upload(lvt_handle vo_system, int frame, const unsigned char *left, const unsigned char *right);
+/* track pool frames [first_frame, first_frame + n_frames) in order; poses: n x 12 doubles
+ * (R row-major, then t), infos: n entries; either may be NULL.  Returns 0 on success. */
+LVT_API int lvt_track_pool(lvt_handle vo_system, int first_frame, int n_frames, double *poses, lvt_frame_info *infos);
+
+/* device time (CUDA events, ms) of the last lvt_track_pool call, and kernels launched so far */
+LVT_API double lvt_last_batch_ms(lvt_handle vo_system);
+LVT_API long lvt_launch_count(void);
+/* per-kernel device time, measured with CUDA event pairs on the launching stream */
+LVT_API void lvt_set_profiling(int on);
+LVT_API int lvt_get_kernel_times(double *ms, long *counts, int cap); /* returns the number of kernels */
+LVT_API void lvt_reset_kernel_times(void);
+LVT_API const char *lvt_kernel_name(int id);
+/* last error text of the calling thread (CUDA library only; "" for the oracle) */
+LVT_API const char *lvtk_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,10 +133,40 @@ class Library:
                                        c_i32p, c_i32p, c_i32p]
         lib.lvtk_solve_pose.argtypes = [vp, c_f64p, c_f32p, C.c_int, c_f64p, c_f64p, c_f64p, c_f64p, c_u8p]
         lib.lvtk_triangulate.argtypes = [vp, c_f64p, c_f64p, c_f32p, c_f32p, C.c_int, c_f64p, c_u8p]
+        lib.lvt_pool_reserve.argtypes = [vp, C.c_int]
+        lib.lvt_pool_upload.argtypes = [vp, C.c_int, c_u8p, c_u8p]
+        lib.lvt_track_pool.argtypes = [vp, C.c_int, C.c_int, c_f64p, C.POINTER(FrameInfo)]
+        lib.lvt_set_profiling.argtypes = [C.c_int]
+        lib.lvt_get_kernel_times.argtypes = [c_f64p, C.POINTER(C.c_long), C.c_int]
+        lib.lvt_kernel_name.argtypes = [C.c_int]
+        lib.lvt_kernel_name.restype = C.c_char_p
+        lib.lvtk_last_error.restype = C.c_char_p
+        lib.lvt_last_batch_ms.argtypes = [vp]
+        lib.lvt_last_batch_ms.restype = C.c_double
+        lib.lvt_launch_count.restype = C.c_long
         self.is_gpu = bool(lib.lvtk_is_gpu())
 
     def has(self, name):
         return hasattr(self.lib, name)
+
+    def set_profiling(self, on):
+        self.lib.lvt_set_profiling(int(on))
+
+    def reset_kernel_times(self):
+        self.lib.lvt_reset_kernel_times()
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream"""
+        ms = np.zeros(32)
+        cnt = (C.c_long * 32)()
+        n = self.lib.lvt_get_kernel_times(_ptr(ms, c_f64p), cnt, 32)
+        return {self.lib.lvt_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def last_error(self):
+        return self.lib.lvtk_last_error().decode()
+
+    def launch_count(self):
+        return int(self.lib.lvt_launch_count())
 
     # -- parameters -----------------------------------------------------------------------
     def default_params(self, **overrides):
@@ -237,6 +267,24 @@ class System:
                                                  _ptr(cl, c_f64p), len(cl), _ptr(cr, c_f64p), len(cr),
                                                  _ptr(self._R, c_f64p), _ptr(self._t, c_f64p))
         return self._pose_out()
+
+    def pool_reserve(self, n_frames):
+        _check(self.lib.lvt_pool_reserve(self.h, n_frames), "lvt_pool_reserve")
+
+    def pool_upload(self, frame, left, right):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        _check(self.lib.lvt_pool_upload(self.h, frame, _u8(left), _u8(right)), "lvt_pool_upload")
+
+    def track_pool(self, first, n, want_infos=True):
+        """Track resident frames [first, first+n): returns (poses n x 12, infos list or None)."""
+        poses = np.zeros((n, 12), np.float64)
+        infos = (FrameInfo * n)() if want_infos else None
+        _check(self.lib.lvt_track_pool(self.h, first, n, _ptr(poses, c_f64p), infos), "lvt_track_pool")
+        return poses, ([infos[i].as_dict() for i in range(n)] if want_infos else None)
+
+    def last_batch_ms(self):
+        return float(self.lib.lvt_last_batch_ms(self.h))
 
     def frame_info(self):
         fi = FrameInfo()

@@ -241,7 +241,7 @@ int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const 
     }
     BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols};
     // persistent-style: 148 SMs x 4 CTAs of 4 warps per image; warps stride over the keypoints
-    brief_kernel<<<dim3(148 * 2, n_images), kBriefWarps * 32, kBriefSmem, stream>>>(pool.tmap_patch, ba);
+    LVT_TIMED(stream, K_BRIEF, (brief_kernel<<<dim3(148 * 2, n_images), kBriefWarps * 32, kBriefSmem, stream>>>(pool.tmap_patch, ba)));
     LVT_LAUNCH_CHECK(stream, "brief_kernel");
     return LVTK_OK;
 }

@@ -26,6 +26,42 @@ const char *last_error();
         }                                                                                                             \
     } while (0)
 
+// per-kernel timing (CUDA event pairs on the launching stream), enabled by lvt_set_profiling(1)
+enum KernelId
+{
+    K_SCORE,
+    K_NMS,
+    K_NMS_FALLBACK,
+    K_TILE,
+    K_GATHER,
+    K_CLEAR,
+    K_BRIEF,
+    K_INDEX,
+    K_TRACK_A,
+    K_MAPCAND,
+    K_ROWCAND,
+    K_POSE,
+    K_STAGEDCAND,
+    K_TRACK_B,
+    K_COUNT
+};
+bool prof_enabled();
+void count_launch();
+long launch_count();
+void prof_begin(cudaStream_t s, int id);
+void prof_end(cudaStream_t s, int id);
+#define LVT_TIMED(stream, id, launch)                                                                                 \
+    do                                                                                                                \
+    {                                                                                                                 \
+        const bool _p = lvtb::prof_enabled();                                                                         \
+        lvtb::count_launch();                                                                                         \
+        if (_p)                                                                                                       \
+            lvtb::prof_begin(stream, id);                                                                             \
+        launch;                                                                                                       \
+        if (_p)                                                                                                       \
+            lvtb::prof_end(stream, id);                                                                               \
+    } while (0)
+
 // LVT_B200_SYNC=1: synchronise and check after every kernel launch (debug aid)
 bool debug_sync_enabled();
 #define LVT_LAUNCH_CHECK(stream, name)                                                                                \

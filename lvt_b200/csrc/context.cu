@@ -26,6 +26,55 @@ void set_last_error(const char *file, int line, const char *what)
         std::fprintf(stderr, "[lvt_b200] %s\n", g_err);
 }
 const char *last_error() { return g_err; }
+// ---- per-kernel device time: CUDA event pairs recorded on the launching stream ---------------
+namespace
+{
+struct Profiler
+{
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> ids; // kernel id of pair i (events 2i, 2i+1)
+    size_t used = 0;
+    double ms[K_COUNT] = {};
+    long count[K_COUNT] = {};
+} g_prof;
+} // namespace
+static long g_launches = 0;
+void count_launch() { g_launches++; }
+long launch_count() { return g_launches; }
+bool prof_enabled() { return g_prof.on; }
+void prof_begin(cudaStream_t s, int id)
+{
+    if (g_prof.pool.size() < 2 * (g_prof.used + 1))
+    {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        g_prof.pool.push_back(a);
+        g_prof.pool.push_back(b);
+        g_prof.ids.push_back(id);
+    }
+    g_prof.ids[g_prof.used] = id;
+    cudaEventRecord(g_prof.pool[2 * g_prof.used], s);
+}
+void prof_end(cudaStream_t s, int)
+{
+    cudaEventRecord(g_prof.pool[2 * g_prof.used + 1], s);
+    g_prof.used++;
+}
+static void prof_collect()
+{
+    for (size_t i = 0; i < g_prof.used; i++)
+    {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]) == cudaSuccess)
+        {
+            g_prof.ms[g_prof.ids[i]] += t;
+            g_prof.count[g_prof.ids[i]]++;
+        }
+    }
+    g_prof.used = 0;
+}
 bool debug_sync_enabled()
 {
     static const bool on = std::getenv("LVT_B200_SYNC") != nullptr;
@@ -322,7 +371,7 @@ struct lvtk_ctx
     ImagePool pool;
     DetectWorkspace ws;
     int fcap = 0, pcap = 0;
-    FeatDev feats_h[2];
+    FeatDev feats_h[4]; // two ping-pong sets of (left, right): extraction of frame t+1 overlaps tracking of t
     FeatDev *feats_d = nullptr;
     int *d_slots = nullptr;
     uint8_t *h_stage = nullptr; // pinned, 2 tightly packed images
@@ -336,9 +385,23 @@ struct lvtk_ctx
     PoseD *d_pose_out = nullptr;
     // tracking
     TrackState *d_state = nullptr;
+    uint8_t *d_ctl = nullptr; // FrameCtl: hand-over between the kernels of the tracking chain
     FrameResult *d_result = nullptr, *h_result = nullptr;
+    // resident frame pool + pipelined streaming (lvt_pool_* / lvt_track_pool)
+    cudaStream_t stream_x = nullptr; // extraction runs here, tracking on `stream`
+    cudaEvent_t ev_extracted[2] = {nullptr, nullptr}, ev_tracked[2] = {nullptr, nullptr};
+    cudaEvent_t ev_batch[2] = {nullptr, nullptr}; // device time of the last lvt_track_pool call
+    float last_batch_ms = 0.f;
+    DeviceArena rarena;
+    ImagePool rpool;
+    int rpool_frames = 0;
+    int *d_slot_table = nullptr;       // [2 * rpool_frames] = 0, 1, 2, ...
+    FrameResult *d_results = nullptr;  // [rpool_frames]
+    FrameResult *h_results = nullptr;  // pinned
+
     PointStore map, staged;
     TrackScratch sc;
+    CandLists row_cand[2]; // per ping-pong feature set
 };
 
 static int ctx_check_error(lvtk_ctx *c)
@@ -385,6 +448,13 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     c->tp.staged_threshold = p.staged_threshold;
     c->tp.triangulation_policy = p.triangulation_policy;
     LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_x, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++)
+    {
+        LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_extracted[i], cudaEventDisableTiming));
+        LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_tracked[i], cudaEventDisableTiming));
+        LVT_CUDA_TRY(cudaEventCreate(&c->ev_batch[i]));
+    }
 
     if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
         return rc;
@@ -413,10 +483,10 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     c->fcap = (int)fcap;
     c->pcap = std::max(32768, 8 * c->fcap);
     const int n_cells = c->cam.cells_x * c->cam.cells_y;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 4; i++)
         if (int rc = make_feat(&c->feats_h[i], c->arena, c->fcap, n_cells, p.img_height))
             return rc;
-    int rc = c->arena.alloc(&c->feats_d, 2);
+    int rc = c->arena.alloc(&c->feats_d, 4);
     rc = rc ? rc : c->arena.alloc(&c->d_slots, 2);
     rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)p.img_width * p.img_height);
     rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->pcap);
@@ -428,17 +498,28 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->d_f_b, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->d_pose_out, 1);
     rc = rc ? rc : c->arena.alloc(&c->d_state, 1);
+    rc = rc ? rc : c->arena.alloc(&c->d_ctl, frame_ctl_bytes());
     rc = rc ? rc : c->arena.alloc(&c->d_result, 1);
     rc = rc ? rc : make_points(&c->map, c->arena, c->pcap);
     rc = rc ? rc : make_points(&c->staged, c->arena, c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.proj, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.vis, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.choice, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.ms.items, (size_t)2 * c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.sol_xyz, (size_t)c->pcap * 3);
     rc = rc ? rc : c->arena.alloc(&c->sc.sol_uv, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.level, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.inlier, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.e2, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.map_cand.keys, (size_t)c->pcap * kMapCandCap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.map_cand.count, (size_t)c->pcap);
+    c->sc.map_cand.cap = kMapCandCap;
+    for (int i = 0; i < 2; i++)
+    {
+        rc = rc ? rc : c->arena.alloc(&c->row_cand[i].keys, (size_t)c->fcap * kRowCandCap);
+        rc = rc ? rc : c->arena.alloc(&c->row_cand[i].count, (size_t)c->fcap);
+        c->row_cand[i].cap = kRowCandCap;
+    }
     rc = rc ? rc : c->arena.alloc(&c->sc.row_choice, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.pair_query, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.pair_train, (size_t)c->pcap);
@@ -475,6 +556,23 @@ static void ctx_free(lvtk_ctx *c)
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
+    if (c->stream_x)
+    {
+        cudaStreamSynchronize(c->stream_x);
+        cudaStreamDestroy(c->stream_x);
+    }
+    for (int i = 0; i < 2; i++)
+    {
+        if (c->ev_extracted[i])
+            cudaEventDestroy(c->ev_extracted[i]);
+        if (c->ev_tracked[i])
+            cudaEventDestroy(c->ev_tracked[i]);
+        if (c->ev_batch[i])
+            cudaEventDestroy(c->ev_batch[i]);
+    }
+    c->rarena.release();
+    if (c->h_results)
+        cudaFreeHost(c->h_results);
     c->arena.release();
     if (c->h_stage)
         cudaFreeHost(c->h_stage);
@@ -590,9 +688,12 @@ struct System
         frame_number++;
         if (state != 3)
             return false;
+        const int map_n = info.map_points_after, staged_n = info.staged_after; // the map is left as it was
         std::memset(&info, 0, sizeof(info));
         info.frame_number = frame_number;
         info.state = 3;
+        info.map_points_after = map_n;
+        info.staged_after = staged_n;
         *out = last_pose;
         return true;
     }
@@ -603,8 +704,11 @@ struct System
         lvtk_ctx *c = ctx;
         if (int rc = launch_index(c->feats_d, sensor == 1 ? 2 : 1, c->cam, c->stream))
             return rc;
-        if (int rc = launch_track_frame(c->d_state, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc, c->fcap,
-                                        c->stream))
+        if (sensor == 1)
+            if (int rc = launch_rowcand(c->feats_d, c->cam, c->row_cand[0], c->stream))
+                return rc;
+        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc,
+                                        c->row_cand[0], c->fcap, c->stream))
             return rc;
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, c->stream));
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -685,6 +789,110 @@ struct System
         if (int rc = launch_depth_gate(c->feats_h[0], c->d_depth, c->params, c->stream))
             return rc;
         return finish(out);
+    }
+
+    // ---- resident pool: frames already in HBM, extraction of frame t+1 overlapped with tracking of t
+    int pool_reserve(int n_frames)
+    {
+        lvtk_ctx *c = ctx;
+        if (n_frames <= 0)
+            return LVTK_ERR_ARG;
+        LVT_CUDA_TRY(cudaDeviceSynchronize());
+        c->rarena.release();
+        if (c->h_results)
+            cudaFreeHost(c->h_results);
+        c->h_results = nullptr;
+        c->rpool_frames = 0;
+        const int per = sensor == 1 ? 2 : 1;
+        if (int rc = make_image_pool(&c->rpool, c->rarena, c->params.img_height, c->params.img_width, per * n_frames))
+            return rc;
+        int rc = c->rarena.alloc(&c->d_slot_table, (size_t)per * n_frames);
+        rc = rc ? rc : c->rarena.alloc(&c->d_results, (size_t)n_frames);
+        if (rc)
+            return rc;
+        std::vector<int> table((size_t)per * n_frames);
+        for (size_t i = 0; i < table.size(); i++)
+            table[i] = (int)i;
+        LVT_CUDA_TRY(cudaMemcpy(c->d_slot_table, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice));
+        LVT_CUDA_TRY(cudaMallocHost(&c->h_results, sizeof(FrameResult) * (size_t)n_frames));
+        LVT_CUDA_TRY(cudaDeviceSynchronize());
+        c->rpool_frames = n_frames;
+        return LVTK_OK;
+    }
+
+    int pool_upload(int frame, const uint8_t *left, const uint8_t *right)
+    {
+        lvtk_ctx *c = ctx;
+        if (frame < 0 || frame >= c->rpool_frames || !left || (sensor == 1 && !right))
+            return LVTK_ERR_ARG;
+        const int per = sensor == 1 ? 2 : 1, rows = c->params.img_height, cols = c->params.img_width;
+        const uint8_t *src[2] = {left, right};
+        for (int k = 0; k < per; k++)
+            LVT_CUDA_TRY(cudaMemcpy2DAsync(c->rpool.data + c->rpool.slot_bytes() * (size_t)(per * frame + k), c->rpool.pitch,
+                                           src[k], cols, cols, rows, cudaMemcpyHostToDevice, c->stream));
+        LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return LVTK_OK;
+    }
+
+    int track_pool(int first, int n, double *poses /* n x 12: R row-major, t */, lvt_frame_info *infos)
+    {
+        lvtk_ctx *c = ctx;
+        if (sensor != 1 || first < 0 || n <= 0 || first + n > c->rpool_frames)
+            return LVTK_ERR_ARG;
+        // the batch is timed on the device: first extraction launch .. last result copy
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
+        LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream_x, c->ev_batch[0], 0));
+        for (int i = 0; i < n; i++)
+        {
+            const int par = i & 1;
+            if (i >= 2)
+                LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream_x, c->ev_tracked[par], 0));
+            const int *slots = c->d_slot_table + 2 * (size_t)(first + i);
+            FeatDev *feats = c->feats_d + 2 * par;
+            if (int rc = launch_detect(c->rpool, c->ws, c->dp, slots, 2, feats, kBriefBorder, 1, c->stream_x))
+                return rc;
+            if (int rc = launch_brief(c->rpool, slots, 2, feats, c->stream_x))
+                return rc;
+            if (int rc = launch_index(feats, 2, c->cam, c->stream_x))
+                return rc;
+            if (int rc = launch_rowcand(feats, c->cam, c->row_cand[par], c->stream_x))
+                return rc;
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_extracted[par], c->stream_x));
+            LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_extracted[par], 0));
+            if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_results + i, c->map, c->staged, feats, c->tp, c->sc,
+                                            c->row_cand[par], c->fcap, c->stream))
+                return rc;
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_tracked[par], c->stream));
+        }
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_results, c->d_results, sizeof(FrameResult) * (size_t)n, cudaMemcpyDeviceToHost,
+                                     c->stream));
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[1], c->stream));
+        LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        LVT_CUDA_TRY(cudaStreamSynchronize(c->stream_x));
+        LVT_CUDA_TRY(cudaEventElapsedTime(&c->last_batch_ms, c->ev_batch[0], c->ev_batch[1]));
+        if (int e = ctx_check_error(c))
+            return e;
+        for (int i = 0; i < n; i++)
+        {
+            const FrameResult &r = c->h_results[i];
+            const bool first_frame = state == 1;
+            frame_number++;
+            info = r.info;
+            info.frame_number = frame_number;
+            state = info.state;
+            if (!first_frame && state == 2)
+                last_pose = r.pose;
+            if (poses)
+            {
+                double m[9];
+                quat_to_mat(r.pose.q, m);
+                std::memcpy(poses + 12 * (size_t)i, m, sizeof(m));
+                std::memcpy(poses + 12 * (size_t)i + 9, r.pose.t, 3 * sizeof(double));
+            }
+            if (infos)
+                infos[i] = info;
+        }
+        return LVTK_OK;
     }
 
     int finish(PoseD *out)
@@ -910,6 +1118,89 @@ LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
 
 LVT_API const char *lvtk_last_error(void) { return last_error(); }
 
+LVT_API int lvt_pool_reserve(lvt_handle h, int n_frames)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    return vo->pool_reserve(n_frames);
+}
+LVT_API int lvt_pool_upload(lvt_handle h, int frame, const unsigned char *left, const unsigned char *right)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    return vo->pool_upload(frame, left, right);
+}
+LVT_API int lvt_track_pool(lvt_handle h, int first_frame, int n_frames, double *poses, lvt_frame_info *infos)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    const int rc = vo->track_pool(first_frame, n_frames, poses, infos);
+    if (prof_enabled())
+        prof_collect();
+    return rc;
+}
+/* profiling aid: clock64() phase marks and fixed-point round counts of pool frame i of the last batch
+ * (or of the last lvt_track call when i < 0) */
+LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int rounds[4])
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return -1;
+    const FrameResult &r = i < 0 ? *vo->ctx->h_result : vo->ctx->h_results[i];
+    std::memcpy(cycles, r.cycles, sizeof(r.cycles));
+    std::memcpy(rounds, r.rounds, sizeof(r.rounds));
+    return 0;
+}
+LVT_API double lvt_last_batch_ms(lvt_handle h)
+{
+    System *vo = static_cast<System *>(h);
+    return vo ? (double)vo->ctx->last_batch_ms : -1.0;
+}
+LVT_API long lvt_launch_count(void) { return launch_count(); }
+LVT_API void lvt_set_profiling(int on)
+{
+    cudaDeviceSynchronize();
+    if (g_prof.used)
+        prof_collect();
+    g_prof.on = on != 0;
+}
+LVT_API int lvt_get_kernel_times(double *ms, long *counts, int cap)
+{
+    cudaDeviceSynchronize();
+    if (g_prof.used)
+        prof_collect();
+    for (int i = 0; i < K_COUNT && i < cap; i++)
+    {
+        ms[i] = g_prof.ms[i];
+        counts[i] = g_prof.count[i];
+    }
+    return K_COUNT;
+}
+LVT_API void lvt_reset_kernel_times(void)
+{
+    cudaDeviceSynchronize();
+    g_prof.used = 0;
+    for (int i = 0; i < K_COUNT; i++)
+    {
+        g_prof.ms[i] = 0;
+        g_prof.count[i] = 0;
+    }
+}
+LVT_API const char *lvt_kernel_name(int id)
+{
+    static const char *names[K_COUNT] = {"score_kernel", "nms_kernel", "nms_fallback_kernel", "tile_kernel", "gather_kernel",
+                                         "clear_counts_kernel", "brief_kernel", "index_kernel", "track_a_kernel",
+                                         "mapcand_kernel", "rowcand_kernel", "pose_kernel", "stagedcand_kernel",
+                                         "track_b_kernel"};
+    return id >= 0 && id < K_COUNT ? names[id] : "";
+}
+
 // ---- seam ABI (include/lvt_kernels.h) ------------------------------------------------------------
 LVT_API lvtk_ctx *lvtk_ctx_create(const lvt_params_c *p, int device)
 {
@@ -1065,7 +1356,7 @@ LVT_API int lvtk_match_projected(lvtk_ctx *c, const double *pts_xyz, const uint8
         LVT_CUDA_TRY(cudaMemcpyAsync(c->map.desc, pts_desc, (size_t)32 * m, cudaMemcpyHostToDevice, c->stream));
     }
     if (int rc = launch_match_seam(c->map.xyz, c->map.desc, m, make_pose(q, t), c->feats_d, c->cam, retry_below, c->sc.ms,
-                                   c->d_int_a, c->d_f_a, c->d_f_b, c->d_int_b, c->fcap, c->stream))
+                                   c->sc.map_cand, c->d_int_a, c->d_f_a, c->d_f_b, c->d_int_b, c->fcap, c->stream))
         return rc;
     int cr[2] = {0, 0};
     if (m)
@@ -1100,8 +1391,8 @@ LVT_API int lvtk_row_match(lvtk_ctx *c, const lvtk_keypoint *kl, const uint8_t *
         return rc;
     if (int rc = ctx_upload_features(c, 1, kr, dr, nr, mr))
         return rc;
-    if (int rc = launch_row_seam(c->feats_d, c->cam, c->sc.row_choice, c->sc.pair_query, c->sc.pair_train, c->d_int_b,
-                                 c->fcap, c->stream))
+    if (int rc = launch_row_seam(c->feats_d, c->cam, c->row_cand[0], c->sc.row_choice, c->sc.ms.items, c->sc.pair_query,
+                                 c->sc.pair_train, c->d_int_b, c->fcap, c->stream))
         return rc;
     int np = 0;
     LVT_CUDA_TRY(cudaMemcpyAsync(&np, c->d_int_b, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1134,7 +1425,7 @@ LVT_API int lvtk_solve_pose(lvtk_ctx *c, const double *pts_xyz, const float *uv,
         LVT_CUDA_TRY(cudaMemcpyAsync(c->sc.sol_uv, uv, sizeof(float) * 2 * m, cudaMemcpyHostToDevice, c->stream));
     }
     if (int rc = launch_pose_seam(c->sc.sol_xyz, c->sc.sol_uv, m, make_pose(q_in, t_in), c->cam, c->sc.level, c->sc.inlier,
-                                  c->sc.e2, c->d_pose_out, c->stream))
+                                  c->sc.e2, c->d_pose_out, c->d_int_b, c->stream))
         return rc;
     PoseD out;
     LVT_CUDA_TRY(cudaMemcpyAsync(&out, c->d_pose_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream));

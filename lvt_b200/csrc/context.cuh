@@ -9,17 +9,19 @@ namespace lvtb
 int launch_border_filter(const float2 *src_xy, const float *src_resp, const int *src_n, int src_stride,
                          const FeatDev *d_feats, int n_images, int rows, int cols, int *error, cudaStream_t stream);
 int launch_depth_gate(const FeatDev &f, const float *d_depth, const lvt_params_c &p, cudaStream_t stream);
-int launch_track_frame(TrackState *st, FrameResult *result, const PointStore &map, const PointStore &staged,
-                       const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, int owner_cap,
-                       cudaStream_t stream);
+int launch_track_frame(TrackState *st, void *ctl, FrameResult *result, const PointStore &map, const PointStore &staged,
+                       const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
+                       int owner_cap, cudaStream_t stream);
+size_t frame_ctl_bytes();
+int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists &L, cudaStream_t stream);
 int launch_reset_state(TrackState *st, cudaStream_t stream);
 int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const PoseD &pose, const FeatDev *d_feat,
-                      const CamParams &cam, int retry_below, const MatchScratch &ms, int *d_match_idx, float *d_d1,
-                      float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream);
-int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, int *d_choice, int *d_query, int *d_train, int *d_count,
-                    int owner_cap, cudaStream_t stream);
+                      const CamParams &cam, int retry_below, const MatchScratch &ms, const CandLists &lists,
+                      int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream);
+int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandLists &lists, int *d_choice, int *d_items,
+                    int *d_query, int *d_train, int *d_count, int owner_cap, cudaStream_t stream);
 int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD &init, const CamParams &cam,
-                     uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, cudaStream_t stream);
+                     uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, int *d_n_inliers, cudaStream_t stream);
 int launch_tri_seam(const PoseD &pose, const CamParams &cam, const float2 *d_uvl, const float2 *d_uvr, int n,
                     double *d_xyz, uint8_t *d_ok, cudaStream_t stream);
 

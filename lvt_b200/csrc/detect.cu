@@ -747,32 +747,32 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
 
     ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold};
     dim3 sgrid((dp.cols + kScoreTileW - 1) / kScoreTileW, (dp.rows + kScoreTileH - 1) / kScoreTileH, n_images);
-    score_kernel<<<sgrid, 256, 0, stream>>>(pool.tmap_score, sa);
+    LVT_TIMED(stream, K_SCORE, (score_kernel<<<sgrid, 256, 0, stream>>>(pool.tmap_score, sa)));
     LVT_LAUNCH_CHECK(stream, "score_kernel");
 
     for (int pass = 0; pass < (allow_retry ? 2 : 1); pass++)
     {
         const int *retry = pass ? ws.retry : nullptr;
         const int th = pass ? dp.threshold_low : dp.threshold;
-        clear_counts_kernel<<<(n_images * nt + 255) / 256, 256, 0, stream>>>(ws.tile_count, ws.tile_overflow,
-                                                                            n_images * nt, retry, nt);
+        LVT_TIMED(stream, K_CLEAR, (clear_counts_kernel<<<(n_images * nt + 255) / 256, 256, 0, stream>>>(ws.tile_count, ws.tile_overflow,
+                                                                            n_images * nt, retry, nt)));
         NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, retry, dp.grid,
                    dp.pitch, dp.rows,     dp.cols,       ws.tile_cap,      nt,       th,    nonmax};
         dim3 ngrid(((dp.cols + 3) / 4 + 127) / 128, dp.rows, n_images);
-        nms_kernel<<<ngrid, 128, 0, stream>>>(na);
+        LVT_TIMED(stream, K_NMS, (nms_kernel<<<ngrid, 128, 0, stream>>>(na)));
         LVT_LAUNCH_CHECK(stream, "nms_kernel");
         if (nonmax)
         {
-            nms_fallback_kernel<<<dim3(nt, n_images), 32, 0, stream>>>(na, ws.parent);
+            LVT_TIMED(stream, K_NMS_FALLBACK, (nms_fallback_kernel<<<dim3(nt, n_images), 32, 0, stream>>>(na, ws.parent)));
             LVT_LAUNCH_CHECK(stream, "nms_fallback_kernel");
         }
         TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count, ws.tile_out_count, retry,
                     dp.grid,      ws.tile_cap, nt,          dp.max_per_cell};
-        tile_kernel<<<dim3(nt, n_images), kTileThreads, kTileSmemBytes, stream>>>(ta);
+        LVT_TIMED(stream, K_TILE, (tile_kernel<<<dim3(nt, n_images), kTileThreads, kTileSmemBytes, stream>>>(ta)));
         LVT_LAUNCH_CHECK(stream, "tile_kernel");
         GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, d_feats, nt, ws.tile_cap,
                       dp.rows,     dp.cols,           border,   pass,     allow_retry ? kCornersLowTh : 0};
-        gather_kernel<<<n_images, 1024, 0, stream>>>(ga);
+        LVT_TIMED(stream, K_GATHER, (gather_kernel<<<n_images, 1024, 0, stream>>>(ga)));
         LVT_LAUNCH_CHECK(stream, "gather_kernel");
     }
     LVT_CUDA_TRY(cudaGetLastError());

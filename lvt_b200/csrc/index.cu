@@ -89,7 +89,7 @@ int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cud
         configured = bytes;
     }
     IndexArgs ia{d_feats, cam};
-    index_kernel<<<n_images, 1024, bytes, stream>>>(ia);
+    LVT_TIMED(stream, K_INDEX, (index_kernel<<<n_images, 1024, bytes, stream>>>(ia)));
     LVT_LAUNCH_CHECK(stream, "index_kernel");
     return LVTK_OK;
 }

@@ -1,19 +1,23 @@
-// Block-level (one CTA) greedy Hamming matchers, bit-exact with the reference's sequential,
-// order-dependent loops.  Header-only device code shared by the seam kernels (match.cu) and the
-// fused per-frame tracking kernel (track.cu).
+// Greedy Hamming matchers, bit-exact with the reference's sequential, order-dependent loops.
+// Header-only device code shared by the seam kernels and the per-frame tracking kernel (track.cu).
 //
 // The reference matches map points one after another; a feature taken by an earlier point is
 // masked for all later ones (lvt/src/lvt_local_map.cpp:149-170,
 // lvt/src/lvt_image_features_struct.cpp:85-101), and stereo row matching does the same over left
 // features (lvt/src/lvt_image_features_handler.cpp:305-322).  The exact sequential result is the
 // unique fixed point of
-//     choice[i] = ratio_test( best2( candidates(i) \ { f : exists j < i, choice[j] == f } ) )
-// (induction on i), so it is computed by parallel rounds: every query re-selects against the
-// owners (= lowest query index choosing each feature) of the previous round until a round
-// changes nothing.  Round r fixes at least queries 0..r; in practice 2-4 rounds suffice.
-// Inside a round one warp serves one query: lanes stride over the candidates, each computes a
-// 256-bit Hamming distance with 8 __popc, and two redux.sync.min give the best two
-// (distance << 20 | index) keys == knnMatch's (distance, index) order.
+//     choice[q] = ratio_test( best2( candidates(q) \ { f : exists p < q, choice[p] == f } ) )
+// (induction on q), so it is computed in two phases:
+//   1. candidates (parallel over the whole GPU, one warp per query): the features inside the
+//      search window, each with its 256-bit Hamming distance (8 x __popc), packed as
+//      (distance << 20 | index) keys == knnMatch's (distance, index) order, sorted per query by a
+//      warp rank-sort and stored as a fixed-capacity list.  Nothing here depends on the order.
+//   2. rounds (one CTA, one thread per query): every query takes the first two keys of its list
+//      whose feature is not owned by an earlier query, applies the ratio test, and publishes its
+//      choice with atomicMin(owner[f], q); rounds repeat until one changes nothing.  Round r fixes
+//      at least queries 0..r; in practice 2-4 rounds suffice.
+// Queries whose window holds more candidates than the list capacity, the radius x2 retry pass and
+// the (small) staged set take the list-free path: one warp re-scans the window each round.
 #pragma once
 #include "extract.cuh"
 
@@ -23,6 +27,15 @@ namespace lvtb
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kFree = 0x7FFFFFFF; // owner of a feature nobody has chosen
 constexpr int kTaken = -1;        // owner of a feature that was marked before the pass started
+constexpr int kMapCandCap = 64;   // keys kept per map point
+constexpr int kRowCandCap = 128;  // keys kept per left feature
+
+struct CandLists
+{
+    uint32_t *keys; // [n_queries][cap], ascending; nullptr = no lists (every query re-scans)
+    int *count;     // [n_queries] true candidate count (> cap: list unusable, re-scan)
+    int cap;
+};
 
 __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint32_t *b)
 {
@@ -65,7 +78,122 @@ struct MatchScratch
     float2 *proj; // [cap] projected pixel (double -> float, struct.cpp:70)
     uint8_t *vis; // [cap] is_point_visible
     int *choice;  // [cap]
+    int *items;   // [2 * cap] work lists of the rounds
 };
+
+// ---------------------------------------------------------------------------------------------
+// window scans (one warp, all lanes call).  visit(key) is called by the lane that owns it.
+// ---------------------------------------------------------------------------------------------
+// find_match_index's candidate set (struct.cpp:71-101) minus the marks: features of the hash
+// cells [hy-r, hy+r] x [hx-r, hx+r] strictly inside the radius
+template <class Visit>
+__device__ __forceinline__ void scan_projected_window(const FeatDev &f, const CamParams &cam, float2 p, float r2,
+                                                      const uint4 q0, const uint4 q1, int lane, Visit &&visit)
+{
+    const float cell = (float)kHashCell;
+    const int hy = (int)floorf(__fdiv_rn(p.y, cell)), hx = (int)floorf(__fdiv_rn(p.x, cell));
+    const int sy = max(hy - cam.cell_search_radius, 0), ey = min(hy + cam.cell_search_radius + 1, cam.cells_y);
+    const int sx = max(hx - cam.cell_search_radius, 0), ex = min(hx + cam.cell_search_radius + 1, cam.cells_x);
+    if (sx >= ex)
+        return;
+    for (int cy = sy; cy < ey; cy++)
+    {
+        // cells of one grid row are contiguous in the CSR
+        const int s = f.cell_start[cy * cam.cells_x + sx], e = f.cell_start[cy * cam.cells_x + ex];
+        for (int base = s; base < e; base += 32)
+        {
+            const int pos = base + lane;
+            bool ok = false;
+            int j = 0;
+            if (pos < e)
+            {
+                j = f.cell_items[pos];
+                const float2 k = f.xy[j];
+                const float dx = __fsub_rn(k.x, p.x), dy = __fsub_rn(k.y, p.y);
+                ok = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2;
+            }
+            visit(ok, ok ? (((uint32_t)hamming256(q0, q1, f.desc + 8 * (size_t)j) << 20) | (uint32_t)j) : kNoKey);
+        }
+    }
+}
+
+// row_match's candidate set (struct.cpp:124-137) minus the marks: right features with
+// start_y <= y <= end_y, no x constraint
+template <class Visit>
+__device__ __forceinline__ void scan_row_band(const FeatDev &fr, const CamParams &cam, float2 p, const uint4 q0,
+                                              const uint4 q1, int lane, Visit &&visit)
+{
+    const int start_y = max((int)p.y - kRowSearchRadius, 0);
+    const int end_y = min((int)p.y + kRowSearchRadius, cam.img_h);
+    if (start_y > end_y)
+        return;
+    // bins floor(y) in [start_y, end_y] are contiguous in the row CSR
+    const int s = fr.row_start[start_y], e = fr.row_start[end_y + 1];
+    for (int base = s; base < e; base += 32)
+    {
+        const int pos = base + lane;
+        bool ok = false;
+        int j = 0;
+        if (pos < e)
+        {
+            j = fr.row_items[pos];
+            const float yj = fr.xy[j].y;
+            ok = yj >= (float)start_y && yj <= (float)end_y;
+        }
+        visit(ok, ok ? (((uint32_t)hamming256(q0, q1, fr.desc + 8 * (size_t)j) << 20) | (uint32_t)j) : kNoKey);
+    }
+}
+
+// warp-aggregated append of the lanes' keys into buf[cap] (shared memory); n counts all of them
+struct WarpCollector
+{
+    uint32_t *buf;
+    int cap, n, lane;
+    __device__ __forceinline__ void operator()(bool ok, uint32_t key)
+    {
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+            const int slot = n + __popc(m & ((1u << lane) - 1u));
+            if (slot < cap)
+                buf[slot] = key;
+        }
+        n += __popc(m);
+    }
+};
+
+// rank-sort the first min(n, 32*KPL) keys of buf (unique keys) and store them ascending
+template <int KPL>
+__device__ __forceinline__ void warp_sort_store(const uint32_t *buf, int n, uint32_t *out, int lane)
+{
+    __syncwarp();
+    uint32_t k[KPL];
+    int rank[KPL];
+#pragma unroll
+    for (int a = 0; a < KPL; a++)
+    {
+        k[a] = (lane + 32 * a < n) ? buf[lane + 32 * a] : kNoKey;
+        rank[a] = 0;
+    }
+    for (int src = 0; src < 32; src++)
+    {
+#pragma unroll
+        for (int b = 0; b < KPL; b++)
+        {
+            if (32 * b >= n)
+                break;
+            const uint32_t other = __shfl_sync(0xffffffffu, k[b], src);
+#pragma unroll
+            for (int a = 0; a < KPL; a++)
+                rank[a] += other < k[a];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < KPL; a++)
+        if (k[a] != kNoKey)
+            out[rank[a]] = k[a];
+    __syncwarp();
+}
 
 // is_point_visible for every point (lvt_local_map.cpp:62-82, :149-157)
 __device__ inline void block_project(const double *xyz, int m, const double *W /* smem, 12 */, const CamParams &cam,
@@ -81,85 +209,136 @@ __device__ inline void block_project(const double *xyz, int m, const double *W /
     __syncthreads();
 }
 
-// One pass of find_match_index over all visible points, in order, greedy (see file header).
-// use_marks: start from f.matched (true) or from a cleared mark vector (false).
-// On return: ms.choice[i] = feature or -1 for visible points; owner_a[f] != kFree <=> f is marked.
-// owner_a / owner_b: int[>= n] each (shared memory).  Returns the number of matches.
-__device__ inline int block_match_projected(const uint32_t *pdesc, const MatchScratch &ms, int m, const FeatDev &f,
-                                            int n, const CamParams &cam, float r2, bool use_marks, int *owner_a,
-                                            int *owner_b, int *s_flag, float *out_d1, float *out_d2)
+// ---------------------------------------------------------------------------------------------
+// phase 2: the rounds.  All threads of the CTA call.
+//   n_q queries, active(q) says whether query q takes part; lists may be empty (keys == nullptr).
+//   slow(q, cur, b1, b2): warp-cooperative window scan restricted to features with cur[f] >= q.
+//   marks: initial marks of the n_f features (nullptr = all clear).
+// On return choice[q] = feature or -1 for active queries, owner_a[f] != kFree <=> f is marked.
+// ---------------------------------------------------------------------------------------------
+template <class Active, class Slow>
+__device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active active, Slow slow, float ratio_th,
+                                   float dist_th, const uint8_t *marks, int *choice, int *items /* [2 * n_q] */,
+                                   int *owner_a, int *owner_b, int *s_flag /* [4] */, float *out_d1, float *out_d2,
+                                   int *rounds_out, long long *dbg = nullptr)
 {
+    (void)dbg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int *cur = owner_a, *nxt = owner_b;
-    for (int j = threadIdx.x; j < n; j += blockDim.x)
-        cur[j] = (use_marks && f.matched[j]) ? kTaken : kFree;
-    for (int i = threadIdx.x; i < m; i += blockDim.x)
-        ms.choice[i] = -1;
+    int *fast = items, *slow_items = items + n_q;
+    if (threadIdx.x == 0)
+        s_flag[2] = 0, s_flag[3] = 0;
+    for (int j = threadIdx.x; j < n_f; j += blockDim.x)
+        cur[j] = (marks && marks[j]) ? kTaken : kFree;
     __syncthreads();
-
-    const float cell = (float)kHashCell;
-    int count = 0;
-    for (int round = 0;; round++)
+    // work lists, built once: queries served from their key list / by a warp re-scan (order is irrelevant)
+    // (warp-aggregated appends: one shared-memory atomic per warp and list)
+    for (int q0 = 0; q0 < n_q; q0 += blockDim.x)
     {
-        for (int j = threadIdx.x; j < n; j += blockDim.x)
+        const int q = q0 + threadIdx.x;
+        int kind = 0; // 1 fast, 2 slow
+        if (q < n_q)
+        {
+            choice[q] = -1;
+            if (active(q))
+                kind = (L.keys && L.count[q] <= L.cap) ? 1 : 2;
+        }
+#pragma unroll
+        for (int which = 1; which <= 2; which++)
+        {
+            const uint32_t m = __ballot_sync(0xffffffffu, kind == which);
+            if (m == 0)
+                continue;
+            int base = 0;
+            if (lane == __ffs(m) - 1)
+                base = atomicAdd(&s_flag[1 + which], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (kind == which)
+                (which == 1 ? fast : slow_items)[base + __popc(m & ((1u << lane) - 1u))] = q;
+        }
+    }
+    __syncthreads();
+    const int n_fast = s_flag[2], n_slow = s_flag[3];
+
+    auto publish = [&](int q, uint32_t b1, uint32_t b2, int &my_count) {
+        const int c = accept_match(b1, b2, ratio_th, dist_th);
+        if (c != choice[q])
+        {
+            choice[q] = c;
+            s_flag[0] = 1;
+        }
+        if (c >= 0)
+        {
+            atomicMin(&nxt[c], q);
+            my_count++;
+            if (out_d1)
+            {
+                out_d1[q] = (float)(b1 >> 20);
+                out_d2[q] = b2 != kNoKey ? (float)(b2 >> 20) : -1.0f;
+            }
+        }
+    };
+
+    int count = 0, rounds = 0;
+    for (;; rounds++)
+    {
+        for (int j = threadIdx.x; j < n_f; j += blockDim.x)
             nxt[j] = cur[j] == kTaken ? kTaken : kFree;
         if (threadIdx.x == 0)
             s_flag[0] = 0, s_flag[1] = 0;
         __syncthreads();
-
         int my_count = 0;
-        for (int i = warp; i < m; i += nwarps)
+        // one thread per query, 4 queries in flight: the first four keys of each sorted list come in
+        // one 16-byte load; the first two keys not owned by an earlier query decide
+        constexpr int U = 4;
+        for (int base = threadIdx.x; base < n_fast; base += blockDim.x * U)
         {
-            if (!ms.vis[i])
-                continue;
-            const float2 p = ms.proj[i];
-            const int hy = (int)floorf(__fdiv_rn(p.y, cell)), hx = (int)floorf(__fdiv_rn(p.x, cell));
-            const int sy = max(hy - cam.cell_search_radius, 0), ey = min(hy + cam.cell_search_radius + 1, cam.cells_y);
-            const int sx = max(hx - cam.cell_search_radius, 0), ex = min(hx + cam.cell_search_radius + 1, cam.cells_x);
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(pdesc + 8 * (size_t)i);
-            const uint4 q1 = *reinterpret_cast<const uint4 *>(pdesc + 8 * (size_t)i + 4);
-            uint32_t k1 = kNoKey, k2 = kNoKey;
-            if (sx < ex)
+            int q[U], cnt[U];
+            uint4 k4[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
             {
-                for (int cy = sy; cy < ey; cy++)
-                {
-                    // cells of one grid row are contiguous in the CSR
-                    const int s = f.cell_start[cy * cam.cells_x + sx], e = f.cell_start[cy * cam.cells_x + ex];
-                    for (int pos = s + lane; pos < e; pos += 32)
-                    {
-                        const int j = f.cell_items[pos];
-                        if (cur[j] < i)
-                            continue; // marked, or taken by an earlier point
-                        const float2 k = f.xy[j];
-                        const float dx = __fsub_rn(k.x, p.x), dy = __fsub_rn(k.y, p.y);
-                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2)
-                            top2_insert(((uint32_t)hamming256(q0, q1, f.desc + 8 * (size_t)j) << 20) | (uint32_t)j, k1, k2);
-                    }
-                }
+                const int it = base + u * blockDim.x;
+                q[u] = it < n_fast ? fast[it] : -1;
             }
-            uint32_t b1, b2;
-            warp_top2(k1, k2, b1, b2);
-            const int c = accept_match(b1, b2, cam.tracking_ratio_th, cam.desc_dist_th);
-            if (lane == 0)
+#pragma unroll
+            for (int u = 0; u < U; u++)
             {
-                if (c != ms.choice[i])
+                cnt[u] = q[u] >= 0 ? L.count[q[u]] : 0;
+                k4[u] = q[u] >= 0 ? *reinterpret_cast<const uint4 *>(L.keys + (size_t)q[u] * L.cap) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (q[u] < 0)
+                    continue;
+                const uint32_t *keys = L.keys + (size_t)q[u] * L.cap;
+                uint32_t b1 = kNoKey, b2 = kNoKey;
+                for (int k = 0; k < cnt[u]; k++)
                 {
-                    ms.choice[i] = c;
-                    s_flag[0] = 1;
-                }
-                if (c >= 0)
-                {
-                    atomicMin(&nxt[c], i);
-                    my_count++;
-                    if (out_d1)
+                    const uint32_t key = k == 0 ? k4[u].x : k == 1 ? k4[u].y : k == 2 ? k4[u].z : k == 3 ? k4[u].w : keys[k];
+                    if (cur[key & 0xFFFFFu] < q[u])
+                        continue; // marked, or taken by an earlier query
+                    if (b1 == kNoKey)
+                        b1 = key;
+                    else
                     {
-                        out_d1[i] = (float)(b1 >> 20);
-                        out_d2[i] = b2 != kNoKey ? (float)(b2 >> 20) : -1.0f;
+                        b2 = key;
+                        break;
                     }
                 }
+                publish(q[u], b1, b2, my_count);
             }
         }
-        if (lane == 0 && my_count)
+        for (int it = warp; it < n_slow; it += nwarps)
+        {
+            const int q = slow_items[it];
+            uint32_t b1, b2;
+            slow(q, cur, b1, b2);
+            if (lane == 0)
+                publish(q, b1, b2, my_count);
+        }
+        if (my_count)
             atomicAdd(&s_flag[1], my_count);
         __syncthreads();
         const int changed = s_flag[0];
@@ -173,92 +352,68 @@ __device__ inline int block_match_projected(const uint32_t *pdesc, const MatchSc
     }
     if (cur != owner_a)
     {
-        for (int j = threadIdx.x; j < n; j += blockDim.x)
+        for (int j = threadIdx.x; j < n_f; j += blockDim.x)
             owner_a[j] = cur[j];
         __syncthreads();
     }
+    if (rounds_out && threadIdx.x == 0)
+        *rounds_out = rounds + 1;
     return count;
 }
 
-// Stereo row matching pass (handler.cpp:302-323 + struct.cpp:122-148).  Queries = left features
-// in index order that are not marked; candidates = unmarked right features whose y lies in
-// [max(0,(int)y-2), min(rows,(int)y+2)] -- no x constraint.  choice: int[>= nl] (global).
-// On return the marks of both sides are updated and the pairs are written in left-index order.
-__device__ inline int block_row_match(const FeatDev &fl, int nl, const FeatDev &fr, int nr, const CamParams &cam,
-                                      int *choice, int *owner_a, int *owner_b, int *s_flag, int *s_scan,
-                                      int *out_query, int *out_train)
+// One pass of find_match_index over all visible points, in order, greedy.
+__device__ inline int block_match_projected(const CandLists &L, const uint32_t *pdesc, const MatchScratch &ms, int m,
+                                            const FeatDev &f, int n, const CamParams &cam, float r2, bool use_marks,
+                                            int *owner_a, int *owner_b, int *s_flag, float *out_d1, float *out_d2,
+                                            int *rounds_out, long long *dbg = nullptr)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int *cur = owner_a, *nxt = owner_b;
-    for (int j = threadIdx.x; j < nr; j += blockDim.x)
-        cur[j] = fr.matched[j] ? kTaken : kFree;
-    for (int i = threadIdx.x; i < nl; i += blockDim.x)
-        choice[i] = -1;
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    auto active = [&](int q) { return ms.vis[q] != 0; };
+    auto slow = [&](int q, const int *cur, uint32_t &b1, uint32_t &b2) {
+        const uint4 q0 = *reinterpret_cast<const uint4 *>(pdesc + 8 * (size_t)q);
+        const uint4 q1 = *reinterpret_cast<const uint4 *>(pdesc + 8 * (size_t)q + 4);
+        uint32_t k1 = kNoKey, k2 = kNoKey;
+        scan_projected_window(f, cam, ms.proj[q], r2, q0, q1, lane, [&](bool ok, uint32_t key) {
+            if (ok && cur[key & 0xFFFFFu] >= q)
+                top2_insert(key, k1, k2);
+        });
+        warp_top2(k1, k2, b1, b2);
+    };
+    return block_rounds(L, m, n, active, slow, cam.tracking_ratio_th, cam.desc_dist_th, use_marks ? f.matched : nullptr,
+                        ms.choice, ms.items, owner_a, owner_b, s_flag, out_d1, out_d2, rounds_out, dbg);
+}
 
-    for (int round = 0;; round++)
-    {
-        for (int j = threadIdx.x; j < nr; j += blockDim.x)
-            nxt[j] = cur[j] == kTaken ? kTaken : kFree;
-        if (threadIdx.x == 0)
-            s_flag[0] = 0;
-        __syncthreads();
-        for (int i = warp; i < nl; i += nwarps)
-        {
-            if (fl.matched[i])
-                continue; // tracked from the map this frame (handler.cpp:307-310)
-            const float2 p = fl.xy[i];
-            const int start_y = max((int)p.y - kRowSearchRadius, 0);
-            const int end_y = min((int)p.y + kRowSearchRadius, cam.img_h);
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(fl.desc + 8 * (size_t)i);
-            const uint4 q1 = *reinterpret_cast<const uint4 *>(fl.desc + 8 * (size_t)i + 4);
-            uint32_t k1 = kNoKey, k2 = kNoKey;
-            if (start_y <= end_y)
-            {
-                // bins floor(y) in [start_y, end_y] are contiguous in the row CSR
-                const int s = fr.row_start[start_y], e = fr.row_start[end_y + 1];
-                for (int pos = s + lane; pos < e; pos += 32)
-                {
-                    const int j = fr.row_items[pos];
-                    if (cur[j] < i)
-                        continue;
-                    const float yj = fr.xy[j].y;
-                    if (yj >= (float)start_y && yj <= (float)end_y)
-                        top2_insert(((uint32_t)hamming256(q0, q1, fr.desc + 8 * (size_t)j) << 20) | (uint32_t)j, k1, k2);
-                }
-            }
-            uint32_t b1, b2;
-            warp_top2(k1, k2, b1, b2);
-            const int c = accept_match(b1, b2, cam.triangulation_ratio_th, cam.desc_dist_th);
-            if (lane == 0)
-            {
-                if (c != choice[i])
-                {
-                    choice[i] = c;
-                    s_flag[0] = 1;
-                }
-                if (c >= 0)
-                    atomicMin(&nxt[c], i);
-            }
-        }
-        __syncthreads();
-        const int changed = s_flag[0];
-        int *t = cur;
-        cur = nxt;
-        nxt = t;
-        __syncthreads();
-        if (!changed)
-            break;
-    }
+// Stereo row matching pass (handler.cpp:302-323 + struct.cpp:122-148).  Queries = unmarked left
+// features in index order.  On return the marks of both sides are updated and the pairs are
+// written in left-index order; returns their count.
+__device__ inline int block_row_match(const CandLists &L, const FeatDev &fl, int nl, const FeatDev &fr, int nr,
+                                      const CamParams &cam, int *choice, int *items, int *owner_a, int *owner_b,
+                                      int *s_flag, int *s_scan, int *out_query, int *out_train, int *rounds_out)
+{
+    const int lane = threadIdx.x & 31;
+    auto active = [&](int q) { return fl.matched[q] == 0; }; // tracked from the map this frame: skipped (handler.cpp:307-310)
+    auto slow = [&](int q, const int *cur, uint32_t &b1, uint32_t &b2) {
+        const uint4 q0 = *reinterpret_cast<const uint4 *>(fl.desc + 8 * (size_t)q);
+        const uint4 q1 = *reinterpret_cast<const uint4 *>(fl.desc + 8 * (size_t)q + 4);
+        uint32_t k1 = kNoKey, k2 = kNoKey;
+        scan_row_band(fr, cam, fl.xy[q], q0, q1, lane, [&](bool ok, uint32_t key) {
+            if (ok && cur[key & 0xFFFFFu] >= q)
+                top2_insert(key, k1, k2);
+        });
+        warp_top2(k1, k2, b1, b2);
+    };
+    block_rounds(L, nl, nr, active, slow, cam.triangulation_ratio_th, cam.desc_dist_th, fr.matched, choice, items,
+                 owner_a, owner_b, s_flag, nullptr, nullptr, rounds_out);
     for (int j = threadIdx.x; j < nr; j += blockDim.x)
-        if (cur[j] != kFree)
+        if (owner_a[j] != kFree)
             fr.matched[j] = 1;
-    // pairs in left-index order + left marks (handler.cpp:313-321)
+    // pairs in left-index order + left marks (handler.cpp:313-321); the marks read by active() are
+    // only written after every thread has read its own
     int running = 0;
     for (int i0 = 0; i0 < nl; i0 += blockDim.x)
     {
         const int i = i0 + threadIdx.x;
-        const int c = i < nl ? choice[i] : -1;
+        const int c = (i < nl && fl.matched[i] == 0) ? choice[i] : -1;
         int total;
         const int pos = block_exclusive_scan(c >= 0, s_scan, &total);
         if (c >= 0)

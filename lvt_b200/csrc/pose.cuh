@@ -13,6 +13,7 @@
 // runs the 6x6 solve and the LM accept / reject logic between evaluations.
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace lvtb
 {
@@ -97,30 +98,84 @@ __device__ inline bool solve6(const double *A_in /* 36 */, const double *b_in, d
     return true;
 }
 
-constexpr int kPoseSums = 28; // 21 (upper H) + 6 (b) + 1 (robust chi2)
+// Cholesky solve of (H + lambda I) x = b, fully unrolled so that everything stays in registers;
+// false when the matrix is not positive definite (the caller then falls back to LU)
+__device__ __forceinline__ bool chol_solve6(const double *H, double lambda, const double *b, double *x)
+{
+    double L[6][6];
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+    {
+        double sum = H[7 * j] + lambda;
+#pragma unroll
+        for (int k = 0; k < j; k++)
+            sum -= L[j][k] * L[j][k];
+        if (!(sum > 0.0))
+            return false;
+        L[j][j] = sqrt(sum);
+        const double inv = 1.0 / L[j][j];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++)
+        {
+            double v = H[6 * i + j];
+#pragma unroll
+            for (int k = 0; k < j; k++)
+                v -= L[i][k] * L[j][k];
+            L[i][j] = v * inv;
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+    {
+        double v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++)
+            v -= L[i][k] * y[k];
+        y[i] = v / L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--)
+    {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++)
+            v -= L[k][i] * x[k];
+        x[i] = v / L[i][i];
+    }
+    return true;
+}
+
+constexpr int kPoseSums = 29;   // 21 (upper H) + 6 (b) + robust chi2 + number of active edges
+constexpr int kPoseCluster = 8; // CTAs (SMs) sharing the correspondences of one solve
+constexpr int kPoseThreads = 256;
 
 struct PoseShared
 {
-    CamState cam;
-    double partial[32][kPoseSums]; // per-warp partial sums
-    double sums[kPoseSums];
-    int cont;
+    CamState cam;                                   // every CTA keeps a copy of the camera under evaluation
+    double partial[kPoseThreads / 32][kPoseSums];   // per-warp partial sums
+    double cta_sums[kPoseSums];                     // this CTA's sums, read by rank 0 through DSMEM
+    double sums[kPoseSums];                         // cluster totals (rank 0 only)
+    int cont;                                       // 0 evaluate again, 1 end of pass, 2 finished
 };
 
-// One evaluation at s.cam over the active edges.  with_system: also accumulate H and b.
-// Writes e2[i] (the edge's chi2 as last computed) and leaves the totals in s.sums.
-template <bool kWithSystem>
-__device__ inline void pose_evaluate(PoseShared &s, const double *xyz, const float2 *uv, const uint8_t *level, double *e2,
-                                     int m)
+// One evaluation at s.cam over the active edges owned by this CTA: errors, robust cost, and the
+// linearisation (H, b) -- g2o recomputes both at every accepted state, so an accepted trial's
+// evaluation doubles as the next iteration's buildSystem.  Edge i is owned by thread
+// (i / blockDim) % nranks == rank, the same one in every evaluation.  Cluster totals end up in
+// rank 0's s.sums after one cluster barrier; the summation order is fixed (deterministic).
+template <class Cluster>
+__device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, const double *xyz, const float2 *uv,
+                                     const uint8_t *level, double *e2, int m, int rank, int nranks)
 {
     const CamState &c = s.cam;
     const double dsqr = kReprojectionTh2, dsqr_reci = 1.0 / kReprojectionTh2; // delta = sqrt(5.991)
-    double acc[kWithSystem ? kPoseSums : 1];
+    double acc[kPoseSums];
 #pragma unroll
-    for (int k = 0; k < (kWithSystem ? kPoseSums : 1); k++)
+    for (int k = 0; k < kPoseSums; k++)
         acc[k] = 0.0;
 
-    for (int i = threadIdx.x; i < m; i += blockDim.x)
+    for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
     {
         if (level[i])
             continue;
@@ -135,85 +190,101 @@ __device__ inline void pose_evaluate(PoseShared &s, const double *xyz, const flo
         const double chi = ex * ex + ey * ey;
         e2[i] = chi;
         const double aux = dsqr_reci * chi + 1.0;
-        acc[kWithSystem ? 27 : 0] += dsqr * log(aux); // RobustKernelCauchy rho[0]
-        if (kWithSystem)
+        acc[27] += dsqr * log(aux); // RobustKernelCauchy rho[0]
+        acc[28] += 1.0;
+        const double w = 1.0 / aux; // rho[1]
+        // EdgeProjectP2MC::linearizeOplus, camera block
+        const double ipz2 = 1.0 / (pz * pz);
+        const double ipz2fx = ipz2 * c.fx, ipz2fy = ipz2 * c.fy;
+        const double pw[3] = {X - c.t[0], Y - c.t[1], Z - c.t[2]};
+        double J0[6], J1[6];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
         {
-            const double w = 1.0 / aux; // rho[1]
-            // EdgeProjectP2MC::linearizeOplus, camera block
-            const double ipz2 = 1.0 / (pz * pz);
-            const double ipz2fx = ipz2 * c.fx, ipz2fy = ipz2 * c.fy;
-            const double pw[3] = {X - c.t[0], Y - c.t[1], Z - c.t[2]};
-            double J0[6], J1[6];
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-            {
-                const double d0 = -c.w2n[k], d1 = -c.w2n[4 + k], d2 = -c.w2n[8 + k];
-                J0[k] = (pz * d0 - px * d2) * ipz2fx;
-                J1[k] = (pz * d1 - py * d2) * ipz2fy;
-            }
-            // dRd{x,y,z} * (p - t), with dRidx = [0 0 0; 0 0 2; 0 -2 0] etc. applied to R^T
-            const double r0 = c.w2n[0] * pw[0] + c.w2n[1] * pw[1] + c.w2n[2] * pw[2];
-            const double r1 = c.w2n[4] * pw[0] + c.w2n[5] * pw[1] + c.w2n[6] * pw[2];
-            const double r2 = c.w2n[8] * pw[0] + c.w2n[9] * pw[1] + c.w2n[10] * pw[2];
-            const double q[3][3] = {{0.0, 2 * r2, -2 * r1}, {-2 * r2, 0.0, 2 * r0}, {2 * r1, -2 * r0, 0.0}};
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-            {
-                J0[3 + k] = (pz * q[k][0] - px * q[k][2]) * ipz2fx;
-                J1[3 + k] = (pz * q[k][1] - py * q[k][2]) * ipz2fy;
-            }
-            const double g0 = -ex * w, g1 = -ey * w;
-            int idx = 0;
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-            {
-#pragma unroll
-                for (int bcol = a; bcol < 6; bcol++)
-                    acc[idx++] += (J0[a] * J0[bcol] + J1[a] * J1[bcol]) * w;
-            }
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-                acc[21 + a] += J0[a] * g0 + J1[a] * g1;
+            const double d0 = -c.w2n[k], d1 = -c.w2n[4 + k], d2 = -c.w2n[8 + k];
+            J0[k] = (pz * d0 - px * d2) * ipz2fx;
+            J1[k] = (pz * d1 - py * d2) * ipz2fy;
         }
+        // dRd{x,y,z} * (p - t), with dRidx = [0 0 0; 0 0 2; 0 -2 0] etc. applied to R^T
+        const double r0 = c.w2n[0] * pw[0] + c.w2n[1] * pw[1] + c.w2n[2] * pw[2];
+        const double r1 = c.w2n[4] * pw[0] + c.w2n[5] * pw[1] + c.w2n[6] * pw[2];
+        const double r2 = c.w2n[8] * pw[0] + c.w2n[9] * pw[1] + c.w2n[10] * pw[2];
+        const double q[3][3] = {{0.0, 2 * r2, -2 * r1}, {-2 * r2, 0.0, 2 * r0}, {2 * r1, -2 * r0, 0.0}};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            J0[3 + k] = (pz * q[k][0] - px * q[k][2]) * ipz2fx;
+            J1[3 + k] = (pz * q[k][1] - py * q[k][2]) * ipz2fy;
+        }
+        const double g0 = -ex * w, g1 = -ey * w;
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+        {
+#pragma unroll
+            for (int bcol = a; bcol < 6; bcol++)
+                acc[idx++] += (J0[a] * J0[bcol] + J1[a] * J1[bcol]) * w;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+            acc[21 + a] += J0[a] * g0 + J1[a] * g1;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (kWithSystem)
-    {
 #pragma unroll
-        for (int k = 0; k < kPoseSums; k++)
-        {
-            const double v = warp_sum(acc[k]);
-            if (lane == 0)
-                s.partial[warp][k] = v;
-        }
-    }
-    else
+    for (int k = 0; k < kPoseSums; k++)
     {
-        const double v = warp_sum(acc[0]);
+        const double v = warp_sum(acc[k]);
         if (lane == 0)
-            s.partial[warp][27] = v;
+            s.partial[warp][k] = v;
     }
     __syncthreads();
-    if (threadIdx.x < kPoseSums && (kWithSystem || threadIdx.x == 27))
+    if (threadIdx.x < kPoseSums)
     {
         double v = 0.0;
         for (int w = 0; w < nwarps; w++)
             v += s.partial[w][threadIdx.x];
-        s.sums[threadIdx.x] = v;
+        s.cta_sums[threadIdx.x] = v;
     }
-    __syncthreads();
+    cluster.sync();
+    if (rank == 0)
+    {
+        if (threadIdx.x < kPoseSums)
+        {
+            double v = 0.0;
+            for (int r = 0; r < nranks; r++)
+                v += *cluster.map_shared_rank(&s.cta_sums[threadIdx.x], r);
+            s.sums[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
 }
 
-// lvt_pnp_solver::compute_pose.  All threads of the block call it.  level / e2: per-edge scratch
-// (global).  On return (thread-uniform) pose_out holds the optimised pose, inlier[i] the marks.
-// Returns the inlier count.  blockDim.x must be a multiple of 32, <= 1024.
-__device__ inline int block_solve_pose(PoseShared &s, const double *xyz, const float2 *uv, int m, const PoseD &init,
-                                       const CamParams &cp, uint8_t *level, double *e2, uint8_t *inlier, PoseD *pose_out,
-                                       int *s_scan)
+// rank 0 publishes its camera and the continuation code to every CTA of the cluster
+template <class Cluster>
+__device__ inline int pose_broadcast(Cluster &cluster, PoseShared &s, int rank)
 {
+    cluster.sync();
+    if (rank != 0 && threadIdx.x == 0)
+    {
+        s.cam = *cluster.map_shared_rank(&s.cam, 0);
+        s.cont = *cluster.map_shared_rank(&s.cont, 0);
+    }
+    __syncthreads();
+    return s.cont;
+}
+
+// lvt_pnp_solver::compute_pose on a thread-block cluster.  Every thread of every CTA calls it.
+// level / e2 / inlier: per-edge scratch (global).  Rank 0 / thread 0 writes *pose_out and
+// *n_inliers_out.  Control flow is uniform across the cluster (driven by the broadcast code).
+template <class Cluster>
+__device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const double *xyz, const float2 *uv, int m,
+                                          const PoseD &init, const CamParams &cp, uint8_t *level, double *e2,
+                                          uint8_t *inlier, PoseD *pose_out, int *n_inliers_out)
+{
+    const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
     if (threadIdx.x == 0)
     {
-        CamState &c = s.cam;
+        CamState &c = s.cam; // the same arithmetic in every CTA: identical copies
         c.fx = cp.fx;
         c.fy = cp.fy;
         c.cx = cp.cx;
@@ -232,7 +303,7 @@ __device__ inline int block_solve_pose(PoseShared &s, const double *xyz, const f
         c.r = quat_normalized(q);
         cam_refresh(c);
     }
-    for (int i = threadIdx.x; i < m; i += blockDim.x)
+    for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
     {
         level[i] = 0;
         inlier[i] = 1;
@@ -240,126 +311,141 @@ __device__ inline int block_solve_pose(PoseShared &s, const double *xyz, const f
     }
     __syncthreads();
 
-    // thread-0 LM state
+    // LM state of rank 0 / thread 0 (OptimizationAlgorithmLevenberg::solve)
     double lambda = 0, ni = 2, current_chi = 0, rho = 0;
     double H[36], bvec[6], x[6];
     CamState backup;
-    int qmax = 0;
+    int qmax = 0, it = 0;
+    const bool boss = rank == 0 && threadIdx.x == 0;
+    auto load_system = [&]() {
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int bcol = a; bcol < 6; bcol++)
+            {
+                H[6 * a + bcol] = s.sums[idx];
+                H[6 * bcol + a] = s.sums[idx];
+                idx++;
+            }
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+            bvec[a] = s.sums[21 + a];
+    };
+    // one block-Jacobi preconditioned CG step on the single 6x6 block (LinearSolverPCG):
+    // d = (H + lambda I)^-1 b, x = (b.d / d.Ad) d; then SBACam::update
+    auto propose = [&]() {
+        backup = s.cam;
+        double d[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+            x[j] = 0.0;
+        bool solved = chol_solve6(H, lambda, bvec, d);
+        if (!solved)
+        {
+            double A[36];
+            for (int i = 0; i < 36; i++)
+                A[i] = H[i];
+            for (int j = 0; j < 6; j++)
+                A[7 * j] += lambda;
+            solved = solve6(A, bvec, d);
+        }
+        if (solved)
+        {
+            double dn = 0, dq = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+            {
+                dn += bvec[i] * d[i];
+                double Ad = lambda * d[i];
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+                    Ad += H[6 * i + j] * d[j];
+                dq += d[i] * Ad;
+            }
+            if (!(dn <= 1e-6 * dn))
+            {
+                const double alpha = dn / dq;
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    x[i] = alpha * d[i];
+            }
+        }
+        cam_update(s.cam, x);
+    };
 
     for (int pass = 0; pass < 2; pass++)
     {
-        // any active edge?  (initializeOptimization(0) with an empty active set does nothing)
-        int mine = 0;
-        for (int i = threadIdx.x; i < m; i += blockDim.x)
-            mine += (level[i] == 0);
-        int n_active;
-        block_exclusive_scan(mine, s_scan, &n_active);
-        if (n_active > 0)
+        // errors + linearisation at the starting state of this optimize()
+        pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks);
+        if (boss)
         {
-            for (int it = 0; it < 5; it++)
+            if (s.sums[28] == 0.0)
+                s.cont = 1; // initializeOptimization(0) with an empty active set: optimize() does nothing
+            else
             {
-                pose_evaluate<true>(s, xyz, uv, level, e2, m);
-                if (threadIdx.x == 0)
+                current_chi = s.sums[27];
+                load_system();
+                double max_diag = 0;
+                for (int j = 0; j < 6; j++)
+                    max_diag = fmax(fabs(H[7 * j]), max_diag);
+                lambda = 1e-5 * max_diag; // computeLambdaInit, _tau = 1e-5
+                ni = 2;
+                it = 0;
+                rho = 0;
+                qmax = 0;
+                propose();
+                s.cont = 0;
+            }
+        }
+        while (pose_broadcast(cluster, s, rank) == 0)
+        {
+            pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks); // the trial state
+            if (boss)
+            {
+                const double temp_chi = s.sums[27];
+                double scale = 0;
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+                    scale += x[j] * (lambda * x[j] + bvec[j]);
+                scale += 1e-3;
+                rho = (current_chi - temp_chi) / scale;
+                if (rho > 0 && isfinite(temp_chi))
                 {
-                    current_chi = s.sums[27];
-                    int idx = 0;
-                    for (int a = 0; a < 6; a++)
-                        for (int bcol = a; bcol < 6; bcol++)
-                        {
-                            H[6 * a + bcol] = s.sums[idx];
-                            H[6 * bcol + a] = s.sums[idx];
-                            idx++;
-                        }
-                    for (int a = 0; a < 6; a++)
-                        bvec[a] = s.sums[21 + a];
-                    if (it == 0)
-                    {
-                        double max_diag = 0;
-                        for (int j = 0; j < 6; j++)
-                            max_diag = fmax(fabs(H[7 * j]), max_diag);
-                        lambda = 1e-5 * max_diag; // computeLambdaInit, _tau = 1e-5
-                        ni = 2;
-                    }
+                    const double tt = 2 * rho - 1;
+                    double alpha = 1. - tt * tt * tt;
+                    alpha = fmin(alpha, 2. / 3.);
+                    lambda *= fmax(1. / 3., alpha);
+                    ni = 2;
+                    current_chi = temp_chi;
+                    load_system(); // the system of the next iteration
+                }
+                else
+                {
+                    lambda *= ni;
+                    ni *= 2;
+                    s.cam = backup; // the edges keep the rejected trial's error
+                }
+                qmax++;
+                if (rho < 0 && qmax < 10)
+                {
+                    propose(); // another trial of the same iteration
+                    s.cont = 0;
+                }
+                else if (qmax == 10 || rho == 0 || it == 4)
+                    s.cont = 1; // Terminate, or optimize(5) is through
+                else
+                {
+                    it++;
                     rho = 0;
                     qmax = 0;
+                    propose();
+                    s.cont = 0;
                 }
-                bool stop_iterations = false;
-                while (true) // trials of OptimizationAlgorithmLevenberg::solve
-                {
-                    if (threadIdx.x == 0)
-                    {
-                        backup = s.cam;
-                        double A[36];
-                        for (int i = 0; i < 36; i++)
-                            A[i] = H[i];
-                        for (int j = 0; j < 6; j++)
-                            A[7 * j] += lambda;
-                        // one block-Jacobi preconditioned CG step on a single block
-                        double d[6];
-                        for (int j = 0; j < 6; j++)
-                            x[j] = 0.0;
-                        if (solve6(A, bvec, d))
-                        {
-                            double dn = 0, dq = 0;
-                            for (int i = 0; i < 6; i++)
-                            {
-                                dn += bvec[i] * d[i];
-                                double Ad = 0;
-                                for (int j = 0; j < 6; j++)
-                                    Ad += A[6 * i + j] * d[j];
-                                dq += d[i] * Ad;
-                            }
-                            if (!(dn <= 1e-6 * dn))
-                            {
-                                const double alpha = dn / dq;
-                                for (int i = 0; i < 6; i++)
-                                    x[i] = alpha * d[i];
-                            }
-                        }
-                        cam_update(s.cam, x);
-                    }
-                    __syncthreads();
-                    pose_evaluate<false>(s, xyz, uv, level, e2, m);
-                    if (threadIdx.x == 0)
-                    {
-                        const double temp_chi = s.sums[27];
-                        double scale = 0;
-                        for (int j = 0; j < 6; j++)
-                            scale += x[j] * (lambda * x[j] + bvec[j]);
-                        scale += 1e-3;
-                        rho = (current_chi - temp_chi) / scale;
-                        if (rho > 0 && isfinite(temp_chi))
-                        {
-                            double alpha = 1. - pow((2 * rho - 1), 3);
-                            alpha = fmin(alpha, 2. / 3.);
-                            lambda *= fmax(1. / 3., alpha);
-                            ni = 2;
-                            current_chi = temp_chi;
-                        }
-                        else
-                        {
-                            lambda *= ni;
-                            ni *= 2;
-                            s.cam = backup; // the edges keep the rejected trial's error
-                        }
-                        qmax++;
-                        const bool again = (rho < 0 && qmax < 10);
-                        // 0: next iteration, 1: another trial, 2: terminate this optimize()
-                        s.cont = again ? 1 : ((qmax == 10 || rho == 0) ? 2 : 0);
-                    }
-                    __syncthreads();
-                    const int cont = s.cont;
-                    if (cont == 1)
-                        continue;
-                    stop_iterations = (cont == 2);
-                    break;
-                }
-                if (stop_iterations)
-                    break;
             }
         }
         // lvt_pnp_solver.cpp:109-116
-        for (int i = threadIdx.x; i < m; i += blockDim.x)
+        for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
         {
             if (e2[i] > kReprojectionTh2)
             {
@@ -369,20 +455,36 @@ __device__ inline int block_solve_pose(PoseShared &s, const double *xyz, const f
         }
         __syncthreads();
     }
-    int mine = 0;
-    for (int i = threadIdx.x; i < m; i += blockDim.x)
-        mine += inlier[i];
-    int n_inliers;
-    block_exclusive_scan(mine, s_scan, &n_inliers);
-    if (threadIdx.x == 0)
+    // inlier count through the same reduction path
     {
-        pose_out->q = s.cam.r;
-        pose_out->t[0] = s.cam.t[0];
-        pose_out->t[1] = s.cam.t[1];
-        pose_out->t[2] = s.cam.t[2];
+        double cnt = 0;
+        for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
+            cnt += inlier[i];
+        cnt = warp_sum(cnt);
+        if ((threadIdx.x & 31) == 0)
+            s.partial[threadIdx.x >> 5][0] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            double v = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++)
+                v += s.partial[w][0];
+            s.cta_sums[0] = v;
+        }
+        cluster.sync();
+        if (boss)
+        {
+            double v = 0;
+            for (int r = 0; r < nranks; r++)
+                v += *cluster.map_shared_rank(&s.cta_sums[0], r);
+            *n_inliers_out = (int)v;
+            pose_out->q = s.cam.r;
+            pose_out->t[0] = s.cam.t[0];
+            pose_out->t[1] = s.cam.t[1];
+            pose_out->t[2] = s.cam.t[2];
+        }
+        cluster.sync(); // nobody leaves while rank 0 still reads remote shared memory
     }
-    __syncthreads();
-    return n_inliers;
 }
 
 } // namespace lvtb

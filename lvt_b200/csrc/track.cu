@@ -1,37 +1,365 @@
-// The per-frame tracking kernel (one persistent CTA per sequence and frame) and the thin
-// kernels behind the seam ABI (lvtk_match_projected / lvtk_row_match / lvtk_solve_pose /
-// lvtk_triangulate), all built from the block-level routines of match.cuh, pose.cuh, track.cuh.
+// The per-frame tracking chain and the thin kernels behind the seam ABI (lvtk_match_projected /
+// lvtk_row_match / lvtk_solve_pose / lvtk_triangulate), all built from the block-level routines
+// of match.cuh, pose.cuh, track.cuh.
+//
+// lvt_system::perform_tracking (lvt/src/lvt_system.cpp:252-306) per frame, all on the device:
+//   mapcand_kernel    whole GPU   predict pose, project the map, candidate keys per map point
+//   track_a_kernel    1 CTA       greedy rounds over the key lists (+ radius x2 retry), marks,
+//                                 map bookkeeping, solver inputs, LOST decision
+//   pose_kernel       8-CTA cluster  motion-only BA (fp64 LM, Cauchy), reductions through DSMEM
+//   stagedcand        whole GPU   project the staged points with the new pose, candidate keys
+//   track_b_kernel    1 CTA       cull, staged rounds + promotion, triangulation policy,
+//                                 row-matching rounds, triangulation, state + result
+// The serial parts are instruction-latency bound, so the single-CTA kernels run 1024 threads and
+// keep fp64-heavy, register-hungry work out (pose has its own kernel); every data-parallel part
+// (candidate generation, projection, Jacobians) is spread over many SMs.  No host round trip:
+// all control flow (first frame, lost, retry, policy) is decided on the device through FrameCtl.
 #include "track.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lvtb
 {
 
-constexpr int kTrackThreads = 512;
+constexpr int kTrackThreads = 1024;
+constexpr int kCandWarps = 8;
+
+// per-frame hand-over between the kernels of the chain (device memory)
+struct FrameCtl
+{
+    int mode; // 0 frame finished by track_a (lost), 1 tracking continues, 2 first frame (track_b seeds the map)
+    int n_matches;
+    int inliers;
+    int pad;
+    PoseD pred, opt;
+    lvt_frame_info info;
+    long long cyc[8];
+    int rounds[4];
+};
 
 struct TrackArgs
 {
     TrackState *st;
+    FrameCtl *ctl;
     FrameResult *result;
     PointStore map, staged;
     const FeatDev *feats; // [2] left (or gray), right
     TrackParams tp;
     TrackScratch sc;
-    int owner_cap; // ints per owner array in dynamic shared memory
+    CandLists row_cand; // candidate keys of this frame's row matching (rowcand_kernel, extraction stream)
+    int owner_cap;      // ints per owner array in dynamic shared memory
 };
 
 struct TrackShared
 {
-    PoseShared pose;
     double W[24]; // world->camera of the left [0..11] and right [12..23] camera
-    PoseD pred, opt;
-    lvt_frame_info info;
-    int flag[2];
+    PoseD pose;
+    int flag[4];
     int scan[34];
     int ctrl[4];
 };
 
-// lvt_local_map::update_with_new_triangulation (lvt/src/lvt_local_map.cpp:331-353) for the pose
-// in sh.opt.  Returns (uniformly) the number of new points; updates *map_n / *staged_n (locals).
+#define LVT_PHASE(k)                                                                                                  \
+    if (threadIdx.x == 0)                                                                                             \
+    a.ctl->cyc[k] = clock64()
+
+// ---------------------------------------------------------------------------------------------
+// phase 1 of the matchers: candidate keys, one warp per query, the whole GPU
+// ---------------------------------------------------------------------------------------------
+struct MapCandArgs
+{
+    const TrackState *st; // nullptr: explicit pose / m (seam)
+    const FrameCtl *ctl;
+    int which;            // 0: map points under the predicted pose, 1: staged points under ctl->opt
+    int staged_threshold;
+    PoseD pose;
+    int m;
+    const double *xyz;
+    const uint32_t *desc;
+    const FeatDev *feat;
+    CamParams cam;
+    MatchScratch ms;
+    CandLists L;
+};
+
+__global__ void __launch_bounds__(kCandWarps * 32) mapcand_kernel(MapCandArgs a)
+{
+    __shared__ double W[12];
+    __shared__ uint32_t buf[kCandWarps][kMapCandCap];
+    int m = a.m;
+    if (a.st)
+    {
+        if (a.which == 0)
+        {
+            if (a.st->state != 2)
+                return; // first frame / lost: no projection matching
+            m = a.st->map_n;
+        }
+        else
+        {
+            if (a.ctl->mode != 1 || a.staged_threshold <= 0)
+                return;
+            m = a.st->staged_n;
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        PoseD pose = a.pose;
+        if (a.st && a.which == 0)
+        {
+            MotionState mm = a.st->motion; // a copy: track_a performs the real update
+            pose = motion_predict(mm, a.st->last_pose);
+        }
+        else if (a.st)
+            pose = a.ctl->opt;
+        world_to_camera(pose, W);
+    }
+    __syncthreads();
+    const FeatDev f = *a.feat;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int R = a.cam.tracking_radius;
+    const float r2 = (float)(R * R);
+    for (int q = blockIdx.x * kCandWarps + warp; q < m; q += gridDim.x * kCandWarps)
+    {
+        double u, v;
+        const bool vis = point_visible(W, a.cam, a.xyz[3 * q], a.xyz[3 * q + 1], a.xyz[3 * q + 2], &u, &v);
+        const float2 p = vis ? make_float2((float)u, (float)v) : make_float2(0.f, 0.f);
+        if (lane == 0)
+        {
+            a.ms.vis[q] = vis;
+            a.ms.proj[q] = p;
+        }
+        int n = 0;
+        if (vis)
+        {
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(a.desc + 8 * (size_t)q);
+            const uint4 q1 = *reinterpret_cast<const uint4 *>(a.desc + 8 * (size_t)q + 4);
+            WarpCollector col{buf[warp], kMapCandCap, 0, lane};
+            scan_projected_window(f, a.cam, p, r2, q0, q1, lane, col);
+            n = col.n;
+            if (n <= kMapCandCap)
+                warp_sort_store<kMapCandCap / 32>(buf[warp], n, a.L.keys + (size_t)q * kMapCandCap, lane);
+        }
+        if (lane == 0)
+            a.L.count[q] = n;
+    }
+}
+
+struct RowCandArgs
+{
+    const FeatDev *feats; // [2] left, right
+    CamParams cam;
+    CandLists L;
+};
+
+__global__ void __launch_bounds__(kCandWarps * 32) rowcand_kernel(RowCandArgs a)
+{
+    __shared__ uint32_t buf[kCandWarps][kRowCandCap];
+    const FeatDev fl = a.feats[0], fr = a.feats[1];
+    const int nl = *fl.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = blockIdx.x * kCandWarps + warp; q < nl; q += gridDim.x * kCandWarps)
+    {
+        const uint4 q0 = *reinterpret_cast<const uint4 *>(fl.desc + 8 * (size_t)q);
+        const uint4 q1 = *reinterpret_cast<const uint4 *>(fl.desc + 8 * (size_t)q + 4);
+        WarpCollector col{buf[warp], kRowCandCap, 0, lane};
+        scan_row_band(fr, a.cam, fl.xy[q], q0, q1, lane, col);
+        if (col.n <= kRowCandCap)
+            warp_sort_store<kRowCandCap / 32>(buf[warp], col.n, a.L.keys + (size_t)q * kRowCandCap, lane);
+        if (lane == 0)
+            a.L.count[q] = col.n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// track_a: find_matches (lvt/src/lvt_local_map.cpp:136-229) + the LOST decision
+// ---------------------------------------------------------------------------------------------
+__device__ void write_result(const TrackArgs &a, TrackState &S, const PoseD &pose, int state, int map_n, int staged_n)
+{
+    FrameCtl &c = *a.ctl;
+    S.frame_number += 1;
+    c.info.frame_number = S.frame_number;
+    c.info.state = state;
+    c.info.map_points_after = map_n;
+    c.info.staged_after = staged_n;
+    a.result->pose = pose;
+    a.result->info = c.info;
+    c.cyc[7] = clock64();
+    for (int k = 0; k < 8; k++)
+        a.result->cycles[k] = c.cyc[k];
+    for (int k = 0; k < 4; k++)
+        a.result->rounds[k] = c.rounds[k];
+}
+
+__global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
+{
+    extern __shared__ int s_owner[];
+    __shared__ TrackShared sh;
+    int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
+
+    TrackState &S = *a.st;
+    FrameCtl &ctl = *a.ctl;
+    const TrackParams &tp = a.tp;
+    const FeatDev fl = a.feats[0], fr = a.feats[1];
+    const int state0 = S.state;
+    const int nl = state0 == 3 ? 0 : min(*fl.n, a.owner_cap);
+    const int nr = (tp.sensor == 1 && state0 != 3) ? min(*fr.n, a.owner_cap) : 0;
+    const int map_n = S.map_n, staged_n = S.staged_n;
+    const PoseD last_pose = S.last_pose;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        lvt_frame_info z = {};
+        ctl.info = z;
+        ctl.info.n_features_left = nl;
+        ctl.info.n_features_right = nr;
+        for (int k = 0; k < 8; k++)
+            ctl.cyc[k] = 0;
+        for (int k = 0; k < 4; k++)
+            ctl.rounds[k] = 0;
+        ctl.n_matches = 0;
+        ctl.inliers = 0;
+        ctl.cyc[0] = clock64();
+    }
+    if (state0 == 3)
+    {
+        // lost: the last pose, nothing else (lvt/src/lvt_system.cpp:159-166)
+        if (threadIdx.x == 0)
+        {
+            ctl.mode = 0;
+            write_result(a, S, last_pose, 3, map_n, staged_n);
+        }
+        return;
+    }
+    if (state0 == 1)
+    {
+        if (threadIdx.x == 0)
+            ctl.mode = 2; // track_b seeds the map at the identity pose (lvt/src/lvt_system.cpp:185-193)
+        return;
+    }
+
+    // ---- predict (lvt/src/lvt_system.cpp:196); mapcand_kernel projected with the same prediction
+    if (threadIdx.x == 0)
+    {
+        sh.pose = motion_predict(S.motion, last_pose);
+        ctl.pred = sh.pose;
+        ctl.info.map_points_before = map_n;
+        ctl.info.staged_before = staged_n;
+    }
+    __syncthreads();
+    const int M = map_n;
+    const int R = tp.cam.tracking_radius;
+    const CandLists no_lists{nullptr, nullptr, 0};
+    int count = block_match_projected(a.sc.map_cand, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)(R * R), false, owner_a,
+                                      owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0]);
+    int retried = 0;
+    if (count < kNMatchesTh)
+    {
+        retried = 1; // marks reset, radius doubled, cell window unchanged (lvt_local_map.cpp:173-199)
+        count = block_match_projected(no_lists, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)((2 * R) * (2 * R)), false,
+                                      owner_a, owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[1]);
+    }
+    for (int j = threadIdx.x; j < nl; j += blockDim.x)
+        fl.matched[j] = owner_a[j] != kFree;
+    LVT_PHASE(1);
+    // bookkeeping (:201-224) + the solver's inputs, in map order
+    int n_matches = 0;
+    for (int i0 = 0; i0 < M; i0 += blockDim.x)
+    {
+        const int i = i0 + threadIdx.x;
+        int c = -3;
+        if (i < M)
+        {
+            c = a.sc.ms.vis[i] ? a.sc.ms.choice[i] : -2;
+            a.map.match_idx[i] = c;
+            if (c < 0)
+                a.map.counter[i] += 1;
+            else
+                a.map.age[i] += 1;
+        }
+        int total;
+        const int pos = block_exclusive_scan(c >= 0, sh.scan, &total);
+        if (c >= 0)
+        {
+            const int d = n_matches + pos;
+            a.sc.sol_xyz[3 * d] = a.map.xyz[3 * i];
+            a.sc.sol_xyz[3 * d + 1] = a.map.xyz[3 * i + 1];
+            a.sc.sol_xyz[3 * d + 2] = a.map.xyz[3 * i + 2];
+            a.sc.sol_uv[d] = fl.xy[c];
+        }
+        n_matches += total;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        ctl.info.tracked = n_matches;
+        ctl.info.retried_matching = retried;
+        ctl.n_matches = n_matches;
+        ctl.cyc[2] = clock64();
+        if (n_matches < tp.min_matches)
+        {
+            // lost: return the last pose (lvt/src/lvt_system.cpp:267-272,199-204)
+            S.state = 3;
+            ctl.mode = 0;
+            write_result(a, S, last_pose, 3, map_n, staged_n);
+        }
+        else
+        {
+            S.last_matches[0] = S.last_matches[1];
+            S.last_matches[1] = S.last_matches[2];
+            S.last_matches[2] = n_matches;
+            ctl.mode = 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pose: lvt_pnp_solver::compute_pose on an 8-CTA cluster
+// ---------------------------------------------------------------------------------------------
+struct PoseArgs
+{
+    FrameCtl *ctl; // nullptr: explicit inputs (seam)
+    const double *xyz;
+    const float2 *uv;
+    int m;
+    PoseD init;
+    CamParams cam;
+    uint8_t *level, *inlier;
+    double *e2;
+    PoseD *out;
+    int *n_inliers;
+};
+
+__global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_kernel(PoseArgs a)
+{
+    __shared__ PoseShared s;
+    cg::cluster_group cluster = cg::this_cluster();
+    int m = a.m;
+    PoseD init = a.init;
+    PoseD *out = a.out;
+    int *n_inl = a.n_inliers;
+    if (a.ctl)
+    {
+        if (a.ctl->mode != 1)
+            return; // uniform over the cluster
+        m = a.ctl->n_matches;
+        init = a.ctl->pred;
+        out = &a.ctl->opt;
+        n_inl = &a.ctl->inliers;
+        if (cluster.block_rank() == 0 && threadIdx.x == 0)
+            a.ctl->cyc[3] = clock64();
+    }
+    cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl);
+    if (a.ctl && cluster.block_rank() == 0 && threadIdx.x == 0)
+        a.ctl->cyc[4] = clock64();
+}
+
+// ---------------------------------------------------------------------------------------------
+// track_b: clean_untracked_points, update_staged_map_points, need_new_triangulation,
+// update_with_new_triangulation (lvt/src/lvt_local_map.cpp:331-413, lvt/src/lvt_system.cpp:287-334)
+// ---------------------------------------------------------------------------------------------
+// lvt_local_map::update_with_new_triangulation for the pose in sh.pose.  Returns (uniformly) the
+// number of new points; updates map_n / staged_n (locals).
 __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, const FeatDev &fl, int nl, const FeatDev &fr,
                                        int nr, bool dont_stage, int *owner_a, int *owner_b, int &map_n, int &staged_n)
 {
@@ -43,14 +371,14 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
 
     if (tp.sensor == 1)
     {
-        const int np = block_row_match(fl, nl, fr, nr, tp.cam, a.sc.row_choice, owner_a, owner_b, sh.flag, sh.scan,
-                                       a.sc.pair_query, a.sc.pair_train);
+        const int np = block_row_match(a.row_cand, fl, nl, fr, nr, tp.cam, a.sc.row_choice, a.sc.ms.items, owner_a,
+                                       owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3]);
         if (np == 0)
             return 0;
         if (threadIdx.x == 0)
         {
-            world_to_camera(sh.opt, sh.W);
-            const PoseD pr = right_pose(sh.opt, (double)tp.cam.baseline);
+            world_to_camera(sh.pose, sh.W);
+            const PoseD pr = right_pose(sh.pose, (double)tp.cam.baseline);
             world_to_camera(pr, sh.W + 12);
         }
         __syncthreads();
@@ -85,10 +413,10 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
         // triangulate_rgbd (lvt/src/lvt_local_map.cpp:231-256): fp32 back-projection of EVERY feature
         if (threadIdx.x == 0)
         {
-            double R[9];
-            quat_to_mat(sh.opt.q, R);
+            double Rm[9];
+            quat_to_mat(sh.pose.q, Rm);
             for (int i = 0; i < 9; i++)
-                sh.W[i] = R[i];
+                sh.W[i] = Rm[i];
         }
         __syncthreads();
         const float inv_fx = __fdiv_rn(1.0f, tp.cam.fx), inv_fy = __fdiv_rn(1.0f, tp.cam.fy);
@@ -103,7 +431,7 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
             const float y = __fmul_rn(__fmul_rn(__fsub_rn(p.y, tp.cam.cy), z), inv_fy);
             double w[3];
             for (int r = 0; r < 3; r++)
-                w[r] = (sh.W[3 * r] * (double)x + sh.W[3 * r + 1] * (double)y + sh.W[3 * r + 2] * (double)z) + sh.opt.t[r];
+                w[r] = (sh.W[3 * r] * (double)x + sh.W[3 * r + 1] * (double)y + sh.W[3 * r + 2] * (double)z) + sh.pose.t[r];
             copy_point(dst, d, w, fl.desc + 8 * (size_t)i, 0, 0, 0);
         }
         added = nl;
@@ -122,243 +450,156 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
     return added;
 }
 
-__global__ void __launch_bounds__(kTrackThreads, 1) track_frame_kernel(TrackArgs a)
+__global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
 {
     extern __shared__ int s_owner[];
     __shared__ TrackShared sh;
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
 
     TrackState &S = *a.st;
+    FrameCtl &ctl = *a.ctl;
     const TrackParams &tp = a.tp;
+    const int mode = ctl.mode;
+    if (mode == 0)
+        return; // track_a finished the frame (lost)
     const FeatDev fl = a.feats[0], fr = a.feats[1];
     const int nl = min(*fl.n, a.owner_cap);
     const int nr = tp.sensor == 1 ? min(*fr.n, a.owner_cap) : 0;
-    const int state0 = S.state;
     int map_n = S.map_n, staged_n = S.staged_n;
-    const PoseD last_pose = S.last_pose;
-
-    if (threadIdx.x == 0)
-    {
-        lvt_frame_info z = {};
-        sh.info = z;
-        sh.info.n_features_left = nl;
-        sh.info.n_features_right = nr;
-        sh.info.map_points_before = 0;
-    }
     __syncthreads();
+    LVT_PHASE(5);
 
-    PoseD out_pose = last_pose;
-    int new_state = state0;
-    bool accepted = false; // computed pose becomes m_last_pose
-
-    if (state0 == 1)
+    if (mode == 2)
     {
         // first frame: identity pose, seed the map (lvt/src/lvt_system.cpp:185-193)
         if (threadIdx.x == 0)
         {
-            sh.opt.q = Quat{1, 0, 0, 0};
-            sh.opt.t[0] = sh.opt.t[1] = sh.opt.t[2] = 0;
+            sh.pose.q = Quat{1, 0, 0, 0};
+            sh.pose.t[0] = sh.pose.t[1] = sh.pose.t[2] = 0;
         }
         __syncthreads();
         const int added = block_new_triangulation(a, sh, fl, nl, fr, nr, true, owner_a, owner_b, map_n, staged_n);
-        new_state = 2;
-        out_pose = sh.opt;
         if (threadIdx.x == 0)
         {
+            S.state = 2;
+            S.map_n = map_n;
+            S.staged_n = staged_n;
             S.last_matches[0] = map_n;
-            sh.info.triangulated = 1;
-            sh.info.new_points = added;
+            ctl.info.triangulated = 1;
+            ctl.info.new_points = added;
+            write_result(a, S, sh.pose, 2, map_n, staged_n);
         }
+        return;
     }
-    else if (state0 == 2)
+
+    if (threadIdx.x == 0)
     {
-        // ---- predict + find_matches (lvt/src/lvt_system.cpp:196, lvt/src/lvt_local_map.cpp:136-229)
-        if (threadIdx.x == 0)
-        {
-            sh.pred = motion_predict(S.motion, last_pose);
-            world_to_camera(sh.pred, sh.W);
-            sh.info.map_points_before = map_n;
-            sh.info.staged_before = staged_n;
-        }
-        __syncthreads();
-        const int M = map_n;
-        block_project(a.map.xyz, M, sh.W, tp.cam, a.sc.ms);
+        sh.pose = ctl.opt;
+        ctl.info.inliers = ctl.inliers;
+    }
+    __syncthreads();
+    // ---- clean_untracked_points (lvt/src/lvt_local_map.cpp:393-413)
+    const int M = map_n;
+    const int th = tp.untracked_threshold;
+    for (int i = threadIdx.x; i < M; i += blockDim.x)
+        if (a.map.counter[i] >= th && a.map.match_idx[i] >= 0)
+            fl.matched[a.map.match_idx[i]] = 0;
+    __syncthreads();
+    const int *cnt = a.map.counter;
+    map_n = block_compact_points(a.map, M, [cnt, th](int i) { return cnt[i] < th; }, sh.scan);
+    LVT_PHASE(6);
+
+    // ---- update_staged_map_points (lvt/src/lvt_local_map.cpp:355-391); stagedcand projected the
+    //      staged points with the optimised pose and listed their candidates
+    if (tp.staged_threshold > 0 && staged_n > 0)
+    {
+        const int Sn = staged_n;
         const int R = tp.cam.tracking_radius;
-        int count = block_match_projected(a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)(R * R), false, owner_a,
-                                          owner_b, sh.flag, nullptr, nullptr);
-        int retried = 0;
-        if (count < kNMatchesTh)
-        {
-            retried = 1; // marks reset, radius doubled, cell window unchanged (lvt_local_map.cpp:173-199)
-            count = block_match_projected(a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)((2 * R) * (2 * R)), false,
-                                          owner_a, owner_b, sh.flag, nullptr, nullptr);
-        }
+        block_match_projected(a.sc.map_cand, a.staged.desc, a.sc.ms, Sn, fl, nl, tp.cam, (float)(R * R), true, owner_a,
+                              owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[2]);
         for (int j = threadIdx.x; j < nl; j += blockDim.x)
-            fl.matched[j] = owner_a[j] != kFree;
-        // bookkeeping (:201-224) + the solver's inputs, in map order
-        int n_matches = 0;
-        for (int i0 = 0; i0 < M; i0 += blockDim.x)
+            if (owner_a[j] != kFree)
+                fl.matched[j] = 1;
+        // hit -> counter++; promote when counter == staged_threshold or the map is still below 250
+        // points.  Sequentially the map grows with every promotion, which is equivalent to:
+        // map_n + (#hits before this one) < 250.
+        const int map0 = map_n;
+        int hits = 0, promoted = 0;
+        uint8_t *flag = a.sc.level; // 0 erase, 1 keep staged, 2 promoted
+        for (int i0 = 0; i0 < Sn; i0 += blockDim.x)
         {
             const int i = i0 + threadIdx.x;
-            int c = -3;
-            if (i < M)
+            const bool hit = i < Sn && a.sc.ms.vis[i] && a.sc.ms.choice[i] >= 0;
+            int tot_h;
+            const int h = block_exclusive_scan(hit, sh.scan, &tot_h);
+            bool prom = false;
+            int cnt_new = 0;
+            if (hit)
             {
-                c = a.sc.ms.vis[i] ? a.sc.ms.choice[i] : -2;
-                a.map.match_idx[i] = c;
-                if (c < 0)
-                    a.map.counter[i] += 1;
-                else
-                    a.map.age[i] += 1;
+                cnt_new = a.staged.counter[i] + 1;
+                a.staged.counter[i] = cnt_new;
+                prom = (cnt_new == tp.staged_threshold) || (map0 + hits + h < kNMapPoints);
             }
-            int total;
-            const int pos = block_exclusive_scan(c >= 0, sh.scan, &total);
-            if (c >= 0)
+            int tot_p;
+            const int pp = block_exclusive_scan(prom, sh.scan, &tot_p);
+            if (i < Sn)
+                flag[i] = prom ? 2 : (hit ? 1 : 0);
+            if (prom)
             {
-                const int d = n_matches + pos;
-                a.sc.sol_xyz[3 * d] = a.map.xyz[3 * i];
-                a.sc.sol_xyz[3 * d + 1] = a.map.xyz[3 * i + 1];
-                a.sc.sol_xyz[3 * d + 2] = a.map.xyz[3 * i + 2];
-                a.sc.sol_uv[d] = fl.xy[c];
+                const int d = map0 + promoted + pp;
+                if (d < a.map.cap)
+                    copy_point(a.map, d, a.staged.xyz + 3 * i, a.staged.desc + 8 * (size_t)i, cnt_new, a.staged.age[i],
+                               a.staged.match_idx[i]);
             }
-            n_matches += total;
+            hits += tot_h;
+            promoted += tot_p;
         }
         __syncthreads();
-        if (threadIdx.x == 0)
+        map_n = map0 + promoted;
+        if (map_n > a.map.cap)
         {
-            sh.info.tracked = n_matches;
-            sh.info.retried_matching = retried;
+            if (threadIdx.x == 0)
+                S.error = LVTK_ERR_CAPACITY;
+            map_n = a.map.cap;
         }
-        if (n_matches < tp.min_matches)
-        {
-            new_state = 3; // lost: return the last pose (lvt/src/lvt_system.cpp:267-272,199-204)
-        }
+        staged_n = block_compact_points(a.staged, Sn, [flag](int i) { return flag[i] == 1; }, sh.scan);
+    }
+
+    // ---- need_new_triangulation (lvt/src/lvt_system.cpp:308-334)
+    if (threadIdx.x == 0)
+    {
+        int need;
+        if (tp.triangulation_policy == 2)
+            need = 1;
+        else if (tp.triangulation_policy == 3)
+            need = map_n < 1000;
         else
         {
-            if (threadIdx.x == 0)
-            {
-                S.last_matches[0] = S.last_matches[1];
-                S.last_matches[1] = S.last_matches[2];
-                S.last_matches[2] = n_matches;
-            }
-            // ---- pose (lvt/src/lvt_pnp_solver.cpp:60-128)
-            const int inl = block_solve_pose(sh.pose, a.sc.sol_xyz, a.sc.sol_uv, n_matches, sh.pred, tp.cam, a.sc.level,
-                                             a.sc.e2, a.sc.inlier, &sh.opt, sh.scan);
-            if (threadIdx.x == 0)
-                sh.info.inliers = inl;
-            // ---- clean_untracked_points (lvt/src/lvt_local_map.cpp:393-413)
-            const int th = tp.untracked_threshold;
-            for (int i = threadIdx.x; i < M; i += blockDim.x)
-                if (a.map.counter[i] >= th && a.map.match_idx[i] >= 0)
-                    fl.matched[a.map.match_idx[i]] = 0;
-            __syncthreads();
-            const int *cnt = a.map.counter;
-            map_n = block_compact_points(a.map, M, [cnt, th](int i) { return cnt[i] < th; }, sh.scan);
-
-            // ---- update_staged_map_points (lvt/src/lvt_local_map.cpp:355-391)
-            if (tp.staged_threshold > 0 && staged_n > 0)
-            {
-                const int Sn = staged_n;
-                if (threadIdx.x == 0)
-                    world_to_camera(sh.opt, sh.W);
-                __syncthreads();
-                block_project(a.staged.xyz, Sn, sh.W, tp.cam, a.sc.ms);
-                block_match_projected(a.staged.desc, a.sc.ms, Sn, fl, nl, tp.cam, (float)(R * R), true, owner_a, owner_b,
-                                      sh.flag, nullptr, nullptr);
-                for (int j = threadIdx.x; j < nl; j += blockDim.x)
-                    if (owner_a[j] != kFree)
-                        fl.matched[j] = 1;
-                // hit -> counter++; promote when counter == staged_threshold or the map is still
-                // below 250 points.  Sequentially the map grows with every promotion, which is
-                // equivalent to: map_n + (#hits before this one) < 250.
-                const int map0 = map_n;
-                int hits = 0, promoted = 0;
-                uint8_t *flag = a.sc.level; // 0 erase, 1 keep staged, 2 promoted
-                for (int i0 = 0; i0 < Sn; i0 += blockDim.x)
-                {
-                    const int i = i0 + threadIdx.x;
-                    const bool hit = i < Sn && a.sc.ms.vis[i] && a.sc.ms.choice[i] >= 0;
-                    int tot_h;
-                    const int h = block_exclusive_scan(hit, sh.scan, &tot_h);
-                    bool prom = false;
-                    int cnt_new = 0;
-                    if (hit)
-                    {
-                        cnt_new = a.staged.counter[i] + 1;
-                        a.staged.counter[i] = cnt_new;
-                        prom = (cnt_new == tp.staged_threshold) || (map0 + hits + h < kNMapPoints);
-                    }
-                    int tot_p;
-                    const int pp = block_exclusive_scan(prom, sh.scan, &tot_p);
-                    if (i < Sn)
-                        flag[i] = prom ? 2 : (hit ? 1 : 0);
-                    if (prom)
-                    {
-                        const int d = map0 + promoted + pp;
-                        if (d < a.map.cap)
-                            copy_point(a.map, d, a.staged.xyz + 3 * i, a.staged.desc + 8 * (size_t)i, cnt_new,
-                                       a.staged.age[i], a.staged.match_idx[i]);
-                    }
-                    hits += tot_h;
-                    promoted += tot_p;
-                }
-                __syncthreads();
-                map_n = map0 + promoted;
-                if (map_n > a.map.cap)
-                {
-                    if (threadIdx.x == 0)
-                        S.error = LVTK_ERR_CAPACITY;
-                    map_n = a.map.cap;
-                }
-                staged_n = block_compact_points(a.staged, Sn, [flag](int i) { return flag[i] == 1; }, sh.scan);
-            }
-
-            // ---- need_new_triangulation (lvt/src/lvt_system.cpp:308-334)
-            if (threadIdx.x == 0)
-            {
-                int need;
-                if (tp.triangulation_policy == 2)
-                    need = 1;
-                else if (tp.triangulation_policy == 3)
-                    need = map_n < 1000;
-                else
-                {
-                    need = 1;
-                    const float ratio = 0.99f;
-                    for (int i = 2; i > 0; --i)
-                        if ((float)S.last_matches[i] > __fmul_rn(ratio, (float)S.last_matches[i - 1]))
-                            need = 0;
-                }
-                sh.ctrl[0] = need;
-            }
-            __syncthreads();
-            if (sh.ctrl[0])
-            {
-                const int added = block_new_triangulation(a, sh, fl, nl, fr, nr, false, owner_a, owner_b, map_n, staged_n);
-                if (threadIdx.x == 0)
-                {
-                    sh.info.triangulated = 1;
-                    sh.info.new_points = added;
-                }
-            }
-            out_pose = sh.opt;
-            accepted = true;
+            need = 1;
+            const float ratio = 0.99f;
+            for (int i = 2; i > 0; --i)
+                if ((float)S.last_matches[i] > __fmul_rn(ratio, (float)S.last_matches[i - 1]))
+                    need = 0;
+        }
+        sh.ctrl[0] = need;
+    }
+    __syncthreads();
+    if (sh.ctrl[0])
+    {
+        const int added = block_new_triangulation(a, sh, fl, nl, fr, nr, false, owner_a, owner_b, map_n, staged_n);
+        if (threadIdx.x == 0)
+        {
+            ctl.info.triangulated = 1;
+            ctl.info.new_points = added;
         }
     }
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        S.frame_number += 1;
-        S.state = new_state;
         S.map_n = map_n;
         S.staged_n = staged_n;
-        if (accepted)
-            S.last_pose = out_pose;
-        sh.info.frame_number = S.frame_number;
-        sh.info.state = new_state;
-        sh.info.map_points_after = map_n;
-        sh.info.staged_after = staged_n;
-        a.result->pose = out_pose;
-        a.result->info = sh.info;
+        S.last_pose = sh.pose;
+        write_result(a, S, sh.pose, 2, map_n, staged_n);
     }
 }
 
@@ -381,14 +622,13 @@ __global__ void reset_state_kernel(TrackState *st)
 // ---------------------------------------------------------------------------------------------
 struct MatchSeamArgs
 {
-    const double *xyz;
     const uint32_t *pdesc;
     int m;
-    PoseD pose;
     const FeatDev *feat;
     CamParams cam;
     int retry_below;
     MatchScratch ms;
+    CandLists lists;
     int *match_idx;
     float *d1, *d2;
     int *count_retried; // [2]
@@ -398,24 +638,20 @@ struct MatchSeamArgs
 __global__ void __launch_bounds__(kTrackThreads, 1) match_seam_kernel(MatchSeamArgs a)
 {
     extern __shared__ int s_owner[];
-    __shared__ double W[12];
-    __shared__ int s_flag[2];
+    __shared__ int s_flag[4];
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
     const FeatDev f = *a.feat;
     const int n = min(*f.n, a.owner_cap);
-    if (threadIdx.x == 0)
-        world_to_camera(a.pose, W);
-    __syncthreads();
-    block_project(a.xyz, a.m, W, a.cam, a.ms);
     const int R = a.cam.tracking_radius;
-    int count = block_match_projected(a.pdesc, a.ms, a.m, f, n, a.cam, (float)(R * R), true, owner_a, owner_b, s_flag,
-                                      a.d1, a.d2);
+    const CandLists no_lists{nullptr, nullptr, 0};
+    int count = block_match_projected(a.lists, a.pdesc, a.ms, a.m, f, n, a.cam, (float)(R * R), true, owner_a, owner_b,
+                                      s_flag, a.d1, a.d2, nullptr);
     int retried = 0;
     if (count < a.retry_below)
     {
         retried = 1;
-        count = block_match_projected(a.pdesc, a.ms, a.m, f, n, a.cam, (float)((2 * R) * (2 * R)), false, owner_a,
-                                      owner_b, s_flag, a.d1, a.d2);
+        count = block_match_projected(no_lists, a.pdesc, a.ms, a.m, f, n, a.cam, (float)((2 * R) * (2 * R)), false,
+                                      owner_a, owner_b, s_flag, a.d1, a.d2, nullptr);
     }
     for (int j = threadIdx.x; j < n; j += blockDim.x)
         f.matched[j] = owner_a[j] != kFree;
@@ -440,43 +676,22 @@ struct RowSeamArgs
 {
     const FeatDev *feats; // [2]
     CamParams cam;
-    int *choice, *query, *train, *count;
+    CandLists lists;
+    int *choice, *items, *query, *train, *count;
     int owner_cap;
 };
 
 __global__ void __launch_bounds__(kTrackThreads, 1) row_seam_kernel(RowSeamArgs a)
 {
     extern __shared__ int s_owner[];
-    __shared__ int s_flag[2];
+    __shared__ int s_flag[4];
     __shared__ int s_scan[34];
     const FeatDev fl = a.feats[0], fr = a.feats[1];
     const int nl = min(*fl.n, a.owner_cap), nr = min(*fr.n, a.owner_cap);
-    const int np = block_row_match(fl, nl, fr, nr, a.cam, a.choice, s_owner, s_owner + a.owner_cap, s_flag, s_scan,
-                                   a.query, a.train);
+    const int np = block_row_match(a.lists, fl, nl, fr, nr, a.cam, a.choice, a.items, s_owner, s_owner + a.owner_cap,
+                                   s_flag, s_scan, a.query, a.train, nullptr);
     if (threadIdx.x == 0)
         *a.count = np;
-}
-
-struct PoseSeamArgs
-{
-    const double *xyz;
-    const float2 *uv;
-    int m;
-    PoseD init;
-    CamParams cam;
-    uint8_t *level, *inlier;
-    double *e2;
-    PoseD *out;
-};
-
-__global__ void __launch_bounds__(kTrackThreads, 1) pose_seam_kernel(PoseSeamArgs a)
-{
-    __shared__ PoseShared s;
-    __shared__ int s_scan[34];
-    __shared__ PoseD s_out;
-    block_solve_pose(s, a.xyz, a.uv, a.m, a.init, a.cam, a.level, a.e2, a.inlier, &s_out, s_scan);
-    if (threadIdx.x == 0)
-        *a.out = s_out;
 }
 
 struct TriSeamArgs
@@ -518,7 +733,8 @@ static int ensure_smem(int owner_cap)
     const int bytes = 2 * owner_cap * (int)sizeof(int);
     if (bytes > configured)
     {
-        LVT_CUDA_TRY(cudaFuncSetAttribute(track_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        LVT_CUDA_TRY(cudaFuncSetAttribute(track_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(match_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(row_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         configured = bytes;
@@ -526,15 +742,38 @@ static int ensure_smem(int owner_cap)
     return LVTK_OK;
 }
 
-int launch_track_frame(TrackState *st, FrameResult *result, const PointStore &map, const PointStore &staged,
-                       const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, int owner_cap,
-                       cudaStream_t stream)
+size_t frame_ctl_bytes() { return sizeof(FrameCtl); }
+
+int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists &L, cudaStream_t stream)
+{
+    RowCandArgs a{d_feats, cam, L};
+    LVT_TIMED(stream, K_ROWCAND, (rowcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(a)));
+    LVT_LAUNCH_CHECK(stream, "rowcand_kernel");
+    return LVTK_OK;
+}
+
+int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const PointStore &map, const PointStore &staged,
+                       const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
+                       int owner_cap, cudaStream_t stream)
 {
     if (int rc = ensure_smem(owner_cap))
         return rc;
-    TrackArgs a{st, result, map, staged, d_feats, tp, sc, owner_cap};
-    track_frame_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
-    LVT_LAUNCH_CHECK(stream, "track_frame_kernel");
+    FrameCtl *ctl = static_cast<FrameCtl *>(ctl_v);
+    const size_t smem = 2 * (size_t)owner_cap * sizeof(int);
+    MapCandArgs mc{st, ctl, 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
+    LVT_TIMED(stream, K_MAPCAND, (mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc)));
+    LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
+    TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, owner_cap};
+    LVT_TIMED(stream, K_TRACK_A, (track_a_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
+    LVT_LAUNCH_CHECK(stream, "track_a_kernel");
+    PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr};
+    LVT_TIMED(stream, K_POSE, (pose_kernel<<<kPoseCluster, kPoseThreads, 0, stream>>>(pa)));
+    LVT_LAUNCH_CHECK(stream, "pose_kernel");
+    MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
+    LVT_TIMED(stream, K_STAGEDCAND, (mapcand_kernel<<<148, kCandWarps * 32, 0, stream>>>(sc2)));
+    LVT_LAUNCH_CHECK(stream, "stagedcand_kernel");
+    LVT_TIMED(stream, K_TRACK_B, (track_b_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
+    LVT_LAUNCH_CHECK(stream, "track_b_kernel");
     return LVTK_OK;
 }
 
@@ -546,34 +785,39 @@ int launch_reset_state(TrackState *st, cudaStream_t stream)
 }
 
 int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const PoseD &pose, const FeatDev *d_feat,
-                      const CamParams &cam, int retry_below, const MatchScratch &ms, int *d_match_idx, float *d_d1,
-                      float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream)
+                      const CamParams &cam, int retry_below, const MatchScratch &ms, const CandLists &lists,
+                      int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream)
 {
     if (int rc = ensure_smem(owner_cap))
         return rc;
-    MatchSeamArgs a{d_xyz, d_pdesc, m, pose, d_feat, cam, retry_below, ms, d_match_idx, d_d1, d_d2, d_count_retried, owner_cap};
+    MapCandArgs mc{nullptr, nullptr, 0, 0, pose, m, d_xyz, d_pdesc, d_feat, cam, ms, lists};
+    mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc);
+    LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
+    MatchSeamArgs a{d_pdesc, m, d_feat, cam, retry_below, ms, lists, d_match_idx, d_d1, d_d2, d_count_retried, owner_cap};
     match_seam_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "match_seam_kernel");
     return LVTK_OK;
 }
 
-int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, int *d_choice, int *d_query, int *d_train, int *d_count,
-                    int owner_cap, cudaStream_t stream)
+int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandLists &lists, int *d_choice, int *d_items,
+                    int *d_query, int *d_train, int *d_count, int owner_cap, cudaStream_t stream)
 {
     if (int rc = ensure_smem(owner_cap))
         return rc;
-    RowSeamArgs a{d_feats, cam, d_choice, d_query, d_train, d_count, owner_cap};
+    if (int rc = launch_rowcand(d_feats, cam, lists, stream))
+        return rc;
+    RowSeamArgs a{d_feats, cam, lists, d_choice, d_items, d_query, d_train, d_count, owner_cap};
     row_seam_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "row_seam_kernel");
     return LVTK_OK;
 }
 
 int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD &init, const CamParams &cam,
-                     uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, cudaStream_t stream)
+                     uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, int *d_n_inliers, cudaStream_t stream)
 {
-    PoseSeamArgs a{d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out};
-    pose_seam_kernel<<<1, kTrackThreads, 0, stream>>>(a);
-    LVT_LAUNCH_CHECK(stream, "pose_seam_kernel");
+    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers};
+    pose_kernel<<<kPoseCluster, kPoseThreads, 0, stream>>>(a);
+    LVT_LAUNCH_CHECK(stream, "pose_kernel");
     return LVTK_OK;
 }
 

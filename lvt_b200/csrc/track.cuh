@@ -45,6 +45,9 @@ struct FrameResult
 {
     PoseD pose;
     lvt_frame_info info;
+    long long cycles[8]; // clock64() at the phase boundaries of the tracking kernel (profiling aid)
+    int rounds[4];       // fixed-point rounds: map pass, retry pass, staged pass, row matching
+    long long dbg[8];    // clock64() marks inside the map pass (profiling aid)
 };
 
 struct TrackParams
@@ -66,6 +69,7 @@ struct TrackScratch
     uint8_t *level;    // [pcap]
     uint8_t *inlier;   // [pcap]
     double *e2;        // [pcap]
+    CandLists map_cand; // [pcap][kMapCandCap] candidate keys of the map pass (mapcand_kernel)
     int *row_choice;   // [fcap]
     int *pair_query;   // [fcap]
     int *pair_train;   // [fcap]

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <climits>
 #include <deque>
+#include <map>
 #include <thread>
 
 namespace lvto
@@ -248,6 +249,15 @@ struct lvtk_ctx
     ImageBounds bounds;
 };
 
+namespace
+{
+struct HostPool
+{
+    std::vector<std::vector<uint8_t>> left, right;
+};
+std::map<void *, HostPool> g_pools;
+} // namespace
+
 static void write_pose(const Pose &pose, double R[3][3], double t[3])
 {
     const Mat3 m = qmat(pose.q);
@@ -296,6 +306,7 @@ LVT_API void lvt_destroy(lvt_handle h)
 {
     try
     {
+        g_pools.erase(h);
         delete static_cast<System *>(h);
     }
     catch (...)
@@ -453,6 +464,57 @@ LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
     brief_set_pairs(pairs);
     return 0;
 }
+
+/* resident-frame streaming: the oracle keeps the "pool" in host memory and runs lvt_track per frame */
+LVT_API int lvt_pool_reserve(lvt_handle h, int n_frames)
+{
+    if (!h || n_frames <= 0)
+        return -1;
+    HostPool &p = g_pools[h];
+    p.left.assign(n_frames, {});
+    p.right.assign(n_frames, {});
+    return 0;
+}
+LVT_API int lvt_pool_upload(lvt_handle h, int frame, const unsigned char *left, const unsigned char *right)
+{
+    auto it = g_pools.find(h);
+    if (it == g_pools.end() || frame < 0 || frame >= (int)it->second.left.size())
+        return -1;
+    const lvt_params_c &prm = static_cast<System *>(h)->params;
+    const size_t n = (size_t)prm.img_width * prm.img_height;
+    it->second.left[frame].assign(left, left + n);
+    it->second.right[frame].assign(right, right + n);
+    return 0;
+}
+LVT_API int lvt_track_pool(lvt_handle h, int first, int n, double *poses, lvt_frame_info *infos)
+{
+    auto it = g_pools.find(h);
+    if (it == g_pools.end() || first < 0 || n <= 0 || first + n > (int)it->second.left.size())
+        return -1;
+    System *vo = static_cast<System *>(h);
+    for (int i = 0; i < n; i++)
+    {
+        double R[3][3], t[3];
+        const Image l{it->second.left[first + i].data(), vo->params.img_height, vo->params.img_width, vo->params.img_width};
+        const Image r{it->second.right[first + i].data(), vo->params.img_height, vo->params.img_width, vo->params.img_width};
+        write_pose(vo->track(l, r, nullptr), R, t);
+        if (poses)
+        {
+            std::memcpy(poses + 12 * (size_t)i, R, sizeof(R));
+            std::memcpy(poses + 12 * (size_t)i + 9, t, sizeof(t));
+        }
+        if (infos)
+            infos[i] = vo->info;
+    }
+    return 0;
+}
+LVT_API double lvt_last_batch_ms(lvt_handle) { return 0.0; }
+LVT_API long lvt_launch_count(void) { return 0; }
+LVT_API void lvt_set_profiling(int) {}
+LVT_API int lvt_get_kernel_times(double *, long *, int) { return 0; }
+LVT_API void lvt_reset_kernel_times(void) {}
+LVT_API const char *lvt_kernel_name(int) { return ""; }
+LVT_API const char *lvtk_last_error(void) { return ""; }
 
 /* ---- seam ABI (include/lvt_kernels.h) ---------------------------------------------------- */
 LVT_API lvtk_ctx *lvtk_ctx_create(const lvt_params_c *p, int device)

@@ -196,8 +196,10 @@ def test_solve_pose(ctxs):
         uv = uv.astype(np.float32)
         qa, ta, ia = g.solve_pose(pts, uv, [1, 0, 0, 0], [0, 0, 0])
         qb, tb, ib = o.solve_pose(pts, uv, [1, 0, 0, 0], [0, 0, 0])
-        # fp64 with a different summation order: 1e-9 m / 1e-9 on the quaternion
-        assert np.abs(ta - tb).max() < 1e-9 and np.abs(qa - qb).max() < 1e-9
+        # fp64, different summation order and 6x6 factorisation: at convergence the LM accept/reject
+        # test (rho > 0) acts on rounding noise, so the two may stop one negligible step apart.
+        # Tolerance 1e-7 m / 1e-8 on the quaternion (north_star: 1e-3 m on the trajectory).
+        assert np.abs(ta - tb).max() < 1e-7 and np.abs(qa - qb).max() < 1e-8
         assert np.array_equal(ia, ib)
     qa, ta, ia = g.solve_pose(np.zeros((0, 3)), np.zeros((0, 2), np.float32), [1, 0, 0, 0], [1, 2, 3])
     assert np.allclose(ta, [1, 2, 3]) and np.allclose(qa, [1, 0, 0, 0])
@@ -307,3 +309,30 @@ def test_create_from_yaml_and_bad_args(cuda, tmp_path):
     # wrong image size: outputs untouched (the reference swallows the failure, lvt_c.cpp:63-88)
     R, t = vo.track(np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))
     assert not R.any() and not t.any() and vo.get_state() == 1
+
+
+def test_track_pool_equals_per_frame_calls(cuda, oracle):
+    """the pipelined resident-frame path returns exactly what lvt_track returns frame by frame"""
+    name, n = "kitti_synth", 24
+    p = configs.make_params(name)
+    st = make_stream(name, n, seed=5)
+    a, b, o = cuda.create(p, 1), cuda.create(p, 1), oracle.create(p, 1)
+    a.pool_reserve(n)
+    for t in range(n):
+        a.pool_upload(t, *st.frame(t))
+    poses, infos = a.track_pool(0, 10)
+    poses2, infos2 = a.track_pool(10, n - 10)
+    poses, infos = np.concatenate([poses, poses2]), infos + infos2
+    for t in range(n):
+        R, tt = b.track(*st.frame(t))
+        Ro, to = o.track(*st.frame(t))
+        assert infos[t] == b.frame_info() == o.frame_info()
+        assert np.array_equal(poses[t, :9].reshape(3, 3), R) and np.array_equal(poses[t, 9:], tt)  # same kernels, same bits
+        assert np.abs(tt - to).max() < 1e-8
+    assert a.last_batch_ms() > 0 and cuda.launch_count() > 0
+    cuda.reset_kernel_times()
+    cuda.set_profiling(True)
+    a.track_pool(n - 2, 2)
+    cuda.set_profiling(False)
+    kt = cuda.kernel_times()
+    assert kt["score_kernel"][1] == 2 and kt["track_a_kernel"][1] == 2 and kt["pose_kernel"][0] > 0

@@ -1,0 +1,35 @@
+import os, sys, ctypes as C
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import lvt_b200
+from lvt_b200 import configs, synth
+lib = lvt_b200.load()
+name = sys.argv[1] if len(sys.argv) > 1 else "kitti_synth"
+p = configs.make_params(name)
+n = 40
+st = synth.StereoStream(n_frames=n, seed=0, **configs.CONFIGS[name]["stream"])
+vo = lib.create(p, 1)
+vo.pool_reserve(n)
+for t in range(n):
+    vo.pool_upload(t, *st.frame(t))
+vo.track_pool(0, 10)
+poses, infos = vo.track_pool(10, 30)
+print("batch ms", vo.last_batch_ms(), "per frame", vo.last_batch_ms() / 30)
+cyc = (C.c_longlong * 8)()
+rnd = (C.c_int * 4)()
+names = ["A.match", "A.bookkeep", "(gap)", "pose", "(gap)", "B.clean", "B.staged+tri"]
+acc = np.zeros(7)
+for i in range(30):
+    lib.lib.lvt_debug_phase_cycles(C.c_void_p(vo.h), i, cyc, rnd)
+    c = np.array(list(cyc), dtype=np.float64)
+    d = np.diff(c[:8])
+    acc += d
+    if i < 12:
+        print(i, "rounds", list(rnd), "tri", infos[i]["triangulated"], "staged", infos[i]["staged_before"], " ".join("%s=%.0fus" % (nm, v / 1965.0) for nm, v in zip(names, d)))
+print("mean us:", " ".join("%s=%.1f" % (nm, v / 30 / 1965.0) for nm, v in zip(names, acc)), "total=%.1f" % (acc.sum() / 30 / 1965.0))
+lib.reset_kernel_times(); lib.set_profiling(True)
+vo.track_pool(20, 20, want_infos=False)
+lib.set_profiling(False)
+for k, (ms, cnt) in lib.kernel_times().items():
+    if cnt: print("%-22s %8.1f us x %d" % (k, 1e3 * ms / cnt, cnt))
