@@ -371,7 +371,10 @@ struct lvtk_ctx
     ImagePool pool;
     DetectWorkspace ws;
     int fcap = 0, pcap = 0;
-    FeatDev feats_h[4]; // two ping-pong sets of (left, right): extraction of frame t+1 overlaps tracking of t
+    static constexpr int kXStreams = 4; // extraction pipelines in flight (lvt_track_pool)
+    static constexpr int kSets = 6;     // feature sets (left, right) cycling through them
+    FeatDev feats_h[2 * kSets];
+    int last_set = 0; // set holding the features of the last tracked frame
     FeatDev *feats_d = nullptr;
     int *d_slots = nullptr;
     uint8_t *h_stage = nullptr; // pinned, 2 tightly packed images
@@ -388,8 +391,9 @@ struct lvtk_ctx
     uint8_t *d_ctl = nullptr; // FrameCtl: hand-over between the kernels of the tracking chain
     FrameResult *d_result = nullptr, *h_result = nullptr;
     // resident frame pool + pipelined streaming (lvt_pool_* / lvt_track_pool)
-    cudaStream_t stream_x = nullptr; // extraction runs here, tracking on `stream`
-    cudaEvent_t ev_extracted[2] = {nullptr, nullptr}, ev_tracked[2] = {nullptr, nullptr};
+    cudaStream_t xs[kXStreams] = {}; // extraction runs here, tracking on `stream`
+    DetectWorkspace wsx[kXStreams]; // wsx[0] == ws
+    cudaEvent_t ev_extracted[kSets] = {}, ev_tracked[kSets] = {};
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; // device time of the last lvt_track_pool call
     float last_batch_ms = 0.f;
     DeviceArena rarena;
@@ -401,7 +405,7 @@ struct lvtk_ctx
 
     PointStore map, staged;
     TrackScratch sc;
-    CandLists row_cand[2]; // per ping-pong feature set
+    CandLists row_cand[kSets]; // per feature set
 };
 
 static int ctx_check_error(lvtk_ctx *c)
@@ -448,13 +452,15 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     c->tp.staged_threshold = p.staged_threshold;
     c->tp.triangulation_policy = p.triangulation_policy;
     LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_x, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < lvtk_ctx::kXStreams; i++)
+        LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->xs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < lvtk_ctx::kSets; i++)
     {
         LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_extracted[i], cudaEventDisableTiming));
         LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_tracked[i], cudaEventDisableTiming));
-        LVT_CUDA_TRY(cudaEventCreate(&c->ev_batch[i]));
     }
+    for (int i = 0; i < 2; i++)
+        LVT_CUDA_TRY(cudaEventCreate(&c->ev_batch[i]));
 
     if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
         return rc;
@@ -472,6 +478,13 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     }
     if (int rc = make_detect_workspace(&c->ws, c->arena, c->dp.grid, p.img_height, c->pool.pitch, 2))
         return rc;
+    c->wsx[0] = c->ws;
+    for (int i = 1; i < lvtk_ctx::kXStreams; i++)
+    {
+        if (int rc = make_detect_workspace(&c->wsx[i], c->arena, c->dp.grid, p.img_height, c->pool.pitch, 2))
+            return rc;
+        c->wsx[i].error = c->ws.error; // one sticky error flag per context
+    }
 
     // capacities: ANMS keeps >= k+1 per tile (ties add a few); 2x headroom, at least 4096
     long want = 2L * c->dp.grid.count() * (p.max_keypoints_per_cell + 1);
@@ -483,10 +496,10 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     c->fcap = (int)fcap;
     c->pcap = std::max(32768, 8 * c->fcap);
     const int n_cells = c->cam.cells_x * c->cam.cells_y;
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 2 * lvtk_ctx::kSets; i++)
         if (int rc = make_feat(&c->feats_h[i], c->arena, c->fcap, n_cells, p.img_height))
             return rc;
-    int rc = c->arena.alloc(&c->feats_d, 4);
+    int rc = c->arena.alloc(&c->feats_d, 2 * lvtk_ctx::kSets);
     rc = rc ? rc : c->arena.alloc(&c->d_slots, 2);
     rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)p.img_width * p.img_height);
     rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->pcap);
@@ -514,7 +527,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->sc.map_cand.keys, (size_t)c->pcap * kMapCandCap);
     rc = rc ? rc : c->arena.alloc(&c->sc.map_cand.count, (size_t)c->pcap);
     c->sc.map_cand.cap = kMapCandCap;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < lvtk_ctx::kSets; i++)
     {
         rc = rc ? rc : c->arena.alloc(&c->row_cand[i].keys, (size_t)c->fcap * kRowCandCap);
         rc = rc ? rc : c->arena.alloc(&c->row_cand[i].count, (size_t)c->fcap);
@@ -556,20 +569,22 @@ static void ctx_free(lvtk_ctx *c)
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
-    if (c->stream_x)
-    {
-        cudaStreamSynchronize(c->stream_x);
-        cudaStreamDestroy(c->stream_x);
-    }
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < lvtk_ctx::kXStreams; i++)
+        if (c->xs[i])
+        {
+            cudaStreamSynchronize(c->xs[i]);
+            cudaStreamDestroy(c->xs[i]);
+        }
+    for (int i = 0; i < lvtk_ctx::kSets; i++)
     {
         if (c->ev_extracted[i])
             cudaEventDestroy(c->ev_extracted[i]);
         if (c->ev_tracked[i])
             cudaEventDestroy(c->ev_tracked[i]);
+    }
+    for (int i = 0; i < 2; i++)
         if (c->ev_batch[i])
             cudaEventDestroy(c->ev_batch[i]);
-    }
     c->rarena.release();
     if (c->h_results)
         cudaFreeHost(c->h_results);
@@ -702,6 +717,7 @@ struct System
     int run_tracking(PoseD *out)
     {
         lvtk_ctx *c = ctx;
+        c->last_set = 0;
         if (int rc = launch_index(c->feats_d, sensor == 1 ? 2 : 1, c->cam, c->stream))
             return rc;
         if (sensor == 1)
@@ -841,34 +857,41 @@ struct System
             return LVTK_ERR_ARG;
         // the batch is timed on the device: first extraction launch .. last result copy
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
-        LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream_x, c->ev_batch[0], 0));
+        for (int x = 0; x < lvtk_ctx::kXStreams; x++)
+            LVT_CUDA_TRY(cudaStreamWaitEvent(c->xs[x], c->ev_batch[0], 0));
         for (int i = 0; i < n; i++)
         {
-            const int par = i & 1;
-            if (i >= 2)
-                LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream_x, c->ev_tracked[par], 0));
+            // frame i: extraction pipeline i % kXStreams, feature set i % kSets.  Extraction is
+            // state-free, so up to kXStreams frames are extracted concurrently while the tracking
+            // stream consumes them in order; a set is reused only after its frame has been tracked.
+            const int set = i % lvtk_ctx::kSets, x = i % lvtk_ctx::kXStreams;
+            cudaStream_t sx = c->xs[x];
+            if (i >= lvtk_ctx::kSets)
+                LVT_CUDA_TRY(cudaStreamWaitEvent(sx, c->ev_tracked[set], 0));
             const int *slots = c->d_slot_table + 2 * (size_t)(first + i);
-            FeatDev *feats = c->feats_d + 2 * par;
-            if (int rc = launch_detect(c->rpool, c->ws, c->dp, slots, 2, feats, kBriefBorder, 1, c->stream_x))
+            FeatDev *feats = c->feats_d + 2 * set;
+            if (int rc = launch_detect(c->rpool, c->wsx[x], c->dp, slots, 2, feats, kBriefBorder, 1, sx))
                 return rc;
-            if (int rc = launch_brief(c->rpool, slots, 2, feats, c->stream_x))
+            if (int rc = launch_brief(c->rpool, slots, 2, feats, sx))
                 return rc;
-            if (int rc = launch_index(feats, 2, c->cam, c->stream_x))
+            if (int rc = launch_index(feats, 2, c->cam, sx))
                 return rc;
-            if (int rc = launch_rowcand(feats, c->cam, c->row_cand[par], c->stream_x))
+            if (int rc = launch_rowcand(feats, c->cam, c->row_cand[set], sx))
                 return rc;
-            LVT_CUDA_TRY(cudaEventRecord(c->ev_extracted[par], c->stream_x));
-            LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_extracted[par], 0));
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_extracted[set], sx));
+            LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_extracted[set], 0));
             if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_results + i, c->map, c->staged, feats, c->tp, c->sc,
-                                            c->row_cand[par], c->fcap, c->stream))
+                                            c->row_cand[set], c->fcap, c->stream))
                 return rc;
-            LVT_CUDA_TRY(cudaEventRecord(c->ev_tracked[par], c->stream));
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_tracked[set], c->stream));
+            c->last_set = set;
         }
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_results, c->d_results, sizeof(FrameResult) * (size_t)n, cudaMemcpyDeviceToHost,
                                      c->stream));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[1], c->stream));
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        LVT_CUDA_TRY(cudaStreamSynchronize(c->stream_x));
+        for (int x = 0; x < lvtk_ctx::kXStreams; x++)
+            LVT_CUDA_TRY(cudaStreamSynchronize(c->xs[x]));
         LVT_CUDA_TRY(cudaEventElapsedTime(&c->last_batch_ms, c->ev_batch[0], c->ev_batch[1]));
         if (int e = ctx_check_error(c))
             return e;
@@ -1052,7 +1075,7 @@ LVT_API int lvt_debug_get_features(lvt_handle h, int which, float *kps_xy, unsig
         return -1;
     lvtk_ctx *c = vo->ctx;
     cudaSetDevice(c->device);
-    const FeatDev &f = c->feats_h[which];
+    const FeatDev &f = c->feats_h[2 * c->last_set + which];
     int n = 0;
     if (cudaMemcpy(&n, f.n, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -1;

@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Turn gpurun_out/ ncu artefacts into the small text summaries committed under profiles/.
+    python tools/summarize_profiles.py <tag>      e.g. r1
+reads gpurun_out/launches_<tag>.csv and gpurun_out/<tag>_*.ncu-rep (needs `ncu` on PATH)."""
+import csv
+import glob
+import io
+import os
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__cluster_size", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__t_bytes.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+
+
+def launches(tag):
+    path = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
+    if not os.path.exists(path):
+        return None
+    lines = [ln for ln in open(path, errors="ignore") if ln.startswith('"')]
+    rows = list(csv.reader(io.StringIO("".join(lines))))
+    hdr = rows[0]
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        name = r[ik].split("(")[0].replace("lvtb::", "")
+        v = float(r[iv].replace(",", ""))
+        v = v / 1e3 if r[iu] in ("ns", "nsecond") else v  # -> us
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    out = ["# ncu launch list summary (%s)" % tag, "",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 420 python bench.py --steps 2 --warmup 1`",
+           "(cold-cache, serialised launches: compare SHARES, not absolutes)", "",
+           "| kernel | launches | avg us | total us | share |", "|---|---:|---:|---:|---:|"]
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append("| %s | %d | %.2f | %.1f | %.1f%% |" % (k, n, t / n, t, 100 * t / tot))
+    out.append("")
+    out.append("total captured device time: %.1f us over %d launches" % (tot, sum(a[0] for a in agg.values())))
+    return "\n".join(out) + "\n"
+
+
+def full(rep):
+    r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+    rows = list(csv.reader(io.StringIO(r.stdout)))
+    if len(rows) < 3:
+        return None
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
+    out = ["## %s  (%s)" % (name, os.path.basename(rep)), "", "| metric | value | unit |", "|---|---:|---|"]
+    for k in KEYS:
+        if k in d:
+            out.append("| %s | %s | %s |" % (k, d[k][0], d[k][1]))
+    try:
+        rd = float(d["dram__bytes_read.sum"][0].replace(",", ""))
+        wr = float(d["dram__bytes_write.sum"][0].replace(",", ""))
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = rd * mult.get(d["dram__bytes_read.sum"][1], 1) + wr * mult.get(d["dram__bytes_write.sum"][1], 1)
+        out.append("| **traffic = dram read + write** | %.0f | byte |" % traffic)
+    except Exception:
+        pass
+    return "\n".join(out) + "\n"
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    os.makedirs(OUT, exist_ok=True)
+    s = launches(tag)
+    if s:
+        open(os.path.join(OUT, "%s_launches.md" % tag), "w").write(s)
+        print(s)
+    parts = ["# ncu --set full captures (%s): `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 6 -c 1 "
+             "python tools/probe/phase_probe.py`\n" % tag]
+    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "%s_*.ncu-rep" % tag))):
+        f = full(rep)
+        if f:
+            parts.append(f)
+    if len(parts) > 1:
+        open(os.path.join(OUT, "%s_ncu_full.md" % tag), "w").write("\n".join(parts))
+        print("\n".join(parts)[:3000])
+
+
+if __name__ == "__main__":
+    main()
