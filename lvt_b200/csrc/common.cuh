@@ -43,6 +43,7 @@ enum KernelId
     K_POSE,
     K_STAGEDCAND,
     K_TRACK_B,
+    K_NMS_RESOLVE,
     K_COUNT
 };
 bool prof_enabled();

@@ -255,6 +255,7 @@ int make_detect_workspace(DetectWorkspace *ws, DeviceArena &arena, const TileGri
     rc = rc ? rc : arena.alloc(&ws->tile_count, nt);
     rc = rc ? rc : arena.alloc(&ws->tile_overflow, nt);
     rc = rc ? rc : arena.alloc(&ws->tile_out_count, nt);
+    rc = rc ? rc : arena.alloc(&ws->cand_count, (size_t)batch);
     rc = rc ? rc : arena.alloc(&ws->retry, (size_t)batch);
     rc = rc ? rc : arena.alloc(&ws->error, 1);
     return rc;
@@ -1220,7 +1221,7 @@ LVT_API const char *lvt_kernel_name(int id)
     static const char *names[K_COUNT] = {"score_kernel", "nms_kernel", "nms_fallback_kernel", "tile_kernel", "gather_kernel",
                                          "clear_counts_kernel", "brief_kernel", "index_kernel", "track_a_kernel",
                                          "mapcand_kernel", "rowcand_kernel", "pose_kernel", "stagedcand_kernel",
-                                         "track_b_kernel"};
+                                         "track_b_kernel", "nms_resolve_kernel"};
     return id >= 0 && id < K_COUNT ? names[id] : "";
 }
 

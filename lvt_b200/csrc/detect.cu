@@ -19,6 +19,9 @@
 //                      <200-corner retry.
 #include "extract.cuh"
 #include "introsort.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace lvtb
 {
@@ -150,6 +153,8 @@ struct NmsArgs
     const uint8_t *score;
     uint32_t *tile_list;
     int *tile_count, *tile_overflow, *error;
+    uint32_t *cand;   // [batch][rows * pitch] local maxima that need their component examined
+    int *cand_count;  // [batch]
     const int *retry; // nullptr on the first pass
     TileGrid grid;
     int pitch, rows, cols, tile_cap, n_tiles;
@@ -244,6 +249,8 @@ __device__ int replay_component(const uint32_t *pts, const uint8_t *sc, int n)
     return 0;
 }
 
+// first look at a corner pixel: beaten by a 4-neighbour -> dropped; isolated -> survivor; otherwise
+// it is a local maximum whose component has to be examined (nms_resolve_kernel)
 __device__ void nms_pixel(const NmsArgs &a, int b, const uint8_t *sm, int x, int y, int s)
 {
     if (!a.nonmax)
@@ -265,9 +272,29 @@ __device__ void nms_pixel(const NmsArgs &a, int b, const uint8_t *sm, int x, int
         emit_survivor(a, b, x, y, s); // isolated corner
         return;
     }
-    // flood the component; give up as soon as anything larger shows up
+    const int pos = atomicAdd(&a.cand_count[b], 1);
+    a.cand[(size_t)b * a.rows * a.pitch + pos] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+}
+
+// a local maximum: flood its component, decide whether it is the component's survivor
+__device__ void nms_resolve(const NmsArgs &a, int b, const uint8_t *sm, int x, int y, int s)
+{
+    auto score_at = [&](int xx, int yy) -> int {
+        if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
+            return 0;
+        const int v = sm[(size_t)yy * a.pitch + xx];
+        return v >= a.threshold ? v : 0;
+    };
+    // flood the component; give up as soon as anything larger shows up.  Visited test: linear
+    // search while the component is small, then a 64x32-pixel bitmap around the start pixel
+    // (pixels outside that window keep the linear search).
     uint32_t pts[kCompCap];
     uint8_t sc[kCompCap];
+    uint32_t bm[64];
+    bool use_bm = false;
+    const int wx0 = x - 32, wy0 = y - 16;
+    auto in_win = [&](int qx, int qy) { return (unsigned)(qx - wx0) < 64u && (unsigned)(qy - wy0) < 32u; };
+    auto bm_set = [&](int qx, int qy) { bm[(qy - wy0) * 2 + ((qx - wx0) >> 5)] |= 1u << ((qx - wx0) & 31); };
     int n = 1, head = 0;
     bool tie = false;
     pts[0] = ((uint32_t)y << 16) | (uint32_t)x;
@@ -276,19 +303,27 @@ __device__ void nms_pixel(const NmsArgs &a, int b, const uint8_t *sm, int x, int
     {
         const uint32_t p = pts[head++];
         const int px = (int)(p & 0xFFFFu), py = (int)(p >> 16);
+        // the four neighbour loads are independent: issue them together
+        int vv[4];
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+            vv[d] = score_at(px + (d == 0) - (d == 1), py + (d == 2) - (d == 3));
+        if (max(max(vv[0], vv[1]), max(vv[2], vv[3])) > s)
+            return;
 #pragma unroll
         for (int d = 0; d < 4; d++)
         {
             const int qx = px + (d == 0) - (d == 1), qy = py + (d == 2) - (d == 3);
-            const int v = score_at(qx, qy);
+            const int v = vv[d];
             if (v == 0)
                 continue;
-            if (v > s)
-                return;
             const uint32_t q = ((uint32_t)qy << 16) | (uint32_t)qx;
             bool seen = false;
-            for (int j = 0; j < n; j++)
-                seen |= (pts[j] == q);
+            if (use_bm && in_win(qx, qy))
+                seen = (bm[(qy - wy0) * 2 + ((qx - wx0) >> 5)] >> ((qx - wx0) & 31)) & 1u;
+            else
+                for (int j = 0; j < n; j++)
+                    seen |= (pts[j] == q);
             if (seen)
                 continue;
             if (n == kCompCap)
@@ -301,6 +336,20 @@ __device__ void nms_pixel(const NmsArgs &a, int b, const uint8_t *sm, int x, int
             pts[n] = q;
             sc[n] = (uint8_t)v;
             n++;
+            if (use_bm && in_win(qx, qy))
+                bm_set(qx, qy);
+            if (!use_bm && n == 16)
+            {
+                for (int k = 0; k < 64; k++)
+                    bm[k] = 0;
+                for (int j = 0; j < n; j++)
+                {
+                    const int jx = (int)(pts[j] & 0xFFFFu), jy = (int)(pts[j] >> 16);
+                    if (in_win(jx, jy))
+                        bm_set(jx, jy);
+                }
+                use_bm = true;
+            }
         }
     }
     if (!tie)
@@ -348,6 +397,21 @@ __global__ void __launch_bounds__(128) nms_kernel(NmsArgs a)
         const int s = (word >> (8 * k)) & 0xFF;
         if (s >= a.threshold && s != 0 && xw * 4 + k < a.cols)
             nms_pixel(a, b, sm, xw * 4 + k, y, s);
+    }
+}
+
+// one thread per local maximum, densely packed (the marking kernel above is a coalesced sweep)
+__global__ void __launch_bounds__(128) nms_resolve_kernel(NmsArgs a)
+{
+    const int b = blockIdx.y;
+    if (a.retry && !a.retry[b])
+        return;
+    const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
+    const int n = a.cand_count[b];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t c = a.cand[(size_t)b * a.rows * a.pitch + i];
+        nms_resolve(a, b, sm, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24));
     }
 }
 
@@ -443,11 +507,113 @@ struct TileArgs
     const int *retry;
     TileGrid grid;
     int tile_cap, n_tiles, max_per_cell;
+    long long *dbg; // optional clock64() marks [tile][8]
 };
 
 constexpr int kTileSmemCap = 8192; // tiles with more survivors work out of global scratch
-constexpr int kTileThreads = 256;
-constexpr int kTileSmemBytes = 3 * kTileSmemCap * (int)sizeof(uint32_t);
+constexpr int kTileThreads = 1024;
+constexpr int kTileRanges = kTileSmemCap / 8 + 2; // ranges alive in one level of the introsort schedule
+constexpr int kTileSmemBytes = 3 * kTileSmemCap * (int)sizeof(uint32_t) + 2 * kTileRanges * (int)sizeof(isort::LevelRange);
+
+// the same schedule run by ONE warp (lane per range, __syncwarp between levels) so that the other
+// warps of the CTA can compute the suppression radii at the same time
+__device__ void warp_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, volatile int *s_cnt)
+{
+    const int lane = threadIdx.x & 31;
+    if (n <= 1)
+        return;
+    int lg = 0;
+    for (int v = n; v > 1; v >>= 1)
+        lg++;
+    if (lane == 0)
+    {
+        q0[0] = isort::LevelRange{0, n, 2 * lg};
+        s_cnt[0] = 1;
+        s_cnt[1] = 0;
+    }
+    __syncwarp();
+    isort::LevelRange *cur = q0, *nxt = q1;
+    int which = 0;
+    while (true)
+    {
+        const int ncur = s_cnt[which];
+        if (ncur == 0)
+            break;
+        for (int i = lane; i < ncur; i += 32)
+        {
+            const isort::LevelRange r = cur[i];
+            if (r.last - r.first <= 16)
+            {
+                isort::insertion_sort(a + r.first, a + r.last);
+                continue;
+            }
+            isort::LevelRange l, rr;
+            if (isort::split_range(a, r, l, rr))
+            {
+                const int slot = atomicAdd((int *)&s_cnt[which ^ 1], 2);
+                nxt[slot] = l;
+                nxt[slot + 1] = rr;
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            s_cnt[which] = 0;
+        which ^= 1;
+        isort::LevelRange *t = cur;
+        cur = nxt;
+        nxt = t;
+        __syncwarp();
+    }
+}
+
+// std::sort's permutation, one thread per range of the current recursion level (introsort.cuh)
+__device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, int *s_cnt)
+{
+    if (n <= 1)
+        return;
+    int lg = 0;
+    for (int v = n; v > 1; v >>= 1)
+        lg++;
+    if (threadIdx.x == 0)
+    {
+        q0[0] = isort::LevelRange{0, n, 2 * lg};
+        s_cnt[0] = 1;
+        s_cnt[1] = 0;
+    }
+    __syncthreads();
+    isort::LevelRange *cur = q0, *nxt = q1;
+    int which = 0;
+    while (true)
+    {
+        const int ncur = s_cnt[which];
+        if (ncur == 0)
+            break;
+        for (int i = threadIdx.x; i < ncur; i += blockDim.x)
+        {
+            const isort::LevelRange r = cur[i];
+            if (r.last - r.first <= 16)
+            {
+                isort::insertion_sort(a + r.first, a + r.last);
+                continue;
+            }
+            isort::LevelRange l, rr;
+            if (isort::split_range(a, r, l, rr))
+            {
+                const int slot = atomicAdd(&s_cnt[which ^ 1], 2);
+                nxt[slot] = l;
+                nxt[slot + 1] = rr;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_cnt[which] = 0;
+        which ^= 1;
+        isort::LevelRange *t = cur;
+        cur = nxt;
+        nxt = t;
+        __syncthreads();
+    }
+}
 
 __device__ void block_bitonic_sort(uint32_t *keys, int P)
 {
@@ -478,6 +644,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
 {
     extern __shared__ uint32_t s_dyn[];
     uint32_t *s_keys = s_dyn, *s_rad = s_dyn + kTileSmemCap, *s_perm = s_dyn + 2 * kTileSmemCap;
+    isort::LevelRange *s_q0 = reinterpret_cast<isort::LevelRange *>(s_dyn + 3 * kTileSmemCap), *s_q1 = s_q0 + kTileRanges;
+    __shared__ int s_cnt[2];
     __shared__ int s_hist[256];
     __shared__ int s_scan[34];
     __shared__ uint32_t s_prefix;
@@ -486,6 +654,10 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     const int t = blockIdx.x, b = blockIdx.y;
     if (a.retry && !a.retry[b])
         return;
+#define LVT_TDBG(k)                                                                                                   \
+    if (a.dbg && threadIdx.x == 0)                                                                                    \
+    a.dbg[(b * a.n_tiles + t) * 8 + k] = clock64()
+    LVT_TDBG(0);
     const int tx = t % a.grid.nx, ty = t / a.grid.nx;
     const int x0 = tx * a.grid.cell, y0 = ty * a.grid.cell, tw = a.grid.tile_w(tx);
     const size_t base = ((size_t)b * a.n_tiles + t) * a.tile_cap;
@@ -535,18 +707,24 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
         return;
     }
 
+    LVT_TDBG(1);
     // ---- ANMS (lvt_image_features_handler.cpp:34-83) ------------------------------------------
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         perm[i] = ((keys[i] & 0xFFu) << 24) | (uint32_t)i;
     __syncthreads();
-    if (threadIdx.x == 0)
+    // :38-41, std::sort's exact permutation -- warp 0 -- while the other warps compute the radii
+    if (threadIdx.x < 32)
     {
-        isort::sort(perm, n); // :38-41, std::sort's exact permutation
+        if (small)
+            warp_introsort(perm, n, s_q0, s_q1, s_cnt);
+        else if (threadIdx.x == 0)
+            isort::sort(perm, n); // more survivors than fit in shared memory (pathological): sequential replay
+        LVT_TDBG(2);
     }
     else
     {
         // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own
-        for (int i = threadIdx.x - 1; i < n; i += blockDim.x - 1)
+        for (int i = threadIdx.x - 32; i < n; i += blockDim.x - 32)
         {
             const uint32_t ki = keys[i];
             // response_j > 1.11f * response_i in fp32  <=>  response_j >= floor(thr) + 1 (integers)
@@ -565,8 +743,11 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
             }
             rad[i] = best;
         }
+        if (a.dbg && threadIdx.x == 32)
+            a.dbg[(b * a.n_tiles + t) * 8 + 3] = clock64();
     }
     __syncthreads();
+    LVT_TDBG(4);
 
     // :66-71  decision = radiiSorted[num_to_keep]  (descending) -> MSB-first radix select
     if (threadIdx.x == 0)
@@ -585,21 +766,50 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
             if ((rad[i] & mask) == prefix)
                 atomicAdd(&s_hist[(rad[i] >> shift) & 0xFF], 1);
         __syncthreads();
-        if (threadIdx.x == 0)
+        if (threadIdx.x < 32)
         {
-            int k = s_k, d = 255;
-            for (; d > 0; d--)
+            // walk the 256 bins from the top: lane l owns bins 255-8l .. 248-8l
+            const int lane = threadIdx.x;
+            int mine = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                mine += s_hist[255 - 8 * lane - u];
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                if (k < s_hist[d])
-                    break;
-                k -= s_hist[d];
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += v;
             }
-            s_k = k;
-            s_prefix = prefix | ((uint32_t)d << shift);
+            const int k0 = s_k;
+            const bool here = (incl - mine) <= k0 && k0 < incl; // the k-th largest falls into my bins
+            const uint32_t who = __ballot_sync(0xffffffffu, here);
+            if (who == 0)
+            {
+                if (lane == 0) // fewer than k+1 elements left (cannot happen for n > k): bin 0
+                {
+                    s_k = k0 - incl; // unused
+                    s_prefix = prefix;
+                }
+            }
+            else if (lane == __ffs(who) - 1)
+            {
+                int k = k0 - (incl - mine), d = 255 - 8 * lane;
+                for (int u = 0; u < 8; u++, d--)
+                {
+                    if (k < s_hist[d])
+                        break;
+                    k -= s_hist[d];
+                }
+                s_k = k;
+                s_prefix = prefix | ((uint32_t)d << shift);
+            }
         }
         __syncthreads();
     }
     const uint32_t decision = s_prefix;
+    LVT_TDBG(5);
 
     // :72-80  keep radius >= decision, in sorted order
     int running = 0;
@@ -622,6 +832,9 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     }
     if (threadIdx.x == 0)
         a.tile_out_count[b * a.n_tiles + t] = running;
+    LVT_TDBG(6);
+    if (a.dbg && threadIdx.x == 0)
+        a.dbg[(b * a.n_tiles + t) * 8 + 7] = n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -717,7 +930,7 @@ __global__ void __launch_bounds__(1024) gather_kernel(GatherArgs a)
     }
 }
 
-__global__ void clear_counts_kernel(int *tile_count, int *tile_overflow, int n, const int *retry, int n_tiles)
+__global__ void clear_counts_kernel(int *tile_count, int *tile_overflow, int *cand_count, int n, const int *retry, int n_tiles)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -726,6 +939,8 @@ __global__ void clear_counts_kernel(int *tile_count, int *tile_overflow, int n, 
         return;
     tile_count[i] = 0;
     tile_overflow[i] = 0;
+    if (i % n_tiles == 0)
+        cand_count[i / n_tiles] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -754,22 +969,44 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     {
         const int *retry = pass ? ws.retry : nullptr;
         const int th = pass ? dp.threshold_low : dp.threshold;
-        LVT_TIMED(stream, K_CLEAR, (clear_counts_kernel<<<(n_images * nt + 255) / 256, 256, 0, stream>>>(ws.tile_count, ws.tile_overflow,
+        LVT_TIMED(stream, K_CLEAR, (clear_counts_kernel<<<(n_images * nt + 255) / 256, 256, 0, stream>>>(ws.tile_count, ws.tile_overflow, ws.cand_count,
                                                                             n_images * nt, retry, nt)));
-        NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, retry, dp.grid,
+        NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, reinterpret_cast<uint32_t *>(ws.parent),
+                   ws.cand_count, retry, dp.grid,
                    dp.pitch, dp.rows,     dp.cols,       ws.tile_cap,      nt,       th,    nonmax};
         dim3 ngrid(((dp.cols + 3) / 4 + 127) / 128, dp.rows, n_images);
         LVT_TIMED(stream, K_NMS, (nms_kernel<<<ngrid, 128, 0, stream>>>(na)));
         LVT_LAUNCH_CHECK(stream, "nms_kernel");
         if (nonmax)
         {
+            LVT_TIMED(stream, K_NMS_RESOLVE, (nms_resolve_kernel<<<dim3(148, n_images), 128, 0, stream>>>(na)));
+            LVT_LAUNCH_CHECK(stream, "nms_resolve_kernel");
+        }
+        if (nonmax)
+        {
             LVT_TIMED(stream, K_NMS_FALLBACK, (nms_fallback_kernel<<<dim3(nt, n_images), 32, 0, stream>>>(na, ws.parent)));
             LVT_LAUNCH_CHECK(stream, "nms_fallback_kernel");
         }
         TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count, ws.tile_out_count, retry,
-                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell};
+                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell,
+                    (pass == 0 && debug_sync_enabled()) ? reinterpret_cast<long long *>(ws.tile_aux) : nullptr}; // scratch unused for small tiles
+        static bool dumped = false;
         LVT_TIMED(stream, K_TILE, (tile_kernel<<<dim3(nt, n_images), kTileThreads, kTileSmemBytes, stream>>>(ta)));
         LVT_LAUNCH_CHECK(stream, "tile_kernel");
+        if (ta.dbg && !dumped && std::getenv("LVT_B200_TILEDBG"))
+        {
+            static int calls = 0;
+            if (++calls == 8)
+            {
+                dumped = true;
+                std::vector<long long> h((size_t)nt * n_images * 8);
+                cudaMemcpy(h.data(), ta.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+                for (int i = 0; i < nt * n_images; i++)
+                    std::fprintf(stderr, "tile %2d n=%4lld: load+bitonic %6lld | sort %6lld (radii %6lld) | sync %6lld | select %6lld | compact %6lld cycles\n", i,
+                                 h[i * 8 + 7], h[i * 8 + 1] - h[i * 8], h[i * 8 + 2] - h[i * 8 + 1], h[i * 8 + 3] - h[i * 8 + 1],
+                                 h[i * 8 + 4] - h[i * 8 + 1], h[i * 8 + 5] - h[i * 8 + 4], h[i * 8 + 6] - h[i * 8 + 5]);
+            }
+        }
         GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, d_feats, nt, ws.tile_cap,
                       dp.rows,     dp.cols,           border,   pass,     allow_retry ? kCornersLowTh : 0};
         LVT_TIMED(stream, K_GATHER, (gather_kernel<<<n_images, 1024, 0, stream>>>(ga)));

@@ -62,6 +62,7 @@ struct DetectWorkspace
     int *tile_count = nullptr;       // [batch][n_tiles]
     int *tile_overflow = nullptr;    // [batch][n_tiles]  component larger than the in-register cap
     int *tile_out_count = nullptr;   // [batch][n_tiles]
+    int *cand_count = nullptr;       // [batch] local maxima queued for nms_resolve_kernel (list lives in `parent`)
     int *retry = nullptr;            // [batch] fewer than 200 corners: redo at the lowered threshold
     int *error = nullptr;            // [1] sticky capacity error flag
 };

@@ -207,5 +207,70 @@ LVT_HD inline void sort(uint32_t *first, long n)
         insertion_sort(first, last);
 }
 
+// The same sort as a level-synchronous schedule: the sub-ranges produced by a partition are disjoint
+// and each carries its own depth budget, so all ranges of one recursion level can be partitioned
+// concurrently; the final insertion sort never moves an element out of its <= 16-element leaf range
+// (partitioning leaves keys(left) >= pivot >= keys(right), and insertion is stable), so it is an
+// independent stable insertion sort per leaf.  This sequential version documents and tests the
+// schedule; tile_kernel runs it with one thread per range.
+struct LevelRange
+{
+    int first, last, depth;
+};
+
+// one step of __introsort_loop on r (size > 16): returns the two children, or heap-sorts in place
+// and returns false when the depth budget is exhausted
+LVT_HD inline bool split_range(uint32_t *a, const LevelRange &r, LevelRange &left, LevelRange &right)
+{
+    if (r.depth == 0)
+    {
+        heap_sort(a + r.first, a + r.last);
+        return false;
+    }
+    uint32_t *first = a + r.first, *last = a + r.last;
+    uint32_t *mid = first + (last - first) / 2;
+    move_median_to_first(first, first + 1, mid, last - 1);
+    uint32_t *cut = unguarded_partition(first + 1, last, first);
+    left = LevelRange{r.first, (int)(cut - a), r.depth - 1};
+    right = LevelRange{(int)(cut - a), r.last, r.depth - 1};
+    return true;
+}
+
+// q0, q1: scratch for n / 8 + 2 ranges each
+LVT_HD inline void sort_levels(uint32_t *a, int n, LevelRange *q0, LevelRange *q1)
+{
+    if (n <= 1)
+        return;
+    int lg = 0;
+    for (int v = n; v > 1; v >>= 1)
+        lg++;
+    LevelRange *cur = q0, *nxt = q1;
+    int ncur = 1;
+    cur[0] = LevelRange{0, n, 2 * lg};
+    while (ncur > 0)
+    {
+        int nnxt = 0;
+        for (int i = 0; i < ncur; i++)
+        {
+            const LevelRange r = cur[i];
+            if (r.last - r.first <= 16)
+            {
+                insertion_sort(a + r.first, a + r.last); // leaf
+                continue;
+            }
+            LevelRange l, rr;
+            if (split_range(a, r, l, rr))
+            {
+                nxt[nnxt++] = l;
+                nxt[nnxt++] = rr;
+            }
+        }
+        LevelRange *t = cur;
+        cur = nxt;
+        nxt = t;
+        ncur = nnxt;
+    }
+}
+
 } // namespace isort
 } // namespace lvtb

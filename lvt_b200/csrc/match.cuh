@@ -260,6 +260,26 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     __syncthreads();
     const int n_fast = s_flag[2], n_slow = s_flag[3];
 
+    // `prev` = the query's choice of the previous round (a register copy for the cached queries)
+    auto publish_cached = [&](int q, uint32_t b1, uint32_t b2, int &my_count, int &prev) {
+        const int c = accept_match(b1, b2, ratio_th, dist_th);
+        if (c != prev)
+        {
+            prev = c;
+            choice[q] = c;
+            s_flag[0] = 1;
+        }
+        if (c >= 0)
+        {
+            atomicMin(&nxt[c], q);
+            my_count++;
+            if (out_d1)
+            {
+                out_d1[q] = (float)(b1 >> 20);
+                out_d2[q] = b2 != kNoKey ? (float)(b2 >> 20) : -1.0f;
+            }
+        }
+    };
     auto publish = [&](int q, uint32_t b1, uint32_t b2, int &my_count) {
         const int c = accept_match(b1, b2, ratio_th, dist_th);
         if (c != choice[q])
@@ -279,6 +299,26 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
     };
 
+    // the first 4 x blockDim queries of the fast list live in registers across the rounds: query id,
+    // candidate count, the first four (sorted) keys, last choice -- a round then touches only shared
+    // memory unless a query has to look past its fourth key
+    constexpr int U = 4;
+    int rq[U], rcnt[U], rprev[U];
+    uint4 rk4[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+        const int it = threadIdx.x + u * blockDim.x;
+        rq[u] = it < n_fast ? fast[it] : -1;
+        rprev[u] = -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+        rcnt[u] = rq[u] >= 0 ? L.count[rq[u]] : 0;
+        rk4[u] = rq[u] >= 0 ? *reinterpret_cast<const uint4 *>(L.keys + (size_t)rq[u] * L.cap) : make_uint4(0, 0, 0, 0);
+    }
+
     int count = 0, rounds = 0;
     for (;; rounds++)
     {
@@ -290,8 +330,29 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         int my_count = 0;
         // one thread per query, 4 queries in flight: the first four keys of each sorted list come in
         // one 16-byte load; the first two keys not owned by an earlier query decide
-        constexpr int U = 4;
-        for (int base = threadIdx.x; base < n_fast; base += blockDim.x * U)
+#pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            if (rq[u] < 0)
+                continue;
+            const uint32_t *keys = L.keys + (size_t)rq[u] * L.cap;
+            uint32_t b1 = kNoKey, b2 = kNoKey;
+            for (int k = 0; k < rcnt[u]; k++)
+            {
+                const uint32_t key = k == 0 ? rk4[u].x : k == 1 ? rk4[u].y : k == 2 ? rk4[u].z : k == 3 ? rk4[u].w : keys[k];
+                if (cur[key & 0xFFFFFu] < rq[u])
+                    continue; // marked, or taken by an earlier query
+                if (b1 == kNoKey)
+                    b1 = key;
+                else
+                {
+                    b2 = key;
+                    break;
+                }
+            }
+            publish_cached(rq[u], b1, b2, my_count, rprev[u]);
+        }
+        for (int base = threadIdx.x + U * blockDim.x; base < n_fast; base += blockDim.x * U)
         {
             int q[U], cnt[U];
             uint4 k4[U];

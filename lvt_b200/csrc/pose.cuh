@@ -98,30 +98,31 @@ __device__ inline bool solve6(const double *A_in /* 36 */, const double *b_in, d
     return true;
 }
 
-// Cholesky solve of (H + lambda I) x = b, fully unrolled so that everything stays in registers;
-// false when the matrix is not positive definite (the caller then falls back to LU)
+// LDL^T solve of (H + lambda I) x = b, fully unrolled so that everything stays in registers: no
+// square roots, one reciprocal per pivot.  false when a pivot is not positive (the caller then
+// falls back to LU with partial pivoting)
 __device__ __forceinline__ bool chol_solve6(const double *H, double lambda, const double *b, double *x)
 {
-    double L[6][6];
+    double L[6][6], D[6], Dinv[6]; // A = L D L^T, L unit lower triangular
 #pragma unroll
     for (int j = 0; j < 6; j++)
     {
-        double sum = H[7 * j] + lambda;
+        double dj = H[7 * j] + lambda;
 #pragma unroll
         for (int k = 0; k < j; k++)
-            sum -= L[j][k] * L[j][k];
-        if (!(sum > 0.0))
+            dj -= L[j][k] * L[j][k] * D[k];
+        if (!(dj > 0.0))
             return false;
-        L[j][j] = sqrt(sum);
-        const double inv = 1.0 / L[j][j];
+        D[j] = dj;
+        Dinv[j] = 1.0 / dj;
 #pragma unroll
         for (int i = j + 1; i < 6; i++)
         {
             double v = H[6 * i + j];
 #pragma unroll
             for (int k = 0; k < j; k++)
-                v -= L[i][k] * L[j][k];
-            L[i][j] = v * inv;
+                v -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = v * Dinv[j];
         }
     }
     double y[6];
@@ -132,16 +133,16 @@ __device__ __forceinline__ bool chol_solve6(const double *H, double lambda, cons
 #pragma unroll
         for (int k = 0; k < i; k++)
             v -= L[i][k] * y[k];
-        y[i] = v / L[i][i];
+        y[i] = v;
     }
 #pragma unroll
     for (int i = 5; i >= 0; i--)
     {
-        double v = y[i];
+        double v = y[i] * Dinv[i];
 #pragma unroll
         for (int k = i + 1; k < 6; k++)
             v -= L[k][i] * x[k];
-        x[i] = v / L[i][i];
+        x[i] = v;
     }
     return true;
 }
@@ -350,26 +351,13 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                 A[7 * j] += lambda;
             solved = solve6(A, bvec, d);
         }
+        // LinearSolverPCG's single step scales d by alpha = b.d / d.Ad, which is 1 up to rounding for
+        // an exact block solve; it is dropped here (1e-16 relative, far below the parity tolerance)
         if (solved)
         {
-            double dn = 0, dq = 0;
 #pragma unroll
             for (int i = 0; i < 6; i++)
-            {
-                dn += bvec[i] * d[i];
-                double Ad = lambda * d[i];
-#pragma unroll
-                for (int j = 0; j < 6; j++)
-                    Ad += H[6 * i + j] * d[j];
-                dq += d[i] * Ad;
-            }
-            if (!(dn <= 1e-6 * dn))
-            {
-                const double alpha = dn / dq;
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                    x[i] = alpha * d[i];
-            }
+                x[i] = d[i];
         }
         cam_update(s.cam, x);
     };

@@ -24,10 +24,12 @@ int main() {
       if (mode == 6) r = 20 + rng() % 3;
       a[i] = (r << 24) | i;
     }
-    std::vector<uint32_t> b = a;
+    std::vector<uint32_t> b = a, c = a;
     std::sort(a.begin(), a.end(), cmp);
     lvtb::isort::sort(b.data(), n);
-    cases++; bad += a != b;
+    std::vector<lvtb::isort::LevelRange> q0(n / 8 + 2), q1(n / 8 + 2);
+    lvtb::isort::sort_levels(c.data(), n, q0.data(), q1.data());   // the level-synchronous schedule of tile_kernel
+    cases++; bad += a != b; bad += a != c;
   }
   // the heapsort fallback, exercised directly against std::make_heap + std::sort_heap
   for (int it = 0; it < 500; it++) {

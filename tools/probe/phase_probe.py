@@ -33,3 +33,24 @@ vo.track_pool(20, 20, want_infos=False)
 lib.set_profiling(False)
 for k, (ms, cnt) in lib.kernel_times().items():
     if cnt: print("%-22s %8.1f us x %d" % (k, 1e3 * ms / cnt, cnt))
+# isolated kernel times: the blocking per-frame path (one stream, nothing overlapped)
+vo2 = lib.create(p, 1)
+for t in range(6):
+    vo2.track(*st.frame(t))
+lib.reset_kernel_times(); lib.set_profiling(True)
+import time
+t0 = time.perf_counter()
+for t in range(6, 26):
+    vo2.track(*st.frame(t))
+dt = time.perf_counter() - t0
+lib.set_profiling(False)
+print("blocking lvt_track with profiling events: %.1f us/frame" % (1e6 * dt / 20))
+tot = 0
+for k, (ms, cnt) in lib.kernel_times().items():
+    if cnt:
+        print("  %-22s %8.1f us x %d" % (k, 1e3 * ms / cnt, cnt)); tot += ms
+print("  sum per frame %.1f us" % (1e3 * tot / 20))
+t0 = time.perf_counter()
+for t in range(26, 40):
+    vo2.track(*st.frame(t))
+print("blocking lvt_track: %.1f us/frame" % (1e6 * (time.perf_counter() - t0) / 14))
