@@ -151,13 +151,16 @@ constexpr int kPoseSums = 29;   // 21 (upper H) + 6 (b) + robust chi2 + number o
 constexpr int kPoseCluster = 8; // CTAs (SMs) sharing the correspondences of one solve
 constexpr int kPoseThreads = 256;
 
+constexpr int kPoseAccStride = kPoseThreads + kPoseThreads / 32; // one pad per 32 entries: conflict-free column sums
+
 struct PoseShared
 {
-    CamState cam;                                   // every CTA keeps a copy of the camera under evaluation
-    double partial[kPoseThreads / 32][kPoseSums];   // per-warp partial sums
-    double cta_sums[kPoseSums];                     // this CTA's sums, read by rank 0 through DSMEM
-    double sums[kPoseSums];                         // cluster totals (rank 0 only)
-    int cont;                                       // 0 evaluate again, 1 end of pass, 2 finished
+    CamState cam;                                   // every CTA keeps its own copy of the camera under evaluation
+    double acc[kPoseSums][kPoseAccStride];          // per-thread partial sums, summed in a fixed order
+    double part[kPoseSums][kPoseThreads / 32];      // per-warp-slice sums
+    double cta_sums[2][kPoseSums];                  // this CTA's sums (double-buffered), read by every CTA through DSMEM
+    double sums[kPoseSums];                         // cluster totals (every CTA computes the same values)
+    int cont;                                       // 0 evaluate again, 1 end of pass
 };
 
 // One evaluation at s.cam over the active edges owned by this CTA: errors, robust cost, and the
@@ -167,8 +170,13 @@ struct PoseShared
 // rank 0's s.sums after one cluster barrier; the summation order is fixed (deterministic).
 template <class Cluster>
 __device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, const double *xyz, const float2 *uv,
-                                     const uint8_t *level, double *e2, int m, int rank, int nranks)
+                                     const uint8_t *level, double *e2, int m, int rank, int nranks, int parity,
+                                     long long *dbg = nullptr)
 {
+#define LVT_PDBG(k)                                                                                                   \
+    if (dbg && rank == 0 && threadIdx.x == 0)                                                                         \
+    dbg[k] = clock64()
+    LVT_PDBG(0);
     const CamState &c = s.cam;
     const double dsqr = kReprojectionTh2, dsqr_reci = 1.0 / kReprojectionTh2; // delta = sqrt(5.991)
     double acc[kPoseSums];
@@ -230,57 +238,56 @@ __device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, const doub
         for (int a = 0; a < 6; a++)
             acc[21 + a] += J0[a] * g0 + J1[a] * g1;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // fixed-order reduction through shared memory: thread -> 32-entry slices -> CTA -> cluster (DSMEM)
+    LVT_PDBG(1);
+    const int slot = threadIdx.x + (threadIdx.x >> 5);
 #pragma unroll
     for (int k = 0; k < kPoseSums; k++)
+        s.acc[k][slot] = acc[k];
+    __syncthreads();
+    constexpr int kSlices = kPoseThreads / 32;
+    if (threadIdx.x < kPoseSums * kSlices)
     {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0)
-            s.partial[warp][k] = v;
+        const int k = threadIdx.x / kSlices, w = threadIdx.x % kSlices;
+        const double *src = &s.acc[k][w * 33];
+        double v = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++)
+            v += src[j];
+        s.part[k][w] = v;
     }
     __syncthreads();
     if (threadIdx.x < kPoseSums)
     {
         double v = 0.0;
-        for (int w = 0; w < nwarps; w++)
-            v += s.partial[w][threadIdx.x];
-        s.cta_sums[threadIdx.x] = v;
+#pragma unroll
+        for (int w = 0; w < kSlices; w++)
+            v += s.part[threadIdx.x][w];
+        s.cta_sums[parity][threadIdx.x] = v;
     }
+    LVT_PDBG(2);
     cluster.sync();
-    if (rank == 0)
+    LVT_PDBG(3);
+    if (threadIdx.x < kPoseSums)
     {
-        if (threadIdx.x < kPoseSums)
-        {
-            double v = 0.0;
-            for (int r = 0; r < nranks; r++)
-                v += *cluster.map_shared_rank(&s.cta_sums[threadIdx.x], r);
-            s.sums[threadIdx.x] = v;
-        }
-        __syncthreads();
-    }
-}
-
-// rank 0 publishes its camera and the continuation code to every CTA of the cluster
-template <class Cluster>
-__device__ inline int pose_broadcast(Cluster &cluster, PoseShared &s, int rank)
-{
-    cluster.sync();
-    if (rank != 0 && threadIdx.x == 0)
-    {
-        s.cam = *cluster.map_shared_rank(&s.cam, 0);
-        s.cont = *cluster.map_shared_rank(&s.cont, 0);
+        double v = 0.0;
+        for (int r = 0; r < nranks; r++)
+            v += *cluster.map_shared_rank(&s.cta_sums[parity][threadIdx.x], r);
+        s.sums[threadIdx.x] = v;
     }
     __syncthreads();
-    return s.cont;
+    LVT_PDBG(4);
 }
 
 // lvt_pnp_solver::compute_pose on a thread-block cluster.  Every thread of every CTA calls it.
 // level / e2 / inlier: per-edge scratch (global).  Rank 0 / thread 0 writes *pose_out and
-// *n_inliers_out.  Control flow is uniform across the cluster (driven by the broadcast code).
+// *n_inliers_out.  Every CTA reads the same cluster totals and its thread 0 runs the same LM step on
+// them (bitwise identical results), so one cluster barrier per evaluation is all the CTAs exchange;
+// control flow is uniform across the cluster.
 template <class Cluster>
 __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const double *xyz, const float2 *uv, int m,
                                           const PoseD &init, const CamParams &cp, uint8_t *level, double *e2,
-                                          uint8_t *inlier, PoseD *pose_out, int *n_inliers_out)
+                                          uint8_t *inlier, PoseD *pose_out, int *n_inliers_out, long long *dbg = nullptr)
 {
     const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
     if (threadIdx.x == 0)
@@ -317,7 +324,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
     double H[36], bvec[6], x[6];
     CamState backup;
     int qmax = 0, it = 0;
-    const bool boss = rank == 0 && threadIdx.x == 0;
+    const bool boss = threadIdx.x == 0; // in every CTA
+    int parity = 0;
     auto load_system = [&]() {
         int idx = 0;
 #pragma unroll
@@ -365,7 +373,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
     for (int pass = 0; pass < 2; pass++)
     {
         // errors + linearisation at the starting state of this optimize()
-        pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks);
+        pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks, parity);
+        parity ^= 1;
         if (boss)
         {
             if (s.sums[28] == 0.0)
@@ -386,9 +395,13 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                 s.cont = 0;
             }
         }
-        while (pose_broadcast(cluster, s, rank) == 0)
+        while (true)
         {
-            pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks); // the trial state
+            __syncthreads();
+            if (s.cont != 0)
+                break;
+            pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks, parity, dbg); // the trial state
+            parity ^= 1;
             if (boss)
             {
                 const double temp_chi = s.sums[27];
@@ -430,6 +443,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                     propose();
                     s.cont = 0;
                 }
+                if (dbg && rank == 0)
+                    dbg[5] = clock64();
             }
         }
         // lvt_pnp_solver.cpp:109-116
@@ -443,35 +458,36 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
         }
         __syncthreads();
     }
-    // inlier count through the same reduction path
+    // inlier count: CTA sums exchanged through DSMEM
     {
         double cnt = 0;
         for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
             cnt += inlier[i];
         cnt = warp_sum(cnt);
+        __syncthreads();
         if ((threadIdx.x & 31) == 0)
-            s.partial[threadIdx.x >> 5][0] = cnt;
+            s.part[0][threadIdx.x >> 5] = cnt;
         __syncthreads();
         if (threadIdx.x == 0)
         {
             double v = 0;
             for (int w = 0; w < (int)(blockDim.x >> 5); w++)
-                v += s.partial[w][0];
-            s.cta_sums[0] = v;
+                v += s.part[0][w];
+            s.cta_sums[parity][0] = v;
         }
         cluster.sync();
-        if (boss)
+        if (rank == 0 && threadIdx.x == 0)
         {
             double v = 0;
             for (int r = 0; r < nranks; r++)
-                v += *cluster.map_shared_rank(&s.cta_sums[0], r);
+                v += *cluster.map_shared_rank(&s.cta_sums[parity][0], r);
             *n_inliers_out = (int)v;
             pose_out->q = s.cam.r;
             pose_out->t[0] = s.cam.t[0];
             pose_out->t[1] = s.cam.t[1];
             pose_out->t[2] = s.cam.t[2];
         }
-        cluster.sync(); // nobody leaves while rank 0 still reads remote shared memory
+        cluster.sync(); // nobody leaves while another CTA may still read its shared memory
     }
 }
 

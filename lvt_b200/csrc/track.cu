@@ -15,6 +15,8 @@
 // (candidate generation, projection, Jacobians) is spread over many SMs.  No host round trip:
 // all control flow (first frame, lost, retry, policy) is decided on the device through FrameCtl.
 #include "track.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -328,11 +330,13 @@ struct PoseArgs
     double *e2;
     PoseD *out;
     int *n_inliers;
+    long long *dbg;
 };
 
 __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_kernel(PoseArgs a)
 {
-    __shared__ PoseShared s;
+    extern __shared__ __align__(16) unsigned char pose_smem[];
+    PoseShared &s = *reinterpret_cast<PoseShared *>(pose_smem);
     cg::cluster_group cluster = cg::this_cluster();
     int m = a.m;
     PoseD init = a.init;
@@ -349,7 +353,7 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
         if (cluster.block_rank() == 0 && threadIdx.x == 0)
             a.ctl->cyc[3] = clock64();
     }
-    cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl);
+    cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl, a.dbg);
     if (a.ctl && cluster.block_rank() == 0 && threadIdx.x == 0)
         a.ctl->cyc[4] = clock64();
 }
@@ -737,6 +741,7 @@ static int ensure_smem(int owner_cap)
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(match_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(row_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        LVT_CUDA_TRY(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoseShared)));
         configured = bytes;
     }
     return LVTK_OK;
@@ -766,9 +771,21 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, owner_cap};
     LVT_TIMED(stream, K_TRACK_A, (track_a_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
-    PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr};
-    LVT_TIMED(stream, K_POSE, (pose_kernel<<<kPoseCluster, kPoseThreads, 0, stream>>>(pa)));
+    PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr};
+    LVT_TIMED(stream, K_POSE, (pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(pa)));
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
+    if (pa.dbg && std::getenv("LVT_B200_POSEDBG"))
+    {
+        static int calls = 0;
+        if (++calls == 8)
+        {
+            long long h[8];
+            cudaMemcpy(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "pose pass: compute %lld | warp+cta reduce %lld | cluster.sync %lld | dsmem reduce %lld | boss LM step %lld cycles\n",
+                         h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+        }
+    }
     MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
     LVT_TIMED(stream, K_STAGEDCAND, (mapcand_kernel<<<148, kCandWarps * 32, 0, stream>>>(sc2)));
     LVT_LAUNCH_CHECK(stream, "stagedcand_kernel");
@@ -815,8 +832,10 @@ int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandList
 int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD &init, const CamParams &cam,
                      uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, int *d_n_inliers, cudaStream_t stream)
 {
-    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers};
-    pose_kernel<<<kPoseCluster, kPoseThreads, 0, stream>>>(a);
+    if (int rc = ensure_smem(16))
+        return rc;
+    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr};
+    pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     return LVTK_OK;
 }
