@@ -513,11 +513,78 @@ struct TileArgs
 constexpr int kTileSmemCap = 8192; // tiles with more survivors work out of global scratch
 constexpr int kTileThreads = 1024;
 constexpr int kTileRanges = kTileSmemCap / 8 + 2; // ranges alive in one level of the introsort schedule
-constexpr int kTileSmemBytes = 3 * kTileSmemCap * (int)sizeof(uint32_t) + 2 * kTileRanges * (int)sizeof(isort::LevelRange);
+constexpr int kTileSmemBytes = 3 * kTileSmemCap * (int)sizeof(uint32_t) + 2 * kTileRanges * (int)sizeof(isort::LevelRange) +
+                               2 * kTileSmemCap * (int)sizeof(uint16_t);
 
-// the same schedule run by ONE warp (lane per range, __syncwarp between levels) so that the other
-// warps of the CTA can compute the suppression radii at the same time
-__device__ void warp_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, volatile int *s_cnt)
+// std::__unguarded_partition(first + 1, last, first) computed by a whole warp with the SAME result as
+// the sequential two-pointer loop.  With pv = key(pivot), the forward pointer stops at elements with
+// key <= pv ("L-stoppers"), the backward pointer at elements with key >= pv ("R-stoppers"); the loop
+// swaps the i-th L-stopper from the left with the i-th R-stopper from the right while the former lies
+// left of the latter, and nothing it swaps is ever looked at again.  So with posL / posR = the two
+// position lists of the ORIGINAL range, K = #{i : posL[i] < posR[i]} swaps happen (the predicate is
+// monotone) and the returned cut is posL[K] if that lies left of posR[K-1], else posR[K-1].
+// Ranks come from ballots + running counts; posL / posR are shared scratch (u16, range length).
+__device__ int warp_partition(uint32_t *a, int first, int last, uint16_t *posL, uint16_t *posR)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t pv = a[first] >> 24;
+    const int lo = first + 1, m = last - lo;
+    int nL = 0;
+    for (int base = 0; base < m; base += 32)
+    {
+        const int p = base + lane;
+        const bool isL = p < m && (a[lo + p] >> 24) <= pv;
+        const uint32_t bl = __ballot_sync(0xffffffffu, isL);
+        if (isL)
+            posL[nL + __popc(bl & ((1u << lane) - 1u))] = (uint16_t)p;
+        nL += __popc(bl);
+    }
+    int nR = 0;
+    for (int base = 0; base < m; base += 32)
+    {
+        const int p = m - 1 - (base + lane); // from the right
+        const bool isR = p >= 0 && (a[lo + p] >> 24) >= pv;
+        const uint32_t br = __ballot_sync(0xffffffffu, isR);
+        if (isR)
+            posR[nR + __popc(br & ((1u << lane) - 1u))] = (uint16_t)p;
+        nR += __popc(br);
+    }
+    __syncwarp();
+    const int nmin = min(nL, nR);
+    int K = 0;
+    for (int base = 0; base < nmin; base += 32)
+    {
+        const int i = base + lane;
+        const bool sw = i < nmin && posL[i] < posR[i];
+        const uint32_t bs = __ballot_sync(0xffffffffu, sw);
+        if (sw)
+        {
+            const int pl = lo + posL[i], pr = lo + posR[i];
+            const uint32_t t = a[pl];
+            a[pl] = a[pr];
+            a[pr] = t;
+        }
+        K += __popc(bs);
+        if (bs != 0xffffffffu)
+            break; // monotone: no further swaps
+    }
+    int cut;
+    const int prevR = K > 0 ? (int)posR[K - 1] : m; // m = one past the range
+    if (K < nL && (int)posL[K] < prevR)
+        cut = lo + posL[K];
+    else
+        cut = lo + prevR;
+    __syncwarp();
+    return cut;
+}
+
+constexpr int kCoopRange = 96; // ranges at least this long are partitioned by the whole warp
+
+// the same schedule run by ONE warp so that the other warps of the CTA can compute the suppression
+// radii at the same time: long ranges are partitioned cooperatively (warp_partition), short ones
+// lane-per-range, __syncwarp between levels
+__device__ void warp_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, volatile int *s_cnt,
+                               uint16_t *posL, uint16_t *posR)
 {
     const int lane = threadIdx.x & 31;
     if (n <= 1)
@@ -539,9 +606,33 @@ __device__ void warp_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort:
         const int ncur = s_cnt[which];
         if (ncur == 0)
             break;
+        // long ranges: one after another, all lanes together
+        for (int i = 0; i < ncur; i++)
+        {
+            const isort::LevelRange r = cur[i];
+            if (r.last - r.first < kCoopRange || r.depth == 0)
+                continue;
+            if (lane == 0)
+            {
+                uint32_t *f = a + r.first, *l = a + r.last;
+                isort::move_median_to_first(f, f + 1, f + (l - f) / 2, l - 1);
+            }
+            __syncwarp();
+            const int cut = warp_partition(a, r.first, r.last, posL, posR);
+            if (lane == 0)
+            {
+                const int slot = atomicAdd((int *)&s_cnt[which ^ 1], 2);
+                nxt[slot] = isort::LevelRange{r.first, cut, r.depth - 1};
+                nxt[slot + 1] = isort::LevelRange{cut, r.last, r.depth - 1};
+            }
+        }
+        __syncwarp();
+        // short ranges (and heap-sort fallbacks): lane per range
         for (int i = lane; i < ncur; i += 32)
         {
             const isort::LevelRange r = cur[i];
+            if (r.last - r.first >= kCoopRange && r.depth != 0)
+                continue;
             if (r.last - r.first <= 16)
             {
                 isort::insertion_sort(a + r.first, a + r.last);
@@ -566,11 +657,34 @@ __device__ void warp_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort:
     }
 }
 
-// std::sort's permutation, one thread per range of the current recursion level (introsort.cuh)
-__device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, int *s_cnt)
+// stable sort of a leaf range (<= 16 elements) by rank: what the final insertion sort does to it
+// (a stable sort's result is unique).  Lanes 0..len-1 hold one element each.
+__device__ __forceinline__ void warp_leaf_sort(uint32_t *a, int first, int len)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t mine = lane < len ? a[first + lane] : 0u;
+    const uint32_t key = mine >> 24;
+    int rank = 0;
+    for (int j = 0; j < len; j++)
+    {
+        const uint32_t other = __shfl_sync(0xffffffffu, key, j);
+        rank += (other > key) || (other == key && j < lane);
+    }
+    __syncwarp();
+    if (lane < len)
+        a[first + rank] = mine;
+}
+
+// std::sort's permutation (introsort.cuh), all warps of the CTA: every warp takes ranges of the current
+// recursion level -- partition by warp_partition (exact), leaves by rank sort, heap-sort fallback by
+// one lane -- with a block barrier between levels.  posL / posR: u16 scratch indexed like the array
+// (ranges of one level are disjoint, so each uses its own slice).
+__device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, int *s_cnt,
+                                uint16_t *posL, uint16_t *posR)
 {
     if (n <= 1)
         return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int lg = 0;
     for (int v = n; v > 1; v >>= 1)
         lg++;
@@ -588,20 +702,33 @@ __device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort
         const int ncur = s_cnt[which];
         if (ncur == 0)
             break;
-        for (int i = threadIdx.x; i < ncur; i += blockDim.x)
+        for (int i = warp; i < ncur; i += nwarps)
         {
             const isort::LevelRange r = cur[i];
-            if (r.last - r.first <= 16)
+            const int len = r.last - r.first;
+            if (len <= 16)
             {
-                isort::insertion_sort(a + r.first, a + r.last);
+                warp_leaf_sort(a, r.first, len);
                 continue;
             }
-            isort::LevelRange l, rr;
-            if (isort::split_range(a, r, l, rr))
+            if (r.depth == 0)
+            {
+                if (lane == 0)
+                    isort::heap_sort(a + r.first, a + r.last);
+                continue;
+            }
+            if (lane == 0)
+            {
+                uint32_t *f = a + r.first, *l = a + r.last;
+                isort::move_median_to_first(f, f + 1, f + (l - f) / 2, l - 1);
+            }
+            __syncwarp();
+            const int cut = warp_partition(a, r.first, r.last, posL + r.first, posR + r.first);
+            if (lane == 0)
             {
                 const int slot = atomicAdd(&s_cnt[which ^ 1], 2);
-                nxt[slot] = l;
-                nxt[slot + 1] = rr;
+                nxt[slot] = isort::LevelRange{r.first, cut, r.depth - 1};
+                nxt[slot + 1] = isort::LevelRange{cut, r.last, r.depth - 1};
             }
         }
         __syncthreads();
@@ -645,8 +772,9 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     extern __shared__ uint32_t s_dyn[];
     uint32_t *s_keys = s_dyn, *s_rad = s_dyn + kTileSmemCap, *s_perm = s_dyn + 2 * kTileSmemCap;
     isort::LevelRange *s_q0 = reinterpret_cast<isort::LevelRange *>(s_dyn + 3 * kTileSmemCap), *s_q1 = s_q0 + kTileRanges;
+    uint16_t *s_posL = reinterpret_cast<uint16_t *>(s_q1 + kTileRanges), *s_posR = s_posL + kTileSmemCap;
     __shared__ int s_cnt[2];
-    __shared__ int s_hist[256];
+    __shared__ int s_hist[257];
     __shared__ int s_scan[34];
     __shared__ uint32_t s_prefix;
     __shared__ int s_k;
@@ -712,40 +840,50 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         perm[i] = ((keys[i] & 0xFFu) << 24) | (uint32_t)i;
     __syncthreads();
-    // :38-41, std::sort's exact permutation -- warp 0 -- while the other warps compute the radii
-    if (threadIdx.x < 32)
+    // :38-41, std::sort's exact permutation
+    if (small)
+        block_introsort(perm, n, s_q0, s_q1, s_cnt, s_posL, s_posR);
+    else if (threadIdx.x == 0)
+        isort::sort(perm, n); // more survivors than fit in shared memory (pathological): sequential replay
+    __syncthreads();
+    LVT_TDBG(2);
+    // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own.  In the sorted
+    // order those corners are a prefix: s_hist[v] = number of corners with response >= v.
+    for (int i = threadIdx.x; i < 257; i += blockDim.x)
+        s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        atomicAdd(&s_hist[keys[i] & 0xFFu], 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
     {
-        if (small)
-            warp_introsort(perm, n, s_q0, s_q1, s_cnt);
-        else if (threadIdx.x == 0)
-            isort::sort(perm, n); // more survivors than fit in shared memory (pathological): sequential replay
-        LVT_TDBG(2);
-    }
-    else
-    {
-        // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own
-        for (int i = threadIdx.x - 32; i < n; i += blockDim.x - 32)
+        int acc = 0;
+        for (int v = 256; v >= 0; v--)
         {
-            const uint32_t ki = keys[i];
-            // response_j > 1.11f * response_i in fp32  <=>  response_j >= floor(thr) + 1 (integers)
-            const float thr = __fmul_rn((float)(ki & 0xFFu), 1.11f);
-            const int need = (int)floorf(thr) + 1;
-            const int yi = (int)(ki >> 20), xi = (int)((ki >> 8) & 0xFFFu);
-            uint32_t best = 0xFFFFFFFFu; // FLT_MAX
-            for (int j = 0; j < n; j++)
-            {
-                const uint32_t kj = keys[j];
-                if ((int)(kj & 0xFFu) >= need)
-                {
-                    const int dx = xi - (int)((kj >> 8) & 0xFFFu), dy = yi - (int)(kj >> 20);
-                    best = min(best, (uint32_t)(dx * dx + dy * dy));
-                }
-            }
-            rad[i] = best;
+            acc += s_hist[v];
+            s_hist[v] = acc;
         }
-        if (a.dbg && threadIdx.x == 32)
-            a.dbg[(b * a.n_tiles + t) * 8 + 3] = clock64();
     }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x)
+    {
+        const int i = (int)(perm[p] & 0xFFFFFFu);
+        const uint32_t ki = keys[i];
+        // response_j > 1.11f * response_i in fp32  <=>  response_j >= floor(thr) + 1 (integers)
+        const float thr = __fmul_rn((float)(ki & 0xFFu), 1.11f);
+        const int need = (int)floorf(thr) + 1;
+        const int prefix_len = need > 255 ? 0 : s_hist[need];
+        const int yi = (int)(ki >> 20), xi = (int)((ki >> 8) & 0xFFFu);
+        uint32_t best = 0xFFFFFFFFu; // FLT_MAX
+        for (int q = 0; q < prefix_len; q++)
+        {
+            const uint32_t kj = keys[perm[q] & 0xFFFFFFu];
+            const int dx = xi - (int)((kj >> 8) & 0xFFFu), dy = yi - (int)(kj >> 20);
+            best = min(best, (uint32_t)(dx * dx + dy * dy));
+        }
+        rad[i] = best;
+    }
+    LVT_TDBG(3);
     __syncthreads();
     LVT_TDBG(4);
 

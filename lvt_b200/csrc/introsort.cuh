@@ -236,8 +236,33 @@ LVT_HD inline bool split_range(uint32_t *a, const LevelRange &r, LevelRange &lef
     return true;
 }
 
-// q0, q1: scratch for n / 8 + 2 ranges each
-LVT_HD inline void sort_levels(uint32_t *a, int n, LevelRange *q0, LevelRange *q1)
+// std::__unguarded_partition(first + 1, last, first) without the two-pointer loop (sequential
+// statement of detect.cu's warp_partition; see there for the argument).  posL / posR: scratch.
+LVT_HD inline int partition_lists(uint32_t *a, int first, int last, uint16_t *posL, uint16_t *posR)
+{
+    const uint32_t pv = a[first] >> 24;
+    const int lo = first + 1, m = last - lo;
+    int nL = 0, nR = 0;
+    for (int p = 0; p < m; p++)
+        if ((a[lo + p] >> 24) <= pv)
+            posL[nL++] = (uint16_t)p;
+    for (int p = m - 1; p >= 0; p--)
+        if ((a[lo + p] >> 24) >= pv)
+            posR[nR++] = (uint16_t)p;
+    const int nmin = nL < nR ? nL : nR;
+    int K = 0;
+    while (K < nmin && posL[K] < posR[K])
+    {
+        swap_el(a + lo + posL[K], a + lo + posR[K]);
+        K++;
+    }
+    const int prevR = K > 0 ? (int)posR[K - 1] : m;
+    return (K < nL && (int)posL[K] < prevR) ? lo + posL[K] : lo + prevR;
+}
+
+// q0, q1: scratch for n / 8 + 2 ranges each; ranges of at least coop_min elements use partition_lists
+LVT_HD inline void sort_levels(uint32_t *a, int n, LevelRange *q0, LevelRange *q1, uint16_t *posL = nullptr,
+                               uint16_t *posR = nullptr, int coop_min = 1 << 30)
 {
     if (n <= 1)
         return;
@@ -259,7 +284,15 @@ LVT_HD inline void sort_levels(uint32_t *a, int n, LevelRange *q0, LevelRange *q
                 continue;
             }
             LevelRange l, rr;
-            if (split_range(a, r, l, rr))
+            if (r.last - r.first >= coop_min && r.depth != 0)
+            {
+                uint32_t *f = a + r.first, *e = a + r.last;
+                move_median_to_first(f, f + 1, f + (e - f) / 2, e - 1);
+                const int cut = partition_lists(a, r.first, r.last, posL, posR);
+                nxt[nnxt++] = LevelRange{r.first, cut, r.depth - 1};
+                nxt[nnxt++] = LevelRange{cut, r.last, r.depth - 1};
+            }
+            else if (split_range(a, r, l, rr))
             {
                 nxt[nnxt++] = l;
                 nxt[nnxt++] = rr;

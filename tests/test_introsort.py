@@ -24,12 +24,15 @@ int main() {
       if (mode == 6) r = 20 + rng() % 3;
       a[i] = (r << 24) | i;
     }
-    std::vector<uint32_t> b = a, c = a;
+    std::vector<uint32_t> b = a, c = a, orig = a;
     std::sort(a.begin(), a.end(), cmp);
     lvtb::isort::sort(b.data(), n);
     std::vector<lvtb::isort::LevelRange> q0(n / 8 + 2), q1(n / 8 + 2);
     lvtb::isort::sort_levels(c.data(), n, q0.data(), q1.data());   // the level-synchronous schedule of tile_kernel
-    cases++; bad += a != b; bad += a != c;
+    std::vector<uint32_t> d2 = orig;
+    std::vector<uint16_t> pl(n + 1), pr(n + 1);
+    lvtb::isort::sort_levels(d2.data(), n, q0.data(), q1.data(), pl.data(), pr.data(), 17);  // list-based partition (warp_partition)
+    cases++; bad += a != b; bad += a != c; bad += a != d2;
   }
   // the heapsort fallback, exercised directly against std::make_heap + std::sort_heap
   for (int it = 0; it < 500; it++) {
