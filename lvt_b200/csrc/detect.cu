@@ -276,15 +276,11 @@ __device__ void nms_pixel(const NmsArgs &a, int b, const uint8_t *sm, int x, int
     a.cand[(size_t)b * a.rows * a.pitch + pos] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
 }
 
-// a local maximum: flood its component, decide whether it is the component's survivor
-__device__ void nms_resolve(const NmsArgs &a, int b, const uint8_t *sm, int x, int y, int s)
+// a local maximum: flood its component, decide whether it is the component's survivor.
+// score_at(x, y) = corner score at the current threshold, 0 outside the image / below it.
+template <class ScoreAt>
+__device__ void nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, int y, int s)
 {
-    auto score_at = [&](int xx, int yy) -> int {
-        if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
-            return 0;
-        const int v = sm[(size_t)yy * a.pitch + xx];
-        return v >= a.threshold ? v : 0;
-    };
     // flood the component; give up as soon as anything larger shows up.  Visited test: linear
     // search while the component is small, then a 64x32-pixel bitmap around the start pixel
     // (pixels outside that window keep the linear search).
@@ -411,7 +407,83 @@ __global__ void __launch_bounds__(128) nms_resolve_kernel(NmsArgs a)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const uint32_t c = a.cand[(size_t)b * a.rows * a.pitch + i];
-        nms_resolve(a, b, sm, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24));
+        auto score_at = [&](int xx, int yy) -> int {
+            if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
+                return 0;
+            const int v = sm[(size_t)yy * a.pitch + xx];
+            return v >= a.threshold ? v : 0;
+        };
+        nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24));
+    }
+}
+
+// Fused NMS: a CTA stages a 64x64 window of the score map (its 32x32 pixels + 16 px halo) in shared
+// memory, sweeps its pixels (beaten / isolated / local maximum), then resolves its local maxima with
+// the component flood reading shared memory (global memory only outside the window).
+constexpr int kNmsTile = 32, kNmsHalo = 16, kNmsWin = kNmsTile + 2 * kNmsHalo;
+
+__global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
+{
+    __shared__ __align__(16) uint8_t win[kNmsWin * kNmsWin];
+    __shared__ uint32_t s_cand[kNmsTile * kNmsTile];
+    __shared__ int s_ncand;
+    const int b = blockIdx.z;
+    if (a.retry && !a.retry[b])
+        return;
+    const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
+    const int x0 = blockIdx.x * kNmsTile - kNmsHalo, y0 = blockIdx.y * kNmsTile - kNmsHalo; // x0 is a multiple of 16
+    if (threadIdx.x == 0)
+        s_ncand = 0;
+    for (int w = threadIdx.x; w < kNmsWin * kNmsWin / 4; w += blockDim.x)
+    {
+        const int row = w / (kNmsWin / 4), gx = x0 + 4 * (w % (kNmsWin / 4)), gy = y0 + row;
+        uint32_t v = 0;
+        if (gy >= 0 && gy < a.rows && gx >= 0 && gx + 3 < a.pitch)
+            v = *reinterpret_cast<const uint32_t *>(sm + (size_t)gy * a.pitch + gx); // pitch padding is zero
+        reinterpret_cast<uint32_t *>(win)[w] = v;
+    }
+    __syncthreads();
+    auto score_at = [&](int xx, int yy) -> int {
+        if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
+            return 0;
+        const int lx = xx - x0, ly = yy - y0;
+        const int v = ((unsigned)lx < (unsigned)kNmsWin && (unsigned)ly < (unsigned)kNmsWin) ? win[ly * kNmsWin + lx]
+                                                                                              : sm[(size_t)yy * a.pitch + xx];
+        return v >= a.threshold ? v : 0;
+    };
+    // sweep: thread = one 4-pixel word of the 32x32 interior
+    {
+        const int row = threadIdx.x / (kNmsTile / 4), c4 = threadIdx.x % (kNmsTile / 4);
+        const int y = y0 + kNmsHalo + row;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const int x = x0 + kNmsHalo + 4 * c4 + k;
+            if (x >= a.cols || y >= a.rows)
+                continue;
+            const int s = score_at(x, y);
+            if (s == 0)
+                continue;
+            if (!a.nonmax)
+            {
+                emit_survivor(a, b, x, y, s);
+                continue;
+            }
+            const int up = score_at(x, y - 1), dn = score_at(x, y + 1), lf = score_at(x - 1, y), rt = score_at(x + 1, y);
+            if (max(max(up, dn), max(lf, rt)) > s)
+                continue; // a neighbour in the same component beats it
+            if ((up | dn | lf | rt) == 0)
+                emit_survivor(a, b, x, y, s); // isolated corner
+            else
+                s_cand[atomicAdd(&s_ncand, 1)] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+        }
+    }
+    __syncthreads();
+    const int n = s_ncand;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const uint32_t c = s_cand[i];
+        nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24));
     }
 }
 
@@ -1112,14 +1184,9 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
         NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, reinterpret_cast<uint32_t *>(ws.parent),
                    ws.cand_count, retry, dp.grid,
                    dp.pitch, dp.rows,     dp.cols,       ws.tile_cap,      nt,       th,    nonmax};
-        dim3 ngrid(((dp.cols + 3) / 4 + 127) / 128, dp.rows, n_images);
-        LVT_TIMED(stream, K_NMS, (nms_kernel<<<ngrid, 128, 0, stream>>>(na)));
-        LVT_LAUNCH_CHECK(stream, "nms_kernel");
-        if (nonmax)
-        {
-            LVT_TIMED(stream, K_NMS_RESOLVE, (nms_resolve_kernel<<<dim3(148, n_images), 128, 0, stream>>>(na)));
-            LVT_LAUNCH_CHECK(stream, "nms_resolve_kernel");
-        }
+        dim3 ngrid((dp.cols + kNmsTile - 1) / kNmsTile, (dp.rows + kNmsTile - 1) / kNmsTile, n_images);
+        LVT_TIMED(stream, K_NMS, (nms_tile_kernel<<<ngrid, 256, 0, stream>>>(na)));
+        LVT_LAUNCH_CHECK(stream, "nms_tile_kernel");
         if (nonmax)
         {
             LVT_TIMED(stream, K_NMS_FALLBACK, (nms_fallback_kernel<<<dim3(nt, n_images), 32, 0, stream>>>(na, ws.parent)));
