@@ -31,10 +31,8 @@ enum KernelId
 {
     K_SCORE,
     K_NMS,
-    K_NMS_FALLBACK,
     K_TILE,
     K_GATHER,
-    K_CLEAR,
     K_BRIEF,
     K_INDEX,
     K_TRACK_A,
@@ -43,7 +41,6 @@ enum KernelId
     K_POSE,
     K_STAGEDCAND,
     K_TRACK_B,
-    K_NMS_RESOLVE,
     K_COUNT
 };
 bool prof_enabled();

@@ -8,6 +8,8 @@
 // return LVTK_ERR_NO_DEVICE.
 #define LVT_EXPORT_FUNCTIONS
 #include "context.cuh"
+#include "upload.cuh"
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -379,6 +381,8 @@ struct lvtk_ctx
     FeatDev *feats_d = nullptr;
     int *d_slots = nullptr;
     uint8_t *h_stage = nullptr; // pinned, 2 tightly packed images
+    UploadLanes lanes;          // host staging lanes of the blocking entry points
+    int upload_bands = 1;       // row bands per image
     float *d_depth = nullptr, *h_depth = nullptr;
     // seam inputs
     float2 *d_in_xy = nullptr;
@@ -391,6 +395,7 @@ struct lvtk_ctx
     TrackState *d_state = nullptr;
     uint8_t *d_ctl = nullptr; // FrameCtl: hand-over between the kernels of the tracking chain
     FrameResult *d_result = nullptr, *h_result = nullptr;
+    int *h_error = nullptr; // pinned copy of ws.error, fetched together with the result
     // resident frame pool + pipelined streaming (lvt_pool_* / lvt_track_pool)
     cudaStream_t xs[kXStreams] = {}; // extraction runs here, tracking on `stream`
     DetectWorkspace wsx[kXStreams]; // wsx[0] == ws
@@ -544,9 +549,23 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     LVT_CUDA_TRY(cudaMemcpy(c->feats_d, c->feats_h, sizeof(c->feats_h), cudaMemcpyHostToDevice));
     const int slots[2] = {0, 1};
     LVT_CUDA_TRY(cudaMemcpy(c->d_slots, slots, sizeof(slots), cudaMemcpyHostToDevice));
-    LVT_CUDA_TRY(cudaMallocHost(&c->h_stage, (size_t)2 * p.img_width * p.img_height));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_stage, (size_t)2 * c->pool.pitch * p.img_height));
+    std::memset(c->h_stage, 0, (size_t)2 * c->pool.pitch * p.img_height);
     LVT_CUDA_TRY(cudaMallocHost(&c->h_depth, sizeof(float) * (size_t)p.img_width * p.img_height));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_result, sizeof(FrameResult)));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_error, sizeof(int)));
+    {
+        // staging lanes (the calling thread + workers): LVT_B200_UPLOAD_THREADS; row bands per image:
+        // LVT_B200_UPLOAD_BANDS.  Measured on the B200 box (tools/probe/host_probe.py): extra lanes
+        // shorten the staging by ~20 us but contend with the launches that follow for the driver's
+        // locks, so the default is the calling thread alone, one band per image.
+        int lanes = 1;
+        if (const char *e = std::getenv("LVT_B200_UPLOAD_THREADS"))
+            lanes = std::max(1, std::min(16, std::atoi(e)));
+        if (const char *e = std::getenv("LVT_B200_UPLOAD_BANDS"))
+            c->upload_bands = std::max(1, std::min(8, std::atoi(e)));
+        c->lanes.start(c->device, lanes - 1);
+    }
     if (!g_pairs_uploaded)
     {
         if (int r2 = upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr))
@@ -565,6 +584,7 @@ static void ctx_free(lvtk_ctx *c)
     if (!c)
         return;
     cudaSetDevice(c->device);
+    c->lanes.stop();
     if (c->stream)
     {
         cudaStreamSynchronize(c->stream);
@@ -596,21 +616,29 @@ static void ctx_free(lvtk_ctx *c)
         cudaFreeHost(c->h_depth);
     if (c->h_result)
         cudaFreeHost(c->h_result);
+    if (c->h_error)
+        cudaFreeHost(c->h_error);
     delete c;
 }
 
-// host image (any stride) -> pinned staging -> pitched pool slot
+// host image (any stride) -> pinned staging -> pitched pool slot, in row bands (upload.cuh);
+// ctx_stage_image queues an image, ctx_stage_flush stages and enqueues everything queued
+static void ctx_stage_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows, int cols, int stride)
+{
+    c->lanes.add_image(img, (size_t)stride, c->h_stage + (size_t)slot * rows * c->pool.pitch,
+                       c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, (size_t)cols, rows, c->upload_bands);
+}
+
+static int ctx_stage_flush(lvtk_ctx *c)
+{
+    LVT_CUDA_TRY(c->lanes.run(c->stream));
+    return LVTK_OK;
+}
+
 static int ctx_upload_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows, int cols, int stride)
 {
-    uint8_t *stage = c->h_stage + (size_t)slot * rows * cols;
-    if (stride == cols)
-        std::memcpy(stage, img, (size_t)rows * cols);
-    else
-        for (int y = 0; y < rows; y++)
-            std::memcpy(stage + (size_t)y * cols, img + (size_t)y * stride, cols);
-    LVT_CUDA_TRY(cudaMemcpy2DAsync(c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, stage, cols, cols, rows,
-                                   cudaMemcpyHostToDevice, c->stream));
-    return LVTK_OK;
+    ctx_stage_image(c, slot, img, rows, cols, stride);
+    return ctx_stage_flush(c);
 }
 
 static int ctx_download_features(lvtk_ctx *c, int which, lvtk_keypoint *out_kps, uint8_t *out_desc, int cap, int *n_out)
@@ -690,6 +718,21 @@ struct System
     PoseD last_pose;
     lvt_frame_info info;
 
+    // host-side time of the blocking entry points: [0] staging + H2D enqueue, [1] kernel enqueue,
+    // [2] waiting for the device, [3] calls  (lvt_debug_host_times)
+    double host_us[4] = {0, 0, 0, 0};
+    std::chrono::steady_clock::time_point marks[4];
+    void host_mark(int k)
+    {
+        marks[k] = std::chrono::steady_clock::now();
+        if (k == 3)
+        {
+            for (int i = 0; i < 3; i++)
+                host_us[i] += std::chrono::duration<double, std::micro>(marks[i + 1] - marks[i]).count();
+            host_us[3] += 1;
+        }
+    }
+
     System()
     {
         last_pose.q = Quat{1, 0, 0, 0};
@@ -728,9 +771,16 @@ struct System
                                         c->row_cand[0], c->fcap, c->stream))
             return rc;
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        host_mark(2);
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (int e = ctx_check_error(c))
+        host_mark(3);
+        if (const int e = *c->h_error)
+        {
+            cudaMemsetAsync(c->ws.error, 0, sizeof(int), c->stream);
+            set_last_error(__FILE__, __LINE__, "device-side capacity error");
             return e;
+        }
         info = c->h_result->info;
         info.frame_number = frame_number;
         state = info.state;
@@ -745,10 +795,12 @@ struct System
             return LVTK_ERR_ARG;
         if (lost_shortcut(out))
             return LVTK_OK;
-        if (int rc = ctx_upload_image(c, 0, left, rows, cols, cols))
+        host_mark(0);
+        ctx_stage_image(c, 0, left, rows, cols, cols);
+        ctx_stage_image(c, 1, right, rows, cols, cols);
+        if (int rc = ctx_stage_flush(c))
             return rc;
-        if (int rc = ctx_upload_image(c, 1, right, rows, cols, cols))
-            return rc;
+        host_mark(1);
         if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 2, c->feats_d, kBriefBorder, 1, c->stream))
             return rc;
         if (int rc = launch_brief(c->pool, c->d_slots, 2, c->feats_d, c->stream))
@@ -766,10 +818,12 @@ struct System
             return LVTK_ERR_CAPACITY;
         if (lost_shortcut(out))
             return LVTK_OK;
-        if (int rc = ctx_upload_image(c, 0, left, rows, cols, cols))
+        host_mark(0);
+        ctx_stage_image(c, 0, left, rows, cols, cols);
+        ctx_stage_image(c, 1, right, rows, cols, cols);
+        if (int rc = ctx_stage_flush(c))
             return rc;
-        if (int rc = ctx_upload_image(c, 1, right, rows, cols, cols))
-            return rc;
+        host_mark(1);
         std::vector<float2> xy((size_t)2 * c->pcap);
         for (int i = 0; i < nl; i++)
             xy[i] = make_float2((float)cl[i][0], (float)cl[i][1]);
@@ -794,11 +848,13 @@ struct System
             return LVTK_ERR_ARG;
         if (lost_shortcut(out))
             return LVTK_OK;
-        if (int rc = ctx_upload_image(c, 0, gray, rows, cols, cols))
+        host_mark(0);
+        ctx_stage_image(c, 0, gray, rows, cols, cols);
+        c->lanes.add_image(depth, sizeof(float) * (size_t)cols, c->h_depth, c->d_depth, sizeof(float) * (size_t)cols,
+                           sizeof(float) * (size_t)cols, rows, 2 * c->upload_bands);
+        if (int rc = ctx_stage_flush(c))
             return rc;
-        std::memcpy(c->h_depth, depth, sizeof(float) * (size_t)rows * cols);
-        LVT_CUDA_TRY(cudaMemcpyAsync(c->d_depth, c->h_depth, sizeof(float) * (size_t)rows * cols, cudaMemcpyHostToDevice,
-                                     c->stream));
+        host_mark(1);
         if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, c->stream))
             return rc;
         if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
@@ -1181,6 +1237,18 @@ LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int
     std::memcpy(rounds, r.rounds, sizeof(r.rounds));
     return 0;
 }
+/* profiling aid: host time of the blocking calls since the last reset, microseconds:
+ * out[0] staging + H2D enqueue, out[1] kernel enqueue, out[2] waiting for the device, out[3] calls */
+LVT_API int lvt_debug_host_times(lvt_handle h, double out[4], int reset)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return -1;
+    std::memcpy(out, vo->host_us, sizeof(vo->host_us));
+    if (reset)
+        std::memset(vo->host_us, 0, sizeof(vo->host_us));
+    return 0;
+}
 LVT_API double lvt_last_batch_ms(lvt_handle h)
 {
     System *vo = static_cast<System *>(h);
@@ -1218,10 +1286,9 @@ LVT_API void lvt_reset_kernel_times(void)
 }
 LVT_API const char *lvt_kernel_name(int id)
 {
-    static const char *names[K_COUNT] = {"score_kernel", "nms_kernel", "nms_fallback_kernel", "tile_kernel", "gather_kernel",
-                                         "clear_counts_kernel", "brief_kernel", "index_kernel", "track_a_kernel",
-                                         "mapcand_kernel", "rowcand_kernel", "pose_kernel", "stagedcand_kernel",
-                                         "track_b_kernel", "nms_resolve_kernel"};
+    static const char *names[K_COUNT] = {"score_kernel",   "nms_tile_kernel", "tile_kernel",    "gather_kernel",
+                                         "brief_kernel",   "index_kernel",    "track_a_kernel", "mapcand_kernel",
+                                         "rowcand_kernel", "pose_kernel",     "stagedcand_kernel", "track_b_kernel"};
     return id >= 0 && id < K_COUNT ? names[id] : "";
 }
 

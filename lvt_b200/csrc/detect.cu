@@ -9,12 +9,13 @@
 //                      exact AGAST score (max threshold for which it is a 9-of-16 segment-test
 //                      corner) is computed branch-free with packed 2 x s16 min/max; the dense
 //                      u8 score map goes to HBM (stays in L2).
-//   K2 nms_kernel    : one survivor per 4-connected component of corner pixels, OpenCV's
-//                      union-find tie-breaking replayed per component; survivors are appended to
-//                      their detection tile's list.
-//   K2b nms_fallback : the sequential algorithm for a tile with a component too large for K2.
-//   K3 tile_kernel   : per tile: raster sort, then (n > k) ANMS = all-pairs suppression radius,
-//                      radix-select of the (k+1)-th largest, emission in std::sort's order.
+//   K2 nms_tile_kernel: one survivor per 4-connected component of corner pixels: components are
+//                      labelled by max-propagation in a shared-memory window; OpenCV's union-find
+//                      tie-breaking is replayed only where several pixels share the maximum.
+//                      Survivors are appended to their detection tile's list.
+//   K3 tile_kernel   : per tile: (sequential NMS redo if K2 flagged the tile,) raster sort, then
+//                      (n > k) ANMS = suppression radius against the stronger prefix, radix-select
+//                      of the (k+1)-th largest, emission in std::sort's order (introsort replay).
 //   K4 gather_kernel : concatenates the tiles, applies BRIEF's 28-px border filter, decides the
 //                      <200-corner retry.
 #include "extract.cuh"
@@ -36,6 +37,8 @@ struct ScoreArgs
     TileGrid grid;
     int pitch, rows, cols;
     int min_score; // scores below this are stored as 0
+    int *tile_count, *tile_overflow; // [batch][n_tiles], zeroed here for the NMS that follows
+    int n_tiles;
 };
 
 // ring offsets (dx, dy) of OAST_9_16 in OpenCV's order
@@ -106,6 +109,9 @@ __global__ void __launch_bounds__(256) score_kernel(const __grid_constant__ CUte
     __shared__ __align__(8) uint64_t bar;
 
     const int x0 = blockIdx.x * kScoreTileW, y0 = blockIdx.y * kScoreTileH, b = blockIdx.z;
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = threadIdx.x; i < a.n_tiles; i += blockDim.x)
+            a.tile_count[b * a.n_tiles + i] = a.tile_overflow[b * a.n_tiles + i] = 0;
     if (threadIdx.x == 0)
     {
         mbar_init(&bar, 1);
@@ -153,8 +159,6 @@ struct NmsArgs
     const uint8_t *score;
     uint32_t *tile_list;
     int *tile_count, *tile_overflow, *error;
-    uint32_t *cand;   // [batch][rows * pitch] local maxima that need their component examined
-    int *cand_count;  // [batch]
     const int *retry; // nullptr on the first pass
     TileGrid grid;
     int pitch, rows, cols, tile_cap, n_tiles;
@@ -162,17 +166,37 @@ struct NmsArgs
     int nonmax;
 };
 
+
 constexpr int kCompCap = 96; // largest component replayed in registers/local memory
 
-__device__ __forceinline__ void emit_survivor(const NmsArgs &a, int b, int x, int y, int s)
+// Appends the CTA's survivors (s << 24 | y << 12 | x) to their detection tiles' lists.  Lanes of a
+// warp that hit the same tile reserve their slots with one atomicAdd (a few hot counters would
+// otherwise serialise tens of thousands of returning atomics per image).
+__device__ void flush_survivors(const NmsArgs &a, int b, const uint32_t *surv, int n)
 {
-    const int tx = x / a.grid.cell, ty = y / a.grid.cell, t = ty * a.grid.nx + tx;
-    const int raster = (y - ty * a.grid.cell) * a.grid.tile_w(tx) + (x - tx * a.grid.cell);
-    const int pos = atomicAdd(&a.tile_count[b * a.n_tiles + t], 1);
-    if (pos < a.tile_cap)
-        a.tile_list[((size_t)b * a.n_tiles + t) * a.tile_cap + pos] = ((uint32_t)raster << 8) | (uint32_t)s;
-    else
-        *a.error = LVTK_ERR_CAPACITY;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x)
+    {
+        const int i = i0 + threadIdx.x;
+        const bool on = i < n;
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, on);
+        if (!on)
+            continue;
+        const uint32_t c = surv[i];
+        const int x = (int)(c & 0xFFFu), y = (int)((c >> 12) & 0xFFFu), s = (int)(c >> 24);
+        const int tx = x / a.grid.cell, ty = y / a.grid.cell, t = ty * a.grid.nx + tx;
+        const int raster = (y - ty * a.grid.cell) * a.grid.tile_w(tx) + (x - tx * a.grid.cell);
+        const unsigned peers = __match_any_sync(active, t);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader)
+            base = atomicAdd(&a.tile_count[b * a.n_tiles + t], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const int pos = base + __popc(peers & ((1u << lane) - 1u));
+        if (pos < a.tile_cap)
+            a.tile_list[((size_t)b * a.n_tiles + t) * a.tile_cap + pos] = ((uint32_t)raster << 8) | (uint32_t)s;
+        else
+            *a.error = LVTK_ERR_CAPACITY;
+    }
 }
 
 // OpenCV's AGAST NMS restricted to one component: pts sorted in raster order, sc their scores.
@@ -249,37 +273,10 @@ __device__ int replay_component(const uint32_t *pts, const uint8_t *sc, int n)
     return 0;
 }
 
-// first look at a corner pixel: beaten by a 4-neighbour -> dropped; isolated -> survivor; otherwise
-// it is a local maximum whose component has to be examined (nms_resolve_kernel)
-__device__ void nms_pixel(const NmsArgs &a, int b, const uint8_t *sm, int x, int y, int s)
-{
-    if (!a.nonmax)
-    {
-        emit_survivor(a, b, x, y, s);
-        return;
-    }
-    auto score_at = [&](int xx, int yy) -> int {
-        if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
-            return 0;
-        const int v = sm[(size_t)yy * a.pitch + xx];
-        return v >= a.threshold ? v : 0;
-    };
-    const int up = score_at(x, y - 1), dn = score_at(x, y + 1), lf = score_at(x - 1, y), rt = score_at(x + 1, y);
-    if (max(max(up, dn), max(lf, rt)) > s)
-        return; // a neighbour in the same component beats it
-    if ((up | dn | lf | rt) == 0)
-    {
-        emit_survivor(a, b, x, y, s); // isolated corner
-        return;
-    }
-    const int pos = atomicAdd(&a.cand_count[b], 1);
-    a.cand[(size_t)b * a.rows * a.pitch + pos] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
-}
-
 // a local maximum: flood its component, decide whether it is the component's survivor.
 // score_at(x, y) = corner score at the current threshold, 0 outside the image / below it.
 template <class ScoreAt>
-__device__ void nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, int y, int s)
+__device__ bool nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, int y, int s)
 {
     // flood the component; give up as soon as anything larger shows up.  Visited test: linear
     // search while the component is small, then a 64x32-pixel bitmap around the start pixel
@@ -305,7 +302,7 @@ __device__ void nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
         for (int d = 0; d < 4; d++)
             vv[d] = score_at(px + (d == 0) - (d == 1), py + (d == 2) - (d == 3));
         if (max(max(vv[0], vv[1]), max(vv[2], vv[3])) > s)
-            return;
+            return false;
 #pragma unroll
         for (int d = 0; d < 4; d++)
         {
@@ -325,8 +322,8 @@ __device__ void nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
             if (n == kCompCap)
             {
                 const int t = (y / a.grid.cell) * a.grid.nx + (x / a.grid.cell);
-                a.tile_overflow[b * a.n_tiles + t] = 1; // K2b redoes this tile sequentially
-                return;
+                a.tile_overflow[b * a.n_tiles + t] = 1; // the tile is redone sequentially (nms_fallback_tile)
+                return false;
             }
             tie |= (v == s);
             pts[n] = q;
@@ -349,10 +346,7 @@ __device__ void nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
         }
     }
     if (!tie)
-    {
-        emit_survivor(a, b, x, y, s); // unique maximum of its component
-        return;
-    }
+        return true; // unique maximum of its component
     // several pixels share the maximum: OpenCV's merge order decides.  Insertion sort to
     // raster order, replay, and emit only if this pixel is the root.
     const uint32_t self = pts[0];
@@ -371,130 +365,372 @@ __device__ void nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
         sc[j + 1] = v;
     }
     const int root = replay_component(pts, sc, n);
-    if (pts[root] == self)
-        emit_survivor(a, b, x, y, s);
+    return pts[root] == self;
 }
 
-__global__ void __launch_bounds__(128) nms_kernel(NmsArgs a)
-{
-    const int b = blockIdx.z;
-    if (a.retry && !a.retry[b])
-        return;
-    const int y = blockIdx.y, xw = blockIdx.x * blockDim.x + threadIdx.x;
-    if (xw * 4 >= a.cols)
-        return;
-    const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
-    const uint32_t word = *reinterpret_cast<const uint32_t *>(sm + (size_t)y * a.pitch + xw * 4);
-    if (word == 0)
-        return;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-    {
-        const int s = (word >> (8 * k)) & 0xFF;
-        if (s >= a.threshold && s != 0 && xw * 4 + k < a.cols)
-            nms_pixel(a, b, sm, xw * 4 + k, y, s);
-    }
-}
-
-// one thread per local maximum, densely packed (the marking kernel above is a coalesced sweep)
-__global__ void __launch_bounds__(128) nms_resolve_kernel(NmsArgs a)
-{
-    const int b = blockIdx.y;
-    if (a.retry && !a.retry[b])
-        return;
-    const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
-    const int n = a.cand_count[b];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const uint32_t c = a.cand[(size_t)b * a.rows * a.pitch + i];
-        auto score_at = [&](int xx, int yy) -> int {
-            if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
-                return 0;
-            const int v = sm[(size_t)yy * a.pitch + xx];
-            return v >= a.threshold ? v : 0;
-        };
-        nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24));
-    }
-}
-
-// Fused NMS: a CTA stages a 64x64 window of the score map (its 32x32 pixels + 16 px halo) in shared
-// memory, sweeps its pixels (beaten / isolated / local maximum), then resolves its local maxima with
-// the component flood reading shared memory (global memory only outside the window).
+// Fused NMS.  A CTA stages a 64x64 window of the score map (its 32x32 pixels + 16 px halo) in shared
+// memory and labels the 4-connected corner components inside it by max-propagation: every corner
+// starts with (score << 12 | local index) and repeatedly takes the maximum over itself and its four
+// neighbours until nothing changes, so each pixel ends up holding the score and position of its
+// component's maximum.  Then, per pixel of the interior:
+//   * score below the component maximum             -> suppressed
+//   * the only pixel carrying the maximum           -> survivor          (the common case)
+//   * one of several pixels carrying the maximum    -> OpenCV's merge order decides: nms_resolve
+//   * component reaches the window's outer ring     -> labels may be incomplete: nms_resolve
+// The propagation is a few dozen shared-memory sweeps over the corner list; the sequential flood
+// of nms_resolve is left for ties and for components that leave the window.
 constexpr int kNmsTile = 32, kNmsHalo = 16, kNmsWin = kNmsTile + 2 * kNmsHalo;
+constexpr uint32_t kNmsOpen = 0xFFFFFFFFu; // label of a corner on the window's ring
+constexpr int kNmsSlowCap = 256;           // per CTA: components with a shared maximum / open-label candidates;
+                                           // beyond that the detection tile is redone sequentially
+
+
+// One warp settles a component whose maximum is shared by several pixels.  The component is the set
+// of window pixels labelled L (complete: its label is closed).  The lanes collect the members in
+// raster order and link each to the member directly above; lane 0 then replays OpenCV's merge
+// sequence (same decisions as replay_component) on shared-memory arrays.  Returns the local index of
+// the surviving root, or -1 if the component has more than kCompCap pixels.
+struct WarpComp
+{
+    uint16_t mem[kCompCap];
+    uint8_t above[kCompCap], sc[kCompCap];
+    int8_t par[kCompCap];
+};
+
+__device__ int warp_replay_component(const uint32_t *lab, const uint8_t *win, int n_win, int row_w, uint32_t L, WarpComp &w)
+{
+    const int lane = threadIdx.x & 31;
+    int n = 0;
+    for (int base = 0; base < n_win; base += 32)
+    {
+        const bool m = lab[base + lane] == L;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
+        if (m)
+        {
+            const int pos = n + __popc(bal & ((1u << lane) - 1u));
+            if (pos < kCompCap)
+                w.mem[pos] = (uint16_t)(base + lane);
+        }
+        n += __popc(bal);
+    }
+    if (n > kCompCap)
+        return -1;
+    __syncwarp();
+    for (int j = lane; j < n; j += 32)
+    {
+        const int lid = w.mem[j], up = lid - row_w;
+        int ab = 255;
+        if (lab[up] == L)
+        {
+            int lo = 0, hi = j - 1; // mem is ascending and contains up
+            while (lo < hi)
+            {
+                const int mid = (lo + hi) >> 1;
+                if (w.mem[mid] < up)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            ab = lo;
+        }
+        w.above[j] = (uint8_t)ab;
+        w.par[j] = -1;
+        w.sc[j] = win[lid];
+    }
+    __syncwarp();
+    int root = 0;
+    if (lane == 0)
+    {
+        auto find = [&](int i) {
+            while (w.par[i] != -1)
+                i = w.par[i];
+            return i;
+        };
+        for (int c = 0; c < n; c++)
+        {
+            if (w.above[c] != 255)
+            {
+                const int r = find(w.above[c]);
+                if (w.sc[c] < w.sc[r])
+                    w.par[c] = (int8_t)r;
+                else
+                    w.par[r] = (int8_t)c;
+            }
+            if (c != 0 && w.mem[c - 1] + 1 == w.mem[c])
+            {
+                const int pa = w.par[c], t = find(c - 1);
+                if (pa == -1)
+                {
+                    if (t != c)
+                    {
+                        if (w.sc[c] < w.sc[t])
+                            w.par[c] = (int8_t)t;
+                        else
+                            w.par[t] = (int8_t)c;
+                    }
+                }
+                else if (t != pa)
+                {
+                    if (w.sc[pa] < w.sc[t])
+                    {
+                        w.par[pa] = (int8_t)t;
+                        w.par[c] = (int8_t)t;
+                    }
+                    else
+                    {
+                        w.par[t] = (int8_t)pa;
+                        w.par[c] = (int8_t)pa;
+                    }
+                }
+            }
+        }
+        for (int i = 0; i < n; i++)
+            if (w.par[i] == -1)
+            {
+                root = i;
+                break;
+            }
+        root = w.mem[root];
+    }
+    return __shfl_sync(0xFFFFFFFFu, root, 0);
+}
+
+#ifdef LVT_NMS_STATS
+// per-CTA trace of the last full launch: [0] start ns, [1] end ns, [2..6] cycles of stage / propagate / classify /
+// resolve / flush, [7] slow candidates, [8] corners in the window, [9] survivors, [10] sweeps, [11] longest resolve
+__device__ long long g_nms_trace[4096][12];
+__device__ __forceinline__ long long nms_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define NMS_TR(k, v)                                                                                                  \
+    if (threadIdx.x == 0)                                                                                             \
+    g_nms_trace[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x][k] = (long long)(v)
+#else
+#define NMS_TR(k, v)
+#endif
 
 __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
 {
+#ifdef LVT_NMS_STATS
+    __shared__ unsigned long long s_longest;
+    if (threadIdx.x == 0)
+        s_longest = 0;
+    long long ck = clock64(), cn;
+    NMS_TR(0, nms_ns());
+#define NMS_PHASE(k)                                                                                                  \
+    cn = clock64();                                                                                                   \
+    NMS_TR(k, cn - ck);                                                                                               \
+    ck = cn
+#else
+#define NMS_PHASE(k)
+#endif
     __shared__ __align__(16) uint8_t win[kNmsWin * kNmsWin];
-    __shared__ uint32_t s_cand[kNmsTile * kNmsTile];
-    __shared__ int s_ncand;
+    __shared__ uint32_t lab[kNmsWin * kNmsWin];
+    __shared__ uint16_t s_list[kNmsWin * kNmsWin];
+    __shared__ __align__(16) uint8_t s_tied[kNmsWin * kNmsWin];
+    __shared__ uint32_t s_cand[kNmsSlowCap], s_surv[kNmsTile * kNmsTile];
+    __shared__ uint16_t s_job[kNmsSlowCap];
+    __shared__ WarpComp s_comp[8];
+    __shared__ int s_nlist, s_ncand, s_nsurv, s_njob;
     const int b = blockIdx.z;
     if (a.retry && !a.retry[b])
         return;
     const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
     const int x0 = blockIdx.x * kNmsTile - kNmsHalo, y0 = blockIdx.y * kNmsTile - kNmsHalo; // x0 is a multiple of 16
     if (threadIdx.x == 0)
-        s_ncand = 0;
+        s_nlist = s_ncand = s_nsurv = s_njob = 0;
+    // stage the window, thresholded: 0 = not a corner
+    const uint32_t th4 = (uint32_t)a.threshold * 0x01010101u;
     for (int w = threadIdx.x; w < kNmsWin * kNmsWin / 4; w += blockDim.x)
     {
         const int row = w / (kNmsWin / 4), gx = x0 + 4 * (w % (kNmsWin / 4)), gy = y0 + row;
         uint32_t v = 0;
         if (gy >= 0 && gy < a.rows && gx >= 0 && gx + 3 < a.pitch)
             v = *reinterpret_cast<const uint32_t *>(sm + (size_t)gy * a.pitch + gx); // pitch padding is zero
+        if (v)
+        {
+            const uint32_t ge = __vcmpgeu4(v, th4); // 0xFF per byte >= threshold
+            v &= ge;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (gx + k >= a.cols)
+                    v &= ~(0xFFu << (8 * k));
+        }
         reinterpret_cast<uint32_t *>(win)[w] = v;
+        reinterpret_cast<uint32_t *>(s_tied)[w] = 0;
     }
     __syncthreads();
     auto score_at = [&](int xx, int yy) -> int {
         if (xx < 0 || yy < 0 || xx >= a.cols || yy >= a.rows)
             return 0;
         const int lx = xx - x0, ly = yy - y0;
-        const int v = ((unsigned)lx < (unsigned)kNmsWin && (unsigned)ly < (unsigned)kNmsWin) ? win[ly * kNmsWin + lx]
-                                                                                              : sm[(size_t)yy * a.pitch + xx];
+        if ((unsigned)lx < (unsigned)kNmsWin && (unsigned)ly < (unsigned)kNmsWin)
+            return win[ly * kNmsWin + lx];
+        const int v = sm[(size_t)yy * a.pitch + xx];
         return v >= a.threshold ? v : 0;
     };
-    // sweep: thread = one 4-pixel word of the 32x32 interior
+    if (!a.nonmax)
     {
-        const int row = threadIdx.x / (kNmsTile / 4), c4 = threadIdx.x % (kNmsTile / 4);
-        const int y = y0 + kNmsHalo + row;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int i = threadIdx.x; i < kNmsTile * kNmsTile; i += blockDim.x)
         {
-            const int x = x0 + kNmsHalo + 4 * c4 + k;
-            if (x >= a.cols || y >= a.rows)
-                continue;
-            const int s = score_at(x, y);
-            if (s == 0)
-                continue;
-            if (!a.nonmax)
+            const int lx = kNmsHalo + i % kNmsTile, ly = kNmsHalo + i / kNmsTile;
+            const int s = win[ly * kNmsWin + lx];
+            if (s && y0 + ly < a.rows)
+                s_surv[atomicAdd(&s_nsurv, 1)] = ((uint32_t)s << 24) | ((uint32_t)(y0 + ly) << 12) | (uint32_t)(x0 + lx);
+        }
+        __syncthreads();
+        flush_survivors(a, b, s_surv, s_nsurv);
+        return;
+    }
+    // initial labels + list of the corners that take part in the propagation
+    for (int i = threadIdx.x; i < kNmsWin * kNmsWin; i += blockDim.x)
+    {
+        const int v = win[i];
+        const int lx = i % kNmsWin, ly = i / kNmsWin;
+        const bool ring = lx == 0 || ly == 0 || lx == kNmsWin - 1 || ly == kNmsWin - 1;
+        uint32_t l = 0;
+        if (v)
+        {
+            l = ring ? kNmsOpen : (((uint32_t)v << 12) | (uint32_t)i);
+            if (!ring)
+                s_list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
+        }
+        lab[i] = l;
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    NMS_PHASE(2);
+    NMS_TR(8, nl);
+    NMS_TR(1, nms_ns());
+    if (nl == 0)
+        return;
+    int sweeps = 0;
+    // max-propagation to the fixed point (in place: the update is monotone, any order converges)
+    for (;;)
+    {
+        int changed = 0;
+        for (int k = threadIdx.x; k < nl; k += blockDim.x)
+        {
+            const int i = s_list[k];
+            const uint32_t cur = lab[i];
+            const uint32_t m = max(max(max(lab[i - 1], lab[i + 1]), max(lab[i - kNmsWin], lab[i + kNmsWin])), cur);
+            if (m != cur)
             {
-                emit_survivor(a, b, x, y, s);
-                continue;
+                lab[i] = m;
+                changed = 1;
             }
-            const int up = score_at(x, y - 1), dn = score_at(x, y + 1), lf = score_at(x - 1, y), rt = score_at(x + 1, y);
-            if (max(max(up, dn), max(lf, rt)) > s)
-                continue; // a neighbour in the same component beats it
-            if ((up | dn | lf | rt) == 0)
-                emit_survivor(a, b, x, y, s); // isolated corner
+        }
+        sweeps++;
+        if (!__syncthreads_or(changed))
+            break;
+    }
+    NMS_PHASE(3);
+    NMS_TR(10, sweeps);
+    // a pixel that carries its component's maximum but is not the label holder: the maximum is shared
+    for (int k = threadIdx.x; k < nl; k += blockDim.x)
+    {
+        const int i = s_list[k];
+        const uint32_t l = lab[i];
+        if (l != kNmsOpen && (l >> 12) == win[i] && (int)(l & 0xFFFu) != i)
+            s_tied[l & 0xFFFu] = 1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nl; k += blockDim.x)
+    {
+        const int i = s_list[k];
+        const int lx = i % kNmsWin, ly = i / kNmsWin;
+        if (lx < kNmsHalo || lx >= kNmsHalo + kNmsTile || ly < kNmsHalo || ly >= kNmsHalo + kNmsTile)
+            continue;
+        const int s = win[i], x = x0 + lx, y = y0 + ly;
+        const uint32_t l = lab[i];
+        if (l != kNmsOpen)
+        {
+            if ((int)(l >> 12) != s)
+                continue; // not the maximum of its component
+            if ((int)(l & 0xFFFu) == i && !s_tied[i])
+                s_surv[atomicAdd(&s_nsurv, 1)] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x; // unique maximum
             else
-                s_cand[atomicAdd(&s_ncand, 1)] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+                s_tied[l & 0xFFFu] = 2; // shared maximum with a pixel in this CTA's interior: settle the component
+            continue;
+        }
+        if (max(max(win[i - 1], win[i + 1]), max(win[i - kNmsWin], win[i + kNmsWin])) > s)
+            continue; // beaten by a neighbour
+        const int pos = atomicAdd(&s_ncand, 1);
+        if (pos < kNmsSlowCap)
+            s_cand[pos] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+        else
+            a.tile_overflow[b * a.n_tiles + (y / a.grid.cell) * a.grid.nx + x / a.grid.cell] = 1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nl; k += blockDim.x)
+    {
+        const int i = s_list[k];
+        if (s_tied[i] == 2 && (int)(lab[i] & 0xFFFu) == i)
+        {
+            const int pos = atomicAdd(&s_njob, 1);
+            if (pos < kNmsSlowCap)
+                s_job[pos] = (uint16_t)i;
+            else
+            {
+                // the component lies in one detection tile (tile borders carry no corners)
+                const int gx = x0 + i % kNmsWin, gy = y0 + i / kNmsWin;
+                a.tile_overflow[b * a.n_tiles + (gy / a.grid.cell) * a.grid.nx + gx / a.grid.cell] = 1;
+            }
         }
     }
     __syncthreads();
-    const int n = s_ncand;
+    NMS_PHASE(4);
+    {
+        const int njob = min(s_njob, kNmsSlowCap);
+        const int warp = threadIdx.x >> 5;
+        for (int j = warp; j < njob; j += 8)
+        {
+            const int h = s_job[j];
+            const int r = warp_replay_component(lab, win, kNmsWin * kNmsWin, kNmsWin, lab[h], s_comp[warp]);
+            if ((threadIdx.x & 31) == 0)
+            {
+                const int q = r < 0 ? h : r, lx = q % kNmsWin, ly = q / kNmsWin;
+                if (r < 0)
+                    a.tile_overflow[b * a.n_tiles + ((y0 + ly) / a.grid.cell) * a.grid.nx + (x0 + lx) / a.grid.cell] = 1;
+                else if (lx >= kNmsHalo && lx < kNmsHalo + kNmsTile && ly >= kNmsHalo && ly < kNmsHalo + kNmsTile)
+                    s_surv[atomicAdd(&s_nsurv, 1)] = ((uint32_t)win[r] << 24) | ((uint32_t)(y0 + ly) << 12) | (uint32_t)(x0 + lx);
+            }
+            __syncwarp();
+        }
+    }
+    const int n = min(s_ncand, kNmsSlowCap);
     for (int i = threadIdx.x; i < n; i += blockDim.x)
     {
         const uint32_t c = s_cand[i];
-        nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24));
+#ifdef LVT_NMS_STATS
+        const long long r0 = clock64();
+#endif
+        if (nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24)))
+            s_surv[atomicAdd(&s_nsurv, 1)] = c;
+#ifdef LVT_NMS_STATS
+        atomicMax(&s_longest, (unsigned long long)(clock64() - r0));
+#endif
     }
+    __syncthreads();
+    NMS_PHASE(5);
+    flush_survivors(a, b, s_surv, s_nsurv);
+#ifdef LVT_NMS_STATS
+    __syncthreads();
+    NMS_PHASE(6);
+    NMS_TR(7, n);
+    NMS_TR(9, s_nsurv);
+    NMS_TR(11, s_longest);
+    NMS_TR(1, nms_ns());
+#endif
 }
 
-// K2b: sequential fallback, one thread per flagged tile (pathological inputs only)
-__global__ void nms_fallback_kernel(NmsArgs a, int *parent_all)
+// K2b: sequential fallback for a tile flagged by nms_resolve (pathological inputs only); run by
+// one thread of the tile's tile_kernel CTA before it reads the list
+__device__ void nms_fallback_tile(const NmsArgs &a, int *parent_all, int t, int b)
 {
-    const int t = blockIdx.x, b = blockIdx.y;
-    if (threadIdx.x != 0 || !a.tile_overflow[b * a.n_tiles + t])
-        return;
-    if (a.retry && !a.retry[b])
-        return;
     const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
     int *parent = parent_all + (size_t)b * a.rows * a.pitch;
     const int tx = t % a.grid.nx, ty = t / a.grid.nx;
@@ -579,7 +815,8 @@ struct TileArgs
     const int *retry;
     TileGrid grid;
     int tile_cap, n_tiles, max_per_cell;
-    long long *dbg; // optional clock64() marks [tile][8]
+    NmsArgs nms; // for the sequential NMS fallback
+    int *parent;
 };
 
 constexpr int kTileSmemCap = 8192; // tiles with more survivors work out of global scratch
@@ -651,83 +888,6 @@ __device__ int warp_partition(uint32_t *a, int first, int last, uint16_t *posL, 
 }
 
 constexpr int kCoopRange = 96; // ranges at least this long are partitioned by the whole warp
-
-// the same schedule run by ONE warp so that the other warps of the CTA can compute the suppression
-// radii at the same time: long ranges are partitioned cooperatively (warp_partition), short ones
-// lane-per-range, __syncwarp between levels
-__device__ void warp_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, volatile int *s_cnt,
-                               uint16_t *posL, uint16_t *posR)
-{
-    const int lane = threadIdx.x & 31;
-    if (n <= 1)
-        return;
-    int lg = 0;
-    for (int v = n; v > 1; v >>= 1)
-        lg++;
-    if (lane == 0)
-    {
-        q0[0] = isort::LevelRange{0, n, 2 * lg};
-        s_cnt[0] = 1;
-        s_cnt[1] = 0;
-    }
-    __syncwarp();
-    isort::LevelRange *cur = q0, *nxt = q1;
-    int which = 0;
-    while (true)
-    {
-        const int ncur = s_cnt[which];
-        if (ncur == 0)
-            break;
-        // long ranges: one after another, all lanes together
-        for (int i = 0; i < ncur; i++)
-        {
-            const isort::LevelRange r = cur[i];
-            if (r.last - r.first < kCoopRange || r.depth == 0)
-                continue;
-            if (lane == 0)
-            {
-                uint32_t *f = a + r.first, *l = a + r.last;
-                isort::move_median_to_first(f, f + 1, f + (l - f) / 2, l - 1);
-            }
-            __syncwarp();
-            const int cut = warp_partition(a, r.first, r.last, posL, posR);
-            if (lane == 0)
-            {
-                const int slot = atomicAdd((int *)&s_cnt[which ^ 1], 2);
-                nxt[slot] = isort::LevelRange{r.first, cut, r.depth - 1};
-                nxt[slot + 1] = isort::LevelRange{cut, r.last, r.depth - 1};
-            }
-        }
-        __syncwarp();
-        // short ranges (and heap-sort fallbacks): lane per range
-        for (int i = lane; i < ncur; i += 32)
-        {
-            const isort::LevelRange r = cur[i];
-            if (r.last - r.first >= kCoopRange && r.depth != 0)
-                continue;
-            if (r.last - r.first <= 16)
-            {
-                isort::insertion_sort(a + r.first, a + r.last);
-                continue;
-            }
-            isort::LevelRange l, rr;
-            if (isort::split_range(a, r, l, rr))
-            {
-                const int slot = atomicAdd((int *)&s_cnt[which ^ 1], 2);
-                nxt[slot] = l;
-                nxt[slot + 1] = rr;
-            }
-        }
-        __syncwarp();
-        if (lane == 0)
-            s_cnt[which] = 0;
-        which ^= 1;
-        isort::LevelRange *t = cur;
-        cur = nxt;
-        nxt = t;
-        __syncwarp();
-    }
-}
 
 // stable sort of a leaf range (<= 16 elements) by rank: what the final insertion sort does to it
 // (a stable sort's result is unique).  Lanes 0..len-1 hold one element each.
@@ -839,7 +999,7 @@ __device__ void block_bitonic_sort(uint32_t *keys, int P)
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
+__global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
 {
     extern __shared__ uint32_t s_dyn[];
     uint32_t *s_keys = s_dyn, *s_rad = s_dyn + kTileSmemCap, *s_perm = s_dyn + 2 * kTileSmemCap;
@@ -854,10 +1014,12 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     const int t = blockIdx.x, b = blockIdx.y;
     if (a.retry && !a.retry[b])
         return;
-#define LVT_TDBG(k)                                                                                                   \
-    if (a.dbg && threadIdx.x == 0)                                                                                    \
-    a.dbg[(b * a.n_tiles + t) * 8 + k] = clock64()
-    LVT_TDBG(0);
+    if (a.nms.tile_overflow[b * a.n_tiles + t])
+    {
+        if (threadIdx.x == 0)
+            nms_fallback_tile(a.nms, a.parent, t, b);
+        __syncthreads();
+    }
     const int tx = t % a.grid.nx, ty = t / a.grid.nx;
     const int x0 = tx * a.grid.cell, y0 = ty * a.grid.cell, tw = a.grid.tile_w(tx);
     const size_t base = ((size_t)b * a.n_tiles + t) * a.tile_cap;
@@ -906,8 +1068,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
             a.tile_out_count[b * a.n_tiles + t] = n;
         return;
     }
-
-    LVT_TDBG(1);
     // ---- ANMS (lvt_image_features_handler.cpp:34-83) ------------------------------------------
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         perm[i] = ((keys[i] & 0xFFu) << 24) | (uint32_t)i;
@@ -918,7 +1078,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     else if (threadIdx.x == 0)
         isort::sort(perm, n); // more survivors than fit in shared memory (pathological): sequential replay
     __syncthreads();
-    LVT_TDBG(2);
     // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own.  In the sorted
     // order those corners are a prefix: s_hist[v] = number of corners with response >= v.
     for (int i = threadIdx.x; i < 257; i += blockDim.x)
@@ -955,9 +1114,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
         }
         rad[i] = best;
     }
-    LVT_TDBG(3);
     __syncthreads();
-    LVT_TDBG(4);
 
     // :66-71  decision = radiiSorted[num_to_keep]  (descending) -> MSB-first radix select
     if (threadIdx.x == 0)
@@ -1019,7 +1176,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
         __syncthreads();
     }
     const uint32_t decision = s_prefix;
-    LVT_TDBG(5);
 
     // :72-80  keep radius >= decision, in sorted order
     int running = 0;
@@ -1042,9 +1198,6 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(TileArgs a)
     }
     if (threadIdx.x == 0)
         a.tile_out_count[b * a.n_tiles + t] = running;
-    LVT_TDBG(6);
-    if (a.dbg && threadIdx.x == 0)
-        a.dbg[(b * a.n_tiles + t) * 8 + 7] = n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1055,6 +1208,7 @@ struct GatherArgs
     const uint32_t *tile_out;
     const int *tile_out_count;
     int *retry, *error;
+    int *tile_count, *tile_overflow; // zeroed for an image that goes into the lowered-threshold pass
     FeatDev *feats;
     int n_tiles, tile_cap, rows, cols;
     int border;      // 28 = BRIEF filter, 0 = none
@@ -1088,7 +1242,11 @@ __global__ void __launch_bounds__(1024) gather_kernel(GatherArgs a)
         if (threadIdx.x == 0)
             a.retry[b] = redo;
         if (redo)
+        {
+            for (int t = threadIdx.x; t < nt; t += blockDim.x)
+                a.tile_count[b * nt + t] = a.tile_overflow[b * nt + t] = 0;
             return;
+        }
     }
     const FeatDev f = a.feats[b];
     int running = 0;
@@ -1140,19 +1298,6 @@ __global__ void __launch_bounds__(1024) gather_kernel(GatherArgs a)
     }
 }
 
-__global__ void clear_counts_kernel(int *tile_count, int *tile_overflow, int *cand_count, int n, const int *retry, int n_tiles)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    if (retry && !retry[i / n_tiles])
-        return;
-    tile_count[i] = 0;
-    tile_overflow[i] = 0;
-    if (i % n_tiles == 0)
-        cand_count[i / n_tiles] = 0;
-}
-
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
@@ -1170,50 +1315,29 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     }
     const bool allow_retry = dp.threshold_low < dp.threshold;
 
-    ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold};
+    ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold,
+                 ws.tile_count, ws.tile_overflow, nt};
     dim3 sgrid((dp.cols + kScoreTileW - 1) / kScoreTileW, (dp.rows + kScoreTileH - 1) / kScoreTileH, n_images);
     LVT_TIMED(stream, K_SCORE, (score_kernel<<<sgrid, 256, 0, stream>>>(pool.tmap_score, sa)));
     LVT_LAUNCH_CHECK(stream, "score_kernel");
 
+    // pass 1 (threshold halved, :161-169) is launched unconditionally and exits at once for images
+    // whose first pass found enough corners: the decision is on the device, the host never waits
     for (int pass = 0; pass < (allow_retry ? 2 : 1); pass++)
     {
         const int *retry = pass ? ws.retry : nullptr;
         const int th = pass ? dp.threshold_low : dp.threshold;
-        LVT_TIMED(stream, K_CLEAR, (clear_counts_kernel<<<(n_images * nt + 255) / 256, 256, 0, stream>>>(ws.tile_count, ws.tile_overflow, ws.cand_count,
-                                                                            n_images * nt, retry, nt)));
-        NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, reinterpret_cast<uint32_t *>(ws.parent),
-                   ws.cand_count, retry, dp.grid,
-                   dp.pitch, dp.rows,     dp.cols,       ws.tile_cap,      nt,       th,    nonmax};
+        NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, retry,      dp.grid,
+                   dp.pitch, dp.rows,      dp.cols,       ws.tile_cap,      nt,       th,         nonmax};
         dim3 ngrid((dp.cols + kNmsTile - 1) / kNmsTile, (dp.rows + kNmsTile - 1) / kNmsTile, n_images);
         LVT_TIMED(stream, K_NMS, (nms_tile_kernel<<<ngrid, 256, 0, stream>>>(na)));
         LVT_LAUNCH_CHECK(stream, "nms_tile_kernel");
-        if (nonmax)
-        {
-            LVT_TIMED(stream, K_NMS_FALLBACK, (nms_fallback_kernel<<<dim3(nt, n_images), 32, 0, stream>>>(na, ws.parent)));
-            LVT_LAUNCH_CHECK(stream, "nms_fallback_kernel");
-        }
-        TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count, ws.tile_out_count, retry,
-                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell,
-                    (pass == 0 && debug_sync_enabled()) ? reinterpret_cast<long long *>(ws.tile_aux) : nullptr}; // scratch unused for small tiles
-        static bool dumped = false;
+        TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count,   ws.tile_out_count, retry,
+                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell, na,                ws.parent};
         LVT_TIMED(stream, K_TILE, (tile_kernel<<<dim3(nt, n_images), kTileThreads, kTileSmemBytes, stream>>>(ta)));
         LVT_LAUNCH_CHECK(stream, "tile_kernel");
-        if (ta.dbg && !dumped && std::getenv("LVT_B200_TILEDBG"))
-        {
-            static int calls = 0;
-            if (++calls == 8)
-            {
-                dumped = true;
-                std::vector<long long> h((size_t)nt * n_images * 8);
-                cudaMemcpy(h.data(), ta.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-                for (int i = 0; i < nt * n_images; i++)
-                    std::fprintf(stderr, "tile %2d n=%4lld: load+bitonic %6lld | sort %6lld (radii %6lld) | sync %6lld | select %6lld | compact %6lld cycles\n", i,
-                                 h[i * 8 + 7], h[i * 8 + 1] - h[i * 8], h[i * 8 + 2] - h[i * 8 + 1], h[i * 8 + 3] - h[i * 8 + 1],
-                                 h[i * 8 + 4] - h[i * 8 + 1], h[i * 8 + 5] - h[i * 8 + 4], h[i * 8 + 6] - h[i * 8 + 5]);
-            }
-        }
-        GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, d_feats, nt, ws.tile_cap,
-                      dp.rows,     dp.cols,           border,   pass,     allow_retry ? kCornersLowTh : 0};
+        GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, ws.tile_count, ws.tile_overflow, d_feats, nt,
+                      ws.tile_cap, dp.rows,           dp.cols,  border,   pass,          allow_retry ? kCornersLowTh : 0};
         LVT_TIMED(stream, K_GATHER, (gather_kernel<<<n_images, 1024, 0, stream>>>(ga)));
         LVT_LAUNCH_CHECK(stream, "gather_kernel");
     }
@@ -1222,3 +1346,12 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
 }
 
 } // namespace lvtb
+
+#ifdef LVT_NMS_STATS
+extern "C" __attribute__((visibility("default"))) int lvt_debug_nms_trace(long long *out /* [4096][12] */)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, lvtb::g_nms_trace, sizeof(long long) * 4096 * 12);
+}
+#endif
+
