@@ -400,6 +400,7 @@ struct lvtk_ctx
     cudaStream_t xs[kXStreams] = {}; // extraction runs here, tracking on `stream`
     DetectWorkspace wsx[kXStreams]; // wsx[0] == ws
     cudaEvent_t ev_extracted[kSets] = {}, ev_tracked[kSets] = {};
+    cudaEvent_t ev_left = nullptr, ev_right = nullptr; // blocking stereo path: left features indexed / right side ready
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; // device time of the last lvt_track_pool call
     float last_batch_ms = 0.f;
     DeviceArena rarena;
@@ -467,6 +468,8 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     }
     for (int i = 0; i < 2; i++)
         LVT_CUDA_TRY(cudaEventCreate(&c->ev_batch[i]));
+    LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming));
+    LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_right, cudaEventDisableTiming));
 
     if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
         return rc;
@@ -606,6 +609,10 @@ static void ctx_free(lvtk_ctx *c)
     for (int i = 0; i < 2; i++)
         if (c->ev_batch[i])
             cudaEventDestroy(c->ev_batch[i]);
+    if (c->ev_left)
+        cudaEventDestroy(c->ev_left);
+    if (c->ev_right)
+        cudaEventDestroy(c->ev_right);
     c->rarena.release();
     if (c->h_results)
         cudaFreeHost(c->h_results);
@@ -629,9 +636,9 @@ static void ctx_stage_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows,
                        c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, (size_t)cols, rows, c->upload_bands);
 }
 
-static int ctx_stage_flush(lvtk_ctx *c)
+static int ctx_stage_flush(lvtk_ctx *c, cudaStream_t stream = nullptr)
 {
-    LVT_CUDA_TRY(c->lanes.run(c->stream));
+    LVT_CUDA_TRY(c->lanes.run(stream ? stream : c->stream));
     return LVTK_OK;
 }
 
@@ -770,6 +777,13 @@ struct System
         if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc,
                                         c->row_cand[0], c->fcap, c->stream))
             return rc;
+        return fetch_result(out);
+    }
+
+    // the frame's kernels are enqueued on ctx->stream: fetch the result (the one host<->device round trip)
+    int fetch_result(PoseD *out)
+    {
+        lvtk_ctx *c = ctx;
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, c->stream));
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         host_mark(2);
@@ -788,6 +802,11 @@ struct System
         return LVTK_OK;
     }
 
+    // Blocking stereo frame.  Only the left image is on the path to the pose (map matching and the
+    // solver never look at the right one), so the two images go down two streams: the left one is
+    // staged, uploaded and extracted first and tracking starts right behind it, while the host stages
+    // the right image and a second stream extracts it and lists the row-matching candidates; the two
+    // meet in front of track_b (staged points + triangulation).
     int track_stereo(const uint8_t *left, const uint8_t *right, int rows, int cols, PoseD *out)
     {
         lvtk_ctx *c = ctx;
@@ -795,17 +814,44 @@ struct System
             return LVTK_ERR_ARG;
         if (lost_shortcut(out))
             return LVTK_OK;
+        const bool first_frame = state == 1;
+        cudaStream_t sl = c->stream, sr = c->xs[1];
         host_mark(0);
+        c->last_set = 0;
         ctx_stage_image(c, 0, left, rows, cols, cols);
+        if (int rc = ctx_stage_flush(c, sl))
+            return rc;
+        if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, sl))
+            return rc;
+        if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, sl))
+            return rc;
+        if (int rc = launch_index(c->feats_d, 1, c->cam, sl))
+            return rc;
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_left, sl));
         ctx_stage_image(c, 1, right, rows, cols, cols);
-        if (int rc = ctx_stage_flush(c))
+        if (int rc = ctx_stage_flush(c, sr))
             return rc;
         host_mark(1);
-        if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 2, c->feats_d, kBriefBorder, 1, c->stream))
+        if (int rc = launch_detect(c->pool, c->wsx[1], c->dp, c->d_slots + 1, 1, c->feats_d + 1, kBriefBorder, 1, sr))
             return rc;
-        if (int rc = launch_brief(c->pool, c->d_slots, 2, c->feats_d, c->stream))
+        if (int rc = launch_brief(c->pool, c->d_slots + 1, 1, c->feats_d + 1, sr))
             return rc;
-        return finish(out);
+        if (int rc = launch_index(c->feats_d + 1, 1, c->cam, sr))
+            return rc;
+        LVT_CUDA_TRY(cudaStreamWaitEvent(sr, c->ev_left, 0)); // the candidates pair left with right descriptors
+        if (int rc = launch_rowcand(c->feats_d, c->cam, c->row_cand[0], sr))
+            return rc;
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_right, sr));
+        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc,
+                                        c->row_cand[0], c->fcap, sl, c->ev_right))
+            return rc;
+        PoseD pose;
+        if (int rc = fetch_result(&pose))
+            return rc;
+        if (!first_frame && state == 2)
+            last_pose = pose; // m_last_pose = computed_pose (lvt_system.cpp:205); not on the first frame
+        *out = pose;
+        return LVTK_OK;
     }
 
     int track_external(const uint8_t *left, const uint8_t *right, int rows, int cols, const double (*cl)[2], int nl,

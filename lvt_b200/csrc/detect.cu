@@ -838,24 +838,18 @@ __device__ int warp_partition(uint32_t *a, int first, int last, uint16_t *posL, 
     const int lane = threadIdx.x & 31;
     const uint32_t pv = a[first] >> 24;
     const int lo = first + 1, m = last - lo;
-    int nL = 0;
+    int nL = 0, nR = 0;
     for (int base = 0; base < m; base += 32)
     {
-        const int p = base + lane;
+        const int p = base + lane, pr = m - 1 - p; // from the left / from the right
         const bool isL = p < m && (a[lo + p] >> 24) <= pv;
-        const uint32_t bl = __ballot_sync(0xffffffffu, isL);
+        const bool isR = pr >= 0 && (a[lo + pr] >> 24) >= pv;
+        const uint32_t bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
         if (isL)
             posL[nL + __popc(bl & ((1u << lane) - 1u))] = (uint16_t)p;
-        nL += __popc(bl);
-    }
-    int nR = 0;
-    for (int base = 0; base < m; base += 32)
-    {
-        const int p = m - 1 - (base + lane); // from the right
-        const bool isR = p >= 0 && (a[lo + p] >> 24) >= pv;
-        const uint32_t br = __ballot_sync(0xffffffffu, isR);
         if (isR)
-            posR[nR + __popc(br & ((1u << lane) - 1u))] = (uint16_t)p;
+            posR[nR + __popc(br & ((1u << lane) - 1u))] = (uint16_t)pr;
+        nL += __popc(bl);
         nR += __popc(br);
     }
     __syncwarp();
@@ -911,7 +905,7 @@ __device__ __forceinline__ void warp_leaf_sort(uint32_t *a, int first, int len)
 // recursion level -- partition by warp_partition (exact), leaves by rank sort, heap-sort fallback by
 // one lane -- with a block barrier between levels.  posL / posR: u16 scratch indexed like the array
 // (ranges of one level are disjoint, so each uses its own slice).
-__device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, int *s_cnt,
+__device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort::LevelRange *q1, int *s_cnt /* [3] */,
                                 uint16_t *posL, uint16_t *posR)
 {
     if (n <= 1)
@@ -925,15 +919,20 @@ __device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort
         q0[0] = isort::LevelRange{0, n, 2 * lg};
         s_cnt[0] = 1;
         s_cnt[1] = 0;
+        s_cnt[2] = 0;
     }
     __syncthreads();
     isort::LevelRange *cur = q0, *nxt = q1;
-    int which = 0;
-    while (true)
+    // counters rotate: level L reads s_cnt[L % 3], fills s_cnt[(L + 1) % 3] and clears s_cnt[(L + 2) % 3]
+    // (last read one barrier ago), so a level costs a single barrier
+    for (int which = 0;; which = (which + 1) % 3)
     {
         const int ncur = s_cnt[which];
         if (ncur == 0)
             break;
+        int *cnt_next = &s_cnt[(which + 1) % 3];
+        if (threadIdx.x == 0)
+            s_cnt[(which + 2) % 3] = 0;
         for (int i = warp; i < ncur; i += nwarps)
         {
             const isort::LevelRange r = cur[i];
@@ -958,19 +957,15 @@ __device__ void block_introsort(uint32_t *a, int n, isort::LevelRange *q0, isort
             const int cut = warp_partition(a, r.first, r.last, posL + r.first, posR + r.first);
             if (lane == 0)
             {
-                const int slot = atomicAdd(&s_cnt[which ^ 1], 2);
+                const int slot = atomicAdd(cnt_next, 2);
                 nxt[slot] = isort::LevelRange{r.first, cut, r.depth - 1};
                 nxt[slot + 1] = isort::LevelRange{cut, r.last, r.depth - 1};
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0)
-            s_cnt[which] = 0;
-        which ^= 1;
         isort::LevelRange *t = cur;
         cur = nxt;
         nxt = t;
-        __syncthreads();
     }
 }
 
@@ -999,14 +994,32 @@ __device__ void block_bitonic_sort(uint32_t *keys, int P)
     }
 }
 
+#ifdef LVT_NMS_STATS
+__device__ long long g_tile_trace[2048][12];
+#define TILE_TR(k, v)                                                                                                 \
+    if (threadIdx.x == 0)                                                                                             \
+    g_tile_trace[blockIdx.y * gridDim.x + blockIdx.x][k] = (long long)(v)
+#define TILE_PHASE(k)                                                                                                 \
+    __syncthreads();                                                                                                  \
+    tcn = clock64();                                                                                                  \
+    TILE_TR(k, tcn - tck);                                                                                            \
+    tck = tcn
+#else
+#define TILE_TR(k, v)
+#define TILE_PHASE(k)
+#endif
+
+constexpr int kTileBitmapBits = 65536; // raster ranks by bitmap for tiles of up to 256 x 256 pixels
+
 __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
 {
-    extern __shared__ uint32_t s_dyn[];
+    extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t *s_keys = s_dyn, *s_rad = s_dyn + kTileSmemCap, *s_perm = s_dyn + 2 * kTileSmemCap;
     isort::LevelRange *s_q0 = reinterpret_cast<isort::LevelRange *>(s_dyn + 3 * kTileSmemCap), *s_q1 = s_q0 + kTileRanges;
     uint16_t *s_posL = reinterpret_cast<uint16_t *>(s_q1 + kTileRanges), *s_posR = s_posL + kTileSmemCap;
-    __shared__ int s_cnt[2];
-    __shared__ int s_hist[257];
+    uint32_t *s_sorted = reinterpret_cast<uint32_t *>(s_posL); // the partition scratch is free once the order is known
+    __shared__ int s_cnt[3];
+    __shared__ int s_hist[512];
     __shared__ int s_scan[34];
     __shared__ uint32_t s_prefix;
     __shared__ int s_k;
@@ -1014,14 +1027,23 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
     const int t = blockIdx.x, b = blockIdx.y;
     if (a.retry && !a.retry[b])
         return;
+#ifdef LVT_NMS_STATS
+    long long tck = clock64(), tcn;
+    TILE_TR(0, nms_ns());
+#endif
     if (a.nms.tile_overflow[b * a.n_tiles + t])
     {
         if (threadIdx.x == 0)
             nms_fallback_tile(a.nms, a.parent, t, b);
         __syncthreads();
+        TILE_TR(11, 1);
+    }
+    else
+    {
+        TILE_TR(11, 0);
     }
     const int tx = t % a.grid.nx, ty = t / a.grid.nx;
-    const int x0 = tx * a.grid.cell, y0 = ty * a.grid.cell, tw = a.grid.tile_w(tx);
+    const int x0 = tx * a.grid.cell, y0 = ty * a.grid.cell, tw = a.grid.tile_w(tx), th = a.grid.tile_h(ty);
     const size_t base = ((size_t)b * a.n_tiles + t) * a.tile_cap;
     const int n = min(a.tile_count[b * a.n_tiles + t], a.tile_cap);
     uint32_t *out = a.tile_out + base;
@@ -1035,29 +1057,71 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
     uint32_t *keys = small ? s_keys : a.tile_list + base;
     uint32_t *rad = small ? s_rad : a.tile_aux + 2 * base;
     uint32_t *perm = small ? s_perm : a.tile_aux + 2 * base + a.tile_cap;
+    for (int i = threadIdx.x; i < 257; i += blockDim.x)
+        s_hist[i] = 0;
 
-    // ---- raster order -------------------------------------------------------------------------
-    int P = 1;
-    while (P < n)
-        P <<= 1;
-    if (small)
-        for (int i = threadIdx.x; i < P; i += blockDim.x)
-            keys[i] = i < n ? a.tile_list[base + i] : 0xFFFFFFFFu;
-    else
-        for (int i = n + threadIdx.x; i < P; i += blockDim.x)
-            keys[i] = 0xFFFFFFFFu; // tile_cap is a power of two >= n
-    __syncthreads();
-    block_bitonic_sort(keys, P);
-    // re-encode in place: (raster << 8 | response) -> (ly << 20 | lx << 8 | response); same order
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    // ---- raster order: keys[rank] = (ly << 20 | lx << 8 | response), perm[rank] = (response << 24 | rank)
+    if (small && tw * th <= kTileBitmapBits)
     {
-        const uint32_t key = keys[i];
-        const int raster = (int)(key >> 8), ly = raster / tw, lx = raster - ly * tw;
-        keys[i] = ((uint32_t)ly << 20) | ((uint32_t)lx << 8) | (key & 0xFFu);
+        // every pixel appears at most once: rank = number of set bits below it in the tile's bitmap
+        uint32_t *bm = s_rad, *wpref = s_rad + kTileBitmapBits / 32;
+        const int nw = (tw * th + 31) >> 5;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x)
+            bm[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t r = a.tile_list[base + i] >> 8;
+            atomicOr(&bm[r >> 5], 1u << (r & 31));
+        }
+        __syncthreads();
+        {
+            const int w0 = 2 * threadIdx.x; // nw <= 2048 = 2 * blockDim.x
+            const int c0 = w0 < nw ? __popc(bm[w0]) : 0, c1 = w0 + 1 < nw ? __popc(bm[w0 + 1]) : 0;
+            int total;
+            const int ex = block_exclusive_scan(c0 + c1, s_scan, &total);
+            if (w0 < nw)
+                wpref[w0] = (uint32_t)ex;
+            if (w0 + 1 < nw)
+                wpref[w0 + 1] = (uint32_t)(ex + c0);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t key = a.tile_list[base + i], r = key >> 8, resp = key & 0xFFu;
+            const int rank = (int)wpref[r >> 5] + __popc(bm[r >> 5] & ((1u << (r & 31)) - 1u));
+            const int ly = (int)r / tw, lx = (int)r - ly * tw;
+            keys[rank] = ((uint32_t)ly << 20) | ((uint32_t)lx << 8) | resp;
+            perm[rank] = (resp << 24) | (uint32_t)rank;
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    else
+    {
+        int P = 1;
+        while (P < n)
+            P <<= 1;
+        if (small)
+            for (int i = threadIdx.x; i < P; i += blockDim.x)
+                keys[i] = i < n ? a.tile_list[base + i] : 0xFFFFFFFFu;
+        else
+            for (int i = n + threadIdx.x; i < P; i += blockDim.x)
+                keys[i] = 0xFFFFFFFFu; // tile_cap is a power of two >= n
+        __syncthreads();
+        block_bitonic_sort(keys, P);
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t key = keys[i];
+            const int raster = (int)(key >> 8), ly = raster / tw, lx = raster - ly * tw;
+            keys[i] = ((uint32_t)ly << 20) | ((uint32_t)lx << 8) | (key & 0xFFu);
+            perm[i] = ((key & 0xFFu) << 24) | (uint32_t)i;
+        }
+        __syncthreads();
+    }
     const uint32_t origin = ((uint32_t)y0 << 20) | ((uint32_t)x0 << 8);
     auto pack_out = [&](uint32_t key) -> uint32_t { return key + origin; };
+    TILE_PHASE(2);
+    TILE_TR(10, n);
 
     if (n <= a.max_per_cell)
     {
@@ -1069,113 +1133,173 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
         return;
     }
     // ---- ANMS (lvt_image_features_handler.cpp:34-83) ------------------------------------------
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        perm[i] = ((keys[i] & 0xFFu) << 24) | (uint32_t)i;
-    __syncthreads();
     // :38-41, std::sort's exact permutation
     if (small)
         block_introsort(perm, n, s_q0, s_q1, s_cnt, s_posL, s_posR);
     else if (threadIdx.x == 0)
         isort::sort(perm, n); // more survivors than fit in shared memory (pathological): sequential replay
     __syncthreads();
-    // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own.  In the sorted
-    // order those corners are a prefix: s_hist[v] = number of corners with response >= v.
-    for (int i = threadIdx.x; i < 257; i += blockDim.x)
-        s_hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        atomicAdd(&s_hist[keys[i] & 0xFFu], 1);
-    __syncthreads();
-    if (threadIdx.x == 0)
+    TILE_PHASE(3);
+    // corners in emission order; s_hist[v] = number of corners with response >= v.
+    // byte_xy: tile-local coordinates fit a byte each -> squared distances by vabsdiff4 + dp4a on
+    // (lx | ly << 8) words, which take over perm's place
+    const uint32_t *sorted = small ? s_sorted : nullptr;
+    const bool byte_xy = small && tw <= 256 && th <= 256;
+    uint32_t *xyb = s_perm;
+    auto sorted_key = [&](int p) -> uint32_t { return sorted ? sorted[p] : keys[perm[p] & 0xFFFFFFu]; };
+    for (int p = threadIdx.x; p < n; p += blockDim.x)
     {
-        int acc = 0;
-        for (int v = 256; v >= 0; v--)
+        const uint32_t k = keys[perm[p] & 0xFFFFFFu];
+        if (small)
+            s_sorted[p] = k;
+        if (byte_xy)
+            xyb[p] = ((k >> 8) & 0xFFu) | ((k >> 20) << 8); // this thread's own perm[p] was read above
+        atomicAdd(&s_hist[k & 0xFFu], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        // suffix sums over the 256 response bins: lane l owns bins 255-8l .. 248-8l
+        const int lane = threadIdx.x;
+        int mine = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            mine += s_hist[255 - 8 * lane - u];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
         {
-            acc += s_hist[v];
-            s_hist[v] = acc;
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        int acc = incl - mine;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+        {
+            acc += s_hist[255 - 8 * lane - u];
+            s_hist[255 - 8 * lane - u] = acc;
         }
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < n; p += blockDim.x)
+    TILE_PHASE(4);
+    // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own.  In the sorted
+    // order those corners are a prefix; eight lanes share one corner's prefix.
+    for (int w = threadIdx.x; w < 8 * n; w += blockDim.x) // blockDim.x is a multiple of 8: whole groups stay together
     {
-        const int i = (int)(perm[p] & 0xFFFFFFu);
-        const uint32_t ki = keys[i];
+        const int p = w >> 3, part = w & 7;
+        const uint32_t ki = sorted_key(p);
         // response_j > 1.11f * response_i in fp32  <=>  response_j >= floor(thr) + 1 (integers)
         const float thr = __fmul_rn((float)(ki & 0xFFu), 1.11f);
         const int need = (int)floorf(thr) + 1;
         const int prefix_len = need > 255 ? 0 : s_hist[need];
         const int yi = (int)(ki >> 20), xi = (int)((ki >> 8) & 0xFFFu);
         uint32_t best = 0xFFFFFFFFu; // FLT_MAX
-        for (int q = 0; q < prefix_len; q++)
+        if (byte_xy)
         {
-            const uint32_t kj = keys[perm[q] & 0xFFFFFFu];
-            const int dx = xi - (int)((kj >> 8) & 0xFFFu), dy = yi - (int)(kj >> 20);
-            best = min(best, (uint32_t)(dx * dx + dy * dy));
+            const uint32_t me = xyb[p];
+            auto dist2 = [me](uint32_t other) -> uint32_t {
+                const uint32_t d = __vabsdiffu4(me, other);
+                return __dp4a(d, d, 0u);
+            };
+            const int full = prefix_len >> 2;
+            for (int g = part; g < full; g += 8)
+            {
+                const uint4 v = reinterpret_cast<const uint4 *>(xyb)[g];
+                best = min(min(best, min(dist2(v.x), dist2(v.y))), min(dist2(v.z), dist2(v.w)));
+            }
+            for (int q = 4 * full + part; q < prefix_len; q += 8)
+                best = min(best, dist2(xyb[q]));
         }
-        rad[i] = best;
+        else
+            for (int q = part; q < prefix_len; q += 8)
+            {
+                const uint32_t kj = sorted_key(q);
+                const int dx = xi - (int)((kj >> 8) & 0xFFFu), dy = yi - (int)(kj >> 20);
+                best = min(best, (uint32_t)(dx * dx + dy * dy));
+            }
+        const unsigned group = 0xFFu << ((threadIdx.x & 31) & ~7);
+        best = min(best, __shfl_xor_sync(group, best, 1));
+        best = min(best, __shfl_xor_sync(group, best, 2));
+        best = min(best, __shfl_xor_sync(group, best, 4));
+        if (part == 0)
+            rad[p] = best;
     }
     __syncthreads();
 
-    // :66-71  decision = radiiSorted[num_to_keep]  (descending) -> MSB-first radix select
-    if (threadIdx.x == 0)
+    TILE_PHASE(5);
+    // :66-71  decision = radiiSorted[num_to_keep]  (descending): MSB-first radix select.  With byte
+    // coordinates a radius is below 2^17 or FLT_MAX, i.e. an 18-bit key -> two 9-bit passes.
     {
-        s_prefix = 0;
-        s_k = a.max_per_cell;
-    }
-    for (int shift = 24; shift >= 0; shift -= 8)
-    {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x)
-            s_hist[i] = 0;
-        __syncthreads();
-        const uint32_t prefix = s_prefix;
-        const uint32_t mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
-            if ((rad[i] & mask) == prefix)
-                atomicAdd(&s_hist[(rad[i] >> shift) & 0xFF], 1);
-        __syncthreads();
-        if (threadIdx.x < 32)
+        const int bits = byte_xy ? 9 : 8, npass = byte_xy ? 2 : 4, nbins = 1 << bits, per = nbins / 32;
+        auto keyof = [&](uint32_t v) -> uint32_t { return byte_xy ? min(v, 0x3FFFFu) : v; };
+        if (threadIdx.x == 0)
         {
-            // walk the 256 bins from the top: lane l owns bins 255-8l .. 248-8l
-            const int lane = threadIdx.x;
-            int mine = 0;
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-                mine += s_hist[255 - 8 * lane - u];
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o)
-                    incl += v;
-            }
-            const int k0 = s_k;
-            const bool here = (incl - mine) <= k0 && k0 < incl; // the k-th largest falls into my bins
-            const uint32_t who = __ballot_sync(0xffffffffu, here);
-            if (who == 0)
-            {
-                if (lane == 0) // fewer than k+1 elements left (cannot happen for n > k): bin 0
-                {
-                    s_k = k0 - incl; // unused
-                    s_prefix = prefix;
-                }
-            }
-            else if (lane == __ffs(who) - 1)
-            {
-                int k = k0 - (incl - mine), d = 255 - 8 * lane;
-                for (int u = 0; u < 8; u++, d--)
-                {
-                    if (k < s_hist[d])
-                        break;
-                    k -= s_hist[d];
-                }
-                s_k = k;
-                s_prefix = prefix | ((uint32_t)d << shift);
-            }
+            s_prefix = 0;
+            s_k = a.max_per_cell;
         }
+        for (int pass = 0; pass < npass; pass++)
+        {
+            const int shift = (npass - 1 - pass) * bits;
+            for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+                s_hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + bits));
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                const uint32_t kv = keyof(rad[i]);
+                if ((kv & mask) == prefix)
+                    atomicAdd(&s_hist[(kv >> shift) & (nbins - 1)], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32)
+            {
+                // walk the bins from the top: lane l owns bins nbins-1-per*l .. nbins-per*(l+1)
+                const int lane = threadIdx.x, top = nbins - 1 - per * lane;
+                int mine = 0;
+                for (int u = 0; u < per; u++)
+                    mine += s_hist[top - u];
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o)
+                        incl += v;
+                }
+                const int k0 = s_k;
+                const bool here = (incl - mine) <= k0 && k0 < incl; // the k-th largest falls into my bins
+                const uint32_t who = __ballot_sync(0xffffffffu, here);
+                if (who == 0)
+                {
+                    if (lane == 0) // fewer than k+1 elements left (cannot happen for n > k): bin 0
+                    {
+                        s_k = k0 - incl; // unused
+                        s_prefix = prefix;
+                    }
+                }
+                else if (lane == __ffs(who) - 1)
+                {
+                    int k = k0 - (incl - mine), d = top;
+                    for (int u = 0; u < per; u++, d--)
+                    {
+                        if (k < s_hist[d])
+                            break;
+                        k -= s_hist[d];
+                    }
+                    s_k = k;
+                    s_prefix = prefix | ((uint32_t)d << shift);
+                }
+            }
+            __syncthreads();
+        }
+        if (byte_xy && threadIdx.x == 0 && s_prefix == 0x3FFFFu)
+            s_prefix = 0xFFFFFFFFu;
         __syncthreads();
     }
     const uint32_t decision = s_prefix;
+    TILE_PHASE(6);
 
     // :72-80  keep radius >= decision, in sorted order
     int running = 0;
@@ -1186,9 +1310,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
         int keep = 0;
         if (p < n)
         {
-            const int i = (int)(perm[p] & 0xFFFFFFu);
-            key = keys[i];
-            keep = rad[i] >= decision;
+            key = sorted_key(p);
+            keep = rad[p] >= decision;
         }
         int total;
         const int pos = block_exclusive_scan(keep, s_scan, &total);
@@ -1198,6 +1321,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
     }
     if (threadIdx.x == 0)
         a.tile_out_count[b * a.n_tiles + t] = running;
+    TILE_PHASE(7);
+    TILE_TR(1, nms_ns());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1348,6 +1473,11 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
 } // namespace lvtb
 
 #ifdef LVT_NMS_STATS
+extern "C" __attribute__((visibility("default"))) int lvt_debug_tile_trace(long long *out /* [2048][12] */)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, lvtb::g_tile_trace, sizeof(long long) * 2048 * 12);
+}
 extern "C" __attribute__((visibility("default"))) int lvt_debug_nms_trace(long long *out /* [4096][12] */)
 {
     cudaDeviceSynchronize();

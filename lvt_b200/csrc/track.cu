@@ -29,7 +29,8 @@ constexpr int kCandWarps = 8;
 // per-frame hand-over between the kernels of the chain (device memory)
 struct FrameCtl
 {
-    int mode; // 0 frame finished by track_a (lost), 1 tracking continues, 2 first frame (track_b seeds the map)
+    int mode; // 0 frame finished by track_a (was lost already), 1 tracking continues, 2 first frame (track_b seeds
+              // the map), 3 lost in this frame (track_b, which may read the right image's features, reports)
     int n_matches;
     int inliers;
     int pad;
@@ -202,10 +203,9 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     TrackState &S = *a.st;
     FrameCtl &ctl = *a.ctl;
     const TrackParams &tp = a.tp;
-    const FeatDev fl = a.feats[0], fr = a.feats[1];
+    const FeatDev fl = a.feats[0];
     const int state0 = S.state;
     const int nl = state0 == 3 ? 0 : min(*fl.n, a.owner_cap);
-    const int nr = (tp.sensor == 1 && state0 != 3) ? min(*fr.n, a.owner_cap) : 0;
     const int map_n = S.map_n, staged_n = S.staged_n;
     const PoseD last_pose = S.last_pose;
     __syncthreads();
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         lvt_frame_info z = {};
         ctl.info = z;
         ctl.info.n_features_left = nl;
-        ctl.info.n_features_right = nr;
+        ctl.info.n_features_right = 0; // track_b: the right image may still be in extraction on another stream
         for (int k = 0; k < 8; k++)
             ctl.cyc[k] = 0;
         for (int k = 0; k < 4; k++)
@@ -302,8 +302,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         {
             // lost: return the last pose (lvt/src/lvt_system.cpp:267-272,199-204)
             S.state = 3;
-            ctl.mode = 0;
-            write_result(a, S, last_pose, 3, map_n, staged_n);
+            ctl.mode = 3;
         }
         else
         {
@@ -472,6 +471,14 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
     int map_n = S.map_n, staged_n = S.staged_n;
     __syncthreads();
     LVT_PHASE(5);
+    if (threadIdx.x == 0)
+        ctl.info.n_features_right = nr;
+    if (mode == 3)
+    {
+        if (threadIdx.x == 0)
+            write_result(a, S, S.last_pose, 3, map_n, staged_n);
+        return;
+    }
 
     if (mode == 2)
     {
@@ -759,7 +766,7 @@ int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists
 
 int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
-                       int owner_cap, cudaStream_t stream)
+                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready)
 {
     if (int rc = ensure_smem(owner_cap))
         return rc;
@@ -789,6 +796,10 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
     LVT_TIMED(stream, K_STAGEDCAND, (mapcand_kernel<<<148, kCandWarps * 32, 0, stream>>>(sc2)));
     LVT_LAUNCH_CHECK(stream, "stagedcand_kernel");
+    // everything up to here needs the left image only; the right image's features and the row-matching
+    // candidates (extracted on another stream by the blocking stereo path) join here
+    if (right_ready)
+        LVT_CUDA_TRY(cudaStreamWaitEvent(stream, right_ready, 0));
     LVT_TIMED(stream, K_TRACK_B, (track_b_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
     LVT_LAUNCH_CHECK(stream, "track_b_kernel");
     return LVTK_OK;

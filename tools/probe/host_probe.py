@@ -38,6 +38,13 @@ if stats_lib:
     worst = np.argsort(tr[:, 1])[-5:]
     for w in worst:
         print("  late CTA %d: start %.1f end %.1f" % (w, (tr[w, 0] - t0) / 1e3, (tr[w, 1] - t0) / 1e3), [round(x / mhz, 1) for x in tr[w, 2:7]], list(tr[w, 7:11]), round(tr[w, 11] / mhz, 1))
+    tt = np.zeros((2048, 12), dtype=np.int64)
+    lib.lib.lvt_debug_tile_trace(tt.ctypes.data_as(C.c_void_p))
+    nt = ((p.img_width + p.detection_cell_size - 1) // p.detection_cell_size) * ((p.img_height + p.detection_cell_size - 1) // p.detection_cell_size)
+    print("tile trace (last launch, %d tiles): span %.1f us" % (nt, (tt[:nt, 1].max() - tt[:nt, 0].min()) / 1e3))
+    for i in range(nt):
+        print("  tile %2d n=%4d fallback=%d raster %.1f | sort %.1f | hist %.1f | radii %.1f | select %.1f | compact %.1f us" % (
+            (i, tt[i, 10], tt[i, 11]) + tuple(tt[i, k] / mhz for k in (2, 3, 4, 5, 6, 7))))
     sys.exit(0)
 
 lib = lvt_b200.load()
