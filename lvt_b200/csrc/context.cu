@@ -380,7 +380,7 @@ struct lvtk_ctx
     int last_set = 0; // set holding the features of the last tracked frame
     FeatDev *feats_d = nullptr;
     int *d_slots = nullptr;
-    uint8_t *h_stage = nullptr; // pinned, 2 tightly packed images
+    uint8_t *h_stage = nullptr; // pinned, one image per pool slot, the pool's pitch
     UploadLanes lanes;          // host staging lanes of the blocking entry points
     int upload_bands = 1;       // row bands per image
     float *d_depth = nullptr, *h_depth = nullptr;
@@ -396,6 +396,13 @@ struct lvtk_ctx
     uint8_t *d_ctl = nullptr; // FrameCtl: hand-over between the kernels of the tracking chain
     FrameResult *d_result = nullptr, *h_result = nullptr;
     int *h_error = nullptr; // pinned copy of ws.error, fetched together with the result
+    EarlyResult *d_early = nullptr, *h_early = nullptr; // pose + state, copied out right behind the pose solver
+    cudaEvent_t ev_pose = nullptr;      // h_early is valid
+    cudaEvent_t ev_frame = nullptr;     // the whole frame (map maintenance, h_result, h_error) is through
+    int parity = 0;                     // blocking stereo frames alternate between two sets of buffers
+    cudaEvent_t ev_tl[4] = {};          // LVT_B200_TIMELINE: call start, left image in HBM, left features, pose
+    double tl_ms[3] = {0, 0, 0};
+    long tl_n = 0;
     // resident frame pool + pipelined streaming (lvt_pool_* / lvt_track_pool)
     cudaStream_t xs[kXStreams] = {}; // extraction runs here, tracking on `stream`
     DetectWorkspace wsx[kXStreams]; // wsx[0] == ws
@@ -470,6 +477,8 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
         LVT_CUDA_TRY(cudaEventCreate(&c->ev_batch[i]));
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming));
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_right, cudaEventDisableTiming));
+    LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pose, cudaEventDisableTiming));
+    LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming));
 
     if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
         return rc;
@@ -509,7 +518,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
         if (int rc = make_feat(&c->feats_h[i], c->arena, c->fcap, n_cells, p.img_height))
             return rc;
     int rc = c->arena.alloc(&c->feats_d, 2 * lvtk_ctx::kSets);
-    rc = rc ? rc : c->arena.alloc(&c->d_slots, 2);
+    rc = rc ? rc : c->arena.alloc(&c->d_slots, 4);
     rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)p.img_width * p.img_height);
     rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->d_in_resp, (size_t)2 * c->pcap);
@@ -522,6 +531,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->d_state, 1);
     rc = rc ? rc : c->arena.alloc(&c->d_ctl, frame_ctl_bytes());
     rc = rc ? rc : c->arena.alloc(&c->d_result, 1);
+    rc = rc ? rc : c->arena.alloc(&c->d_early, 1);
     rc = rc ? rc : make_points(&c->map, c->arena, c->pcap);
     rc = rc ? rc : make_points(&c->staged, c->arena, c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.proj, (size_t)c->pcap);
@@ -550,21 +560,25 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     if (rc)
         return rc;
     LVT_CUDA_TRY(cudaMemcpy(c->feats_d, c->feats_h, sizeof(c->feats_h), cudaMemcpyHostToDevice));
-    const int slots[2] = {0, 1};
+    const int slots[4] = {0, 1, 2, 3};
     LVT_CUDA_TRY(cudaMemcpy(c->d_slots, slots, sizeof(slots), cudaMemcpyHostToDevice));
-    LVT_CUDA_TRY(cudaMallocHost(&c->h_stage, (size_t)2 * c->pool.pitch * p.img_height));
-    std::memset(c->h_stage, 0, (size_t)2 * c->pool.pitch * p.img_height);
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_stage, (size_t)n_slots * c->pool.pitch * p.img_height));
+    std::memset(c->h_stage, 0, (size_t)n_slots * c->pool.pitch * p.img_height);
     LVT_CUDA_TRY(cudaMallocHost(&c->h_depth, sizeof(float) * (size_t)p.img_width * p.img_height));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_result, sizeof(FrameResult)));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_error, sizeof(int)));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_early, sizeof(EarlyResult)));
     {
-        // staging lanes (the calling thread + workers): LVT_B200_UPLOAD_THREADS; row bands per image:
-        // LVT_B200_UPLOAD_BANDS.  Measured on the B200 box (tools/probe/host_probe.py): extra lanes
-        // shorten the staging by ~20 us but contend with the launches that follow for the driver's
-        // locks, so the default is the calling thread alone, one band per image.
-        int lanes = 1;
+        // staging lanes (the calling thread + helpers, upload.cuh): LVT_B200_UPLOAD_THREADS; row bands
+        // per image: LVT_B200_UPLOAD_BANDS.  Default: up to 4 lanes, a quarter of the host cores
+        // shared between the GPUs of the box, one band per lane (tools/probe/host_probe.py).
+        int ndev_all = 1;
+        cudaGetDeviceCount(&ndev_all);
+        const int cores = (int)std::thread::hardware_concurrency();
+        int lanes = std::max(1, std::min(4, cores / (4 * std::max(1, ndev_all))));
         if (const char *e = std::getenv("LVT_B200_UPLOAD_THREADS"))
             lanes = std::max(1, std::min(16, std::atoi(e)));
+        c->upload_bands = lanes;
         if (const char *e = std::getenv("LVT_B200_UPLOAD_BANDS"))
             c->upload_bands = std::max(1, std::min(8, std::atoi(e)));
         c->lanes.start(c->device, lanes - 1);
@@ -613,6 +627,12 @@ static void ctx_free(lvtk_ctx *c)
         cudaEventDestroy(c->ev_left);
     if (c->ev_right)
         cudaEventDestroy(c->ev_right);
+    if (c->ev_pose)
+        cudaEventDestroy(c->ev_pose);
+    if (c->ev_frame)
+        cudaEventDestroy(c->ev_frame);
+    if (c->h_early)
+        cudaFreeHost(c->h_early);
     c->rarena.release();
     if (c->h_results)
         cudaFreeHost(c->h_results);
@@ -724,6 +744,7 @@ struct System
     int frame_number = 0;
     PoseD last_pose;
     lvt_frame_info info;
+    bool pending = false; // the last blocking frame returned at its pose; info / error flag are still on their way
 
     // host-side time of the blocking entry points: [0] staging + H2D enqueue, [1] kernel enqueue,
     // [2] waiting for the device, [3] calls  (lvt_debug_host_times)
@@ -748,9 +769,31 @@ struct System
         info.state = 1;
     }
 
+    // lvt_track hands the pose back as soon as the solver is through; the rest of that frame (staged
+    // points, triangulation, counters) is collected here, before anything needs it
+    int finish_pending()
+    {
+        if (!pending)
+            return LVTK_OK;
+        pending = false;
+        lvtk_ctx *c = ctx;
+        LVT_CUDA_TRY(cudaEventSynchronize(c->ev_frame));
+        if (const int e = *c->h_error)
+        {
+            cudaMemsetAsync(c->ws.error, 0, sizeof(int), c->stream);
+            set_last_error(__FILE__, __LINE__, "device-side capacity error");
+            return e;
+        }
+        info = c->h_result->info;
+        info.frame_number = frame_number;
+        return LVTK_OK;
+    }
+
     // the LOST short-circuit of lvt_system::track (lvt/src/lvt_system.cpp:159-166)
     bool lost_shortcut(PoseD *out)
     {
+        if (state == 3)
+            finish_pending();
         frame_number++;
         if (state != 3)
             return false;
@@ -789,6 +832,7 @@ struct System
         host_mark(2);
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
         host_mark(3);
+        pending = false;
         if (const int e = *c->h_error)
         {
             cudaMemsetAsync(c->ws.error, 0, sizeof(int), c->stream);
@@ -804,9 +848,11 @@ struct System
 
     // Blocking stereo frame.  Only the left image is on the path to the pose (map matching and the
     // solver never look at the right one), so the two images go down two streams: the left one is
-    // staged, uploaded and extracted first and tracking starts right behind it, while the host stages
-    // the right image and a second stream extracts it and lists the row-matching candidates; the two
-    // meet in front of track_b (staged points + triangulation).
+    // staged, uploaded and extracted first and the tracking kernels up to the pose solver are queued
+    // right behind it; then the host stages the right image, a second stream extracts it and lists
+    // the row-matching candidates, and both meet in front of track_b (staged points, triangulation).
+    // The call returns when the pose is on the host: track_b and the right image finish while the
+    // caller prepares the next frame, everything after them is ordered behind them by the streams.
     int track_stereo(const uint8_t *left, const uint8_t *right, int rows, int cols, PoseD *out)
     {
         lvtk_ctx *c = ctx;
@@ -815,39 +861,94 @@ struct System
         if (lost_shortcut(out))
             return LVTK_OK;
         const bool first_frame = state == 1;
-        cudaStream_t sl = c->stream, sr = c->xs[1];
+        if (pending && cudaEventQuery(c->ev_frame) == cudaSuccess)
+            if (int rc = finish_pending()) // surfaces a capacity error of the previous frame's map maintenance
+                return rc;
+        // Buffers (pool slots, staging, feature sets, candidate lists) alternate between two sets, so
+        // nothing of this frame waits for the previous frame's map maintenance except the map
+        // matching itself.  The set used two frames ago is free: its track_b ran before the pose of
+        // the previous frame, which this thread has waited for.
+        const int s = c->parity;
+        c->parity ^= 1;
+        cudaStream_t xl = c->xs[0], xr = c->xs[1], st = c->stream;
+        FeatDev *feats = c->feats_d + 2 * s;
+        const int *slots = c->d_slots + 2 * s;
         host_mark(0);
-        c->last_set = 0;
-        ctx_stage_image(c, 0, left, rows, cols, cols);
-        if (int rc = ctx_stage_flush(c, sl))
+        c->last_set = s;
+        static const bool timeline = std::getenv("LVT_B200_TIMELINE") != nullptr;
+        if (timeline)
+        {
+            if (!c->ev_tl[0])
+                for (int k = 0; k < 4; k++)
+                    cudaEventCreate(&c->ev_tl[k]);
+            cudaEventRecord(c->ev_tl[0], xl);
+        }
+        ctx_stage_image(c, 2 * s, left, rows, cols, cols);
+        if (int rc = ctx_stage_flush(c, xl))
             return rc;
-        if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, sl))
+        if (timeline)
+            cudaEventRecord(c->ev_tl[1], xl);
+        if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, slots, 1, feats, kBriefBorder, 1, xl))
             return rc;
-        if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, sl))
+        if (int rc = launch_brief(c->pool, slots, 1, feats, xl))
             return rc;
-        if (int rc = launch_index(c->feats_d, 1, c->cam, sl))
+        if (int rc = launch_index(feats, 1, c->cam, xl))
             return rc;
-        LVT_CUDA_TRY(cudaEventRecord(c->ev_left, sl));
-        ctx_stage_image(c, 1, right, rows, cols, cols);
-        if (int rc = ctx_stage_flush(c, sr))
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_left, xl));
+        if (timeline)
+            cudaEventRecord(c->ev_tl[2], xl);
+        LVT_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_left, 0));
+        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc,
+                                        c->row_cand[s], c->fcap, st, nullptr, 1, c->d_early))
+            return rc;
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_early, c->d_early, sizeof(EarlyResult), cudaMemcpyDeviceToHost, st));
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
+        if (timeline)
+            cudaEventRecord(c->ev_tl[3], st);
+        ctx_stage_image(c, 2 * s + 1, right, rows, cols, cols);
+        if (int rc = ctx_stage_flush(c, xr))
             return rc;
         host_mark(1);
-        if (int rc = launch_detect(c->pool, c->wsx[1], c->dp, c->d_slots + 1, 1, c->feats_d + 1, kBriefBorder, 1, sr))
+        if (int rc = launch_detect(c->pool, c->wsx[1], c->dp, slots + 1, 1, feats + 1, kBriefBorder, 1, xr))
             return rc;
-        if (int rc = launch_brief(c->pool, c->d_slots + 1, 1, c->feats_d + 1, sr))
+        if (int rc = launch_brief(c->pool, slots + 1, 1, feats + 1, xr))
             return rc;
-        if (int rc = launch_index(c->feats_d + 1, 1, c->cam, sr))
+        if (int rc = launch_index(feats + 1, 1, c->cam, xr))
             return rc;
-        LVT_CUDA_TRY(cudaStreamWaitEvent(sr, c->ev_left, 0)); // the candidates pair left with right descriptors
-        if (int rc = launch_rowcand(c->feats_d, c->cam, c->row_cand[0], sr))
+        LVT_CUDA_TRY(cudaStreamWaitEvent(xr, c->ev_left, 0)); // the candidates pair left with right descriptors
+        if (int rc = launch_rowcand(feats, c->cam, c->row_cand[s], xr))
             return rc;
-        LVT_CUDA_TRY(cudaEventRecord(c->ev_right, sr));
-        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc,
-                                        c->row_cand[0], c->fcap, sl, c->ev_right))
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_right, xr));
+        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc,
+                                        c->row_cand[s], c->fcap, st, c->ev_right, 2, nullptr))
             return rc;
-        PoseD pose;
-        if (int rc = fetch_result(&pose))
-            return rc;
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_frame, st));
+        host_mark(2);
+        LVT_CUDA_TRY(cudaEventSynchronize(c->ev_pose));
+        host_mark(3);
+        if (timeline)
+        {
+            cudaEventSynchronize(c->ev_tl[3]);
+            for (int k = 0; k < 3; k++)
+            {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, c->ev_tl[k], c->ev_tl[k + 1]);
+                c->tl_ms[k] += ms;
+            }
+            if (++c->tl_n % 50 == 0)
+            {
+                std::fprintf(stderr, "timeline (mean of 50 frames): stage+H2D %.1f us | left extraction %.1f us | mapcand..pose+copy %.1f us\n",
+                             20.0 * c->tl_ms[0], 20.0 * c->tl_ms[1], 20.0 * c->tl_ms[2]);
+                c->tl_ms[0] = c->tl_ms[1] = c->tl_ms[2] = 0;
+            }
+        }
+        pending = true;
+        const PoseD pose = c->h_early->pose;
+        state = c->h_early->state;
+        info.state = state;
+        info.frame_number = frame_number;
         if (!first_frame && state == 2)
             last_pose = pose; // m_last_pose = computed_pose (lvt_system.cpp:205); not on the first frame
         *out = pose;
@@ -862,6 +963,8 @@ struct System
             return LVTK_ERR_ARG;
         if (nl > c->pcap || nr > c->pcap)
             return LVTK_ERR_CAPACITY;
+        if (int rc = finish_pending())
+            return rc;
         if (lost_shortcut(out))
             return LVTK_OK;
         host_mark(0);
@@ -892,6 +995,8 @@ struct System
         lvtk_ctx *c = ctx;
         if (rows != c->params.img_height || cols != c->params.img_width)
             return LVTK_ERR_ARG;
+        if (int rc = finish_pending())
+            return rc;
         if (lost_shortcut(out))
             return LVTK_OK;
         host_mark(0);
@@ -916,6 +1021,7 @@ struct System
         lvtk_ctx *c = ctx;
         if (n_frames <= 0)
             return LVTK_ERR_ARG;
+        finish_pending();
         LVT_CUDA_TRY(cudaDeviceSynchronize());
         c->rarena.release();
         if (c->h_results)
@@ -958,6 +1064,8 @@ struct System
         lvtk_ctx *c = ctx;
         if (sensor != 1 || first < 0 || n <= 0 || first + n > c->rpool_frames)
             return LVTK_ERR_ARG;
+        if (int rc = finish_pending())
+            return rc;
         // the batch is timed on the device: first extraction launch .. last result copy
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
         for (int x = 0; x < lvtk_ctx::kXStreams; x++)
@@ -1058,7 +1166,7 @@ LVT_API lvt_handle lvt_create_from_params(const lvt_params_c *p, int sensor_type
     System *vo = new System();
     vo->sensor = sensor_type;
     vo->ctx = new lvtk_ctx();
-    if (ctx_build(vo->ctx, *p, -1, 2) != LVTK_OK)
+    if (ctx_build(vo->ctx, *p, -1, 4) != LVTK_OK)
     {
         ctx_free(vo->ctx);
         delete vo;
@@ -1081,6 +1189,11 @@ LVT_API void lvt_destroy(lvt_handle h)
     System *vo = static_cast<System *>(h);
     if (!vo)
         return;
+    if (vo->ctx)
+    {
+        cudaSetDevice(vo->ctx->device);
+        cudaDeviceSynchronize(); // a frame that returned at its pose may still be finishing
+    }
     ctx_free(vo->ctx);
     delete vo;
 }
@@ -1091,6 +1204,8 @@ LVT_API void lvt_reset(lvt_handle h)
     if (!vo)
         return;
     cudaSetDevice(vo->ctx->device);
+    vo->finish_pending();
+    cudaStreamSynchronize(vo->ctx->xs[1]);
     launch_reset_state(vo->ctx->d_state, vo->ctx->stream);
     cudaStreamSynchronize(vo->ctx->stream);
     lvtk_ctx *c = vo->ctx;
@@ -1152,6 +1267,8 @@ LVT_API int lvt_get_frame_info(lvt_handle h, lvt_frame_info *out)
     System *vo = static_cast<System *>(h);
     if (!vo || !out)
         return -1;
+    cudaSetDevice(vo->ctx->device);
+    vo->finish_pending();
     *out = vo->info;
     return 0;
 }
@@ -1178,6 +1295,7 @@ LVT_API int lvt_debug_get_features(lvt_handle h, int which, float *kps_xy, unsig
         return -1;
     lvtk_ctx *c = vo->ctx;
     cudaSetDevice(c->device);
+    vo->finish_pending();
     const FeatDev &f = c->feats_h[2 * c->last_set + which];
     int n = 0;
     if (cudaMemcpy(&n, f.n, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -1200,6 +1318,7 @@ LVT_API int lvt_debug_get_points(lvt_handle h, int which, double *xyz, unsigned 
         return -1;
     lvtk_ctx *c = vo->ctx;
     cudaSetDevice(c->device);
+    vo->finish_pending();
     TrackState st;
     if (cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -1;
@@ -1278,6 +1397,7 @@ LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int
     System *vo = static_cast<System *>(h);
     if (!vo)
         return -1;
+    vo->finish_pending();
     const FrameResult &r = i < 0 ? *vo->ctx->h_result : vo->ctx->h_results[i];
     std::memcpy(cycles, r.cycles, sizeof(r.cycles));
     std::memcpy(rounds, r.rounds, sizeof(r.rounds));

@@ -219,15 +219,19 @@ __device__ inline void block_project(const double *xyz, int m, const double *W /
 template <class Active, class Slow>
 __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active active, Slow slow, float ratio_th,
                                    float dist_th, const uint8_t *marks, int *choice, int *items /* [2 * n_q] */,
-                                   int *owner_a, int *owner_b, int *s_flag /* [4] */, float *out_d1, float *out_d2,
-                                   int *rounds_out, long long *dbg = nullptr)
+                                   int *owner_a, int *owner_b, int *s_flag /* [8] */, float *out_d1, float *out_d2,
+                                   int *rounds_out, long long *dbg = nullptr, uint32_t *skeys = nullptr,
+                                   int skey_cap = 0)
 {
-    (void)dbg;
+#define LVT_RDBG(k)                                                                                                   \
+    if (dbg && threadIdx.x == 0)                                                                                      \
+    dbg[k] = clock64()
+    LVT_RDBG(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int *cur = owner_a, *nxt = owner_b;
     int *fast = items, *slow_items = items + n_q;
     if (threadIdx.x == 0)
-        s_flag[2] = 0, s_flag[3] = 0;
+        s_flag[2] = 0, s_flag[3] = 0, s_flag[4] = 0;
     for (int j = threadIdx.x; j < n_f; j += blockDim.x)
         cur[j] = (marks && marks[j]) ? kTaken : kFree;
     __syncthreads();
@@ -259,6 +263,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     }
     __syncthreads();
     const int n_fast = s_flag[2], n_slow = s_flag[3];
+    LVT_RDBG(1);
 
     // `prev` = the query's choice of the previous round (a register copy for the cached queries)
     auto publish_cached = [&](int q, uint32_t b1, uint32_t b2, int &my_count, int &prev) {
@@ -299,12 +304,12 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
     };
 
-    // the first 4 x blockDim queries of the fast list live in registers across the rounds: query id,
-    // candidate count, the first four (sorted) keys, last choice -- a round then touches only shared
-    // memory unless a query has to look past its fourth key
+    // the first 4 x blockDim queries of the fast list stay with their thread across the rounds: query
+    // id, candidate count and last choice in registers, the sorted key list in shared memory (skeys,
+    // a private slice per query, so no barrier is needed between the copy and the reads) -- a round
+    // then touches only shared memory.  A list that does not fit in skeys is read from global memory.
     constexpr int U = 4;
-    int rq[U], rcnt[U], rprev[U];
-    uint4 rk4[U];
+    int rq[U], rcnt[U], rprev[U], roff[U];
 #pragma unroll
     for (int u = 0; u < U; u++)
     {
@@ -312,12 +317,87 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         rq[u] = it < n_fast ? fast[it] : -1;
         rprev[u] = -1;
     }
+    int max_cnt = 0;
 #pragma unroll
     for (int u = 0; u < U; u++)
     {
         rcnt[u] = rq[u] >= 0 ? L.count[rq[u]] : 0;
-        rk4[u] = rq[u] >= 0 ? *reinterpret_cast<const uint4 *>(L.keys + (size_t)rq[u] * L.cap) : make_uint4(0, 0, 0, 0);
+        max_cnt = max(max_cnt, rcnt[u]);
     }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+        // slices are multiples of 4 keys (16-byte copies); one shared-memory atomic per warp
+        const int pad = (rcnt[u] + 3) & ~3;
+        int incl = pad;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += nb;
+        }
+        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 31 && warp_total > 0 && skeys)
+            base = atomicAdd(&s_flag[4], warp_total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        const int off = base + incl - pad;
+        roff[u] = (skeys && pad > 0 && off + pad <= skey_cap) ? off : -1;
+    }
+    // asynchronous 16-byte copies (LDGSTS): every chunk of every list is in flight at once
+#pragma unroll
+    for (int u = 0; u < U; u++)
+        if (roff[u] >= 0)
+        {
+            const uint32_t *src = L.keys + (size_t)rq[u] * L.cap;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(skeys + roff[u]);
+            for (int k = 0; k < rcnt[u]; k += 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * k), "l"(src + k) : "memory");
+        }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    if (dbg)
+    {
+        int sum = 0, mx = max_cnt, nglob = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            sum += rcnt[u], nglob += (rq[u] >= 0 && roff[u] < 0 && rcnt[u] > 0);
+        if (threadIdx.x == 0)
+            dbg[16] = n_fast, dbg[17] = n_slow, dbg[19] = 0, dbg[20] = 0, dbg[21] = 0;
+        __syncthreads();
+        atomicAdd((unsigned long long *)&dbg[19], (unsigned long long)sum);
+        atomicMax((unsigned long long *)&dbg[20], (unsigned long long)mx);
+        atomicAdd((unsigned long long *)&dbg[21], (unsigned long long)nglob);
+        __syncthreads();
+        if (threadIdx.x == 0)
+            dbg[18] = s_flag[4];
+    }
+    // the first two keys of a sorted list whose feature is not marked / taken by an earlier query;
+    // four keys per step: one 16-byte load, four independent owner look-ups, then the decision
+    auto best2 = [](const uint32_t *keys, int cnt, const int *cur_owner, int q, uint32_t &b1, uint32_t &b2) {
+        b1 = kNoKey;
+        b2 = kNoKey;
+        for (int k = 0; k < cnt; k += 4)
+        {
+            const uint4 c = *reinterpret_cast<const uint4 *>(keys + k);
+            const uint32_t key[4] = {c.x, c.y, c.z, c.w};
+            bool open[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                open[i] = (k + i < cnt) && cur_owner[key[i] & 0xFFFFFu] >= q; // keys past cnt: stale slots of the list row
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (open[i])
+                {
+                    if (b1 == kNoKey)
+                        b1 = key[i];
+                    else if (b2 == kNoKey)
+                        b2 = key[i];
+                }
+            if (b2 != kNoKey)
+                break;
+        }
+    };
 
     int count = 0, rounds = 0;
     for (;; rounds++)
@@ -327,69 +407,28 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         if (threadIdx.x == 0)
             s_flag[0] = 0, s_flag[1] = 0;
         __syncthreads();
+        if (rounds == 0)
+            LVT_RDBG(2);
         int my_count = 0;
-        // one thread per query, 4 queries in flight: the first four keys of each sorted list come in
-        // one 16-byte load; the first two keys not owned by an earlier query decide
+        // one thread per query; the first two keys not owned by an earlier query decide
 #pragma unroll
         for (int u = 0; u < U; u++)
         {
             if (rq[u] < 0)
                 continue;
-            const uint32_t *keys = L.keys + (size_t)rq[u] * L.cap;
-            uint32_t b1 = kNoKey, b2 = kNoKey;
-            for (int k = 0; k < rcnt[u]; k++)
-            {
-                const uint32_t key = k == 0 ? rk4[u].x : k == 1 ? rk4[u].y : k == 2 ? rk4[u].z : k == 3 ? rk4[u].w : keys[k];
-                if (cur[key & 0xFFFFFu] < rq[u])
-                    continue; // marked, or taken by an earlier query
-                if (b1 == kNoKey)
-                    b1 = key;
-                else
-                {
-                    b2 = key;
-                    break;
-                }
-            }
+            uint32_t b1, b2;
+            if (roff[u] >= 0)
+                best2(skeys + roff[u], rcnt[u], cur, rq[u], b1, b2);
+            else
+                best2(L.keys + (size_t)rq[u] * L.cap, rcnt[u], cur, rq[u], b1, b2);
             publish_cached(rq[u], b1, b2, my_count, rprev[u]);
         }
-        for (int base = threadIdx.x + U * blockDim.x; base < n_fast; base += blockDim.x * U)
+        for (int it = threadIdx.x + U * blockDim.x; it < n_fast; it += blockDim.x)
         {
-            int q[U], cnt[U];
-            uint4 k4[U];
-#pragma unroll
-            for (int u = 0; u < U; u++)
-            {
-                const int it = base + u * blockDim.x;
-                q[u] = it < n_fast ? fast[it] : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++)
-            {
-                cnt[u] = q[u] >= 0 ? L.count[q[u]] : 0;
-                k4[u] = q[u] >= 0 ? *reinterpret_cast<const uint4 *>(L.keys + (size_t)q[u] * L.cap) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++)
-            {
-                if (q[u] < 0)
-                    continue;
-                const uint32_t *keys = L.keys + (size_t)q[u] * L.cap;
-                uint32_t b1 = kNoKey, b2 = kNoKey;
-                for (int k = 0; k < cnt[u]; k++)
-                {
-                    const uint32_t key = k == 0 ? k4[u].x : k == 1 ? k4[u].y : k == 2 ? k4[u].z : k == 3 ? k4[u].w : keys[k];
-                    if (cur[key & 0xFFFFFu] < q[u])
-                        continue; // marked, or taken by an earlier query
-                    if (b1 == kNoKey)
-                        b1 = key;
-                    else
-                    {
-                        b2 = key;
-                        break;
-                    }
-                }
-                publish(q[u], b1, b2, my_count);
-            }
+            const int q = fast[it];
+            uint32_t b1, b2;
+            best2(L.keys + (size_t)q * L.cap, L.count[q], cur, q, b1, b2);
+            publish(q, b1, b2, my_count);
         }
         for (int it = warp; it < n_slow; it += nwarps)
         {
@@ -408,6 +447,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         cur = nxt;
         nxt = t;
         __syncthreads();
+        if (rounds < 12)
+            LVT_RDBG(3 + rounds);
         if (!changed)
             break;
     }
@@ -419,6 +460,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     }
     if (rounds_out && threadIdx.x == 0)
         *rounds_out = rounds + 1;
+    LVT_RDBG(15);
+#undef LVT_RDBG
     return count;
 }
 
@@ -426,7 +469,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
 __device__ inline int block_match_projected(const CandLists &L, const uint32_t *pdesc, const MatchScratch &ms, int m,
                                             const FeatDev &f, int n, const CamParams &cam, float r2, bool use_marks,
                                             int *owner_a, int *owner_b, int *s_flag, float *out_d1, float *out_d2,
-                                            int *rounds_out, long long *dbg = nullptr)
+                                            int *rounds_out, long long *dbg = nullptr, uint32_t *skeys = nullptr,
+                                            int skey_cap = 0)
 {
     const int lane = threadIdx.x & 31;
     auto active = [&](int q) { return ms.vis[q] != 0; };
@@ -441,7 +485,7 @@ __device__ inline int block_match_projected(const CandLists &L, const uint32_t *
         warp_top2(k1, k2, b1, b2);
     };
     return block_rounds(L, m, n, active, slow, cam.tracking_ratio_th, cam.desc_dist_th, use_marks ? f.matched : nullptr,
-                        ms.choice, ms.items, owner_a, owner_b, s_flag, out_d1, out_d2, rounds_out, dbg);
+                        ms.choice, ms.items, owner_a, owner_b, s_flag, out_d1, out_d2, rounds_out, dbg, skeys, skey_cap);
 }
 
 // Stereo row matching pass (handler.cpp:302-323 + struct.cpp:122-148).  Queries = unmarked left
@@ -449,7 +493,8 @@ __device__ inline int block_match_projected(const CandLists &L, const uint32_t *
 // written in left-index order; returns their count.
 __device__ inline int block_row_match(const CandLists &L, const FeatDev &fl, int nl, const FeatDev &fr, int nr,
                                       const CamParams &cam, int *choice, int *items, int *owner_a, int *owner_b,
-                                      int *s_flag, int *s_scan, int *out_query, int *out_train, int *rounds_out)
+                                      int *s_flag, int *s_scan, int *out_query, int *out_train, int *rounds_out,
+                                      uint32_t *skeys = nullptr, int skey_cap = 0)
 {
     const int lane = threadIdx.x & 31;
     auto active = [&](int q) { return fl.matched[q] == 0; }; // tracked from the map this frame: skipped (handler.cpp:307-310)
@@ -464,7 +509,7 @@ __device__ inline int block_row_match(const CandLists &L, const FeatDev &fl, int
         warp_top2(k1, k2, b1, b2);
     };
     block_rounds(L, nl, nr, active, slow, cam.triangulation_ratio_th, cam.desc_dist_th, fr.matched, choice, items,
-                 owner_a, owner_b, s_flag, nullptr, nullptr, rounds_out);
+                 owner_a, owner_b, s_flag, nullptr, nullptr, rounds_out, nullptr, skeys, skey_cap);
     for (int j = threadIdx.x; j < nr; j += blockDim.x)
         if (owner_a[j] != kFree)
             fr.matched[j] = 1;

@@ -51,13 +51,15 @@ struct TrackArgs
     TrackScratch sc;
     CandLists row_cand; // candidate keys of this frame's row matching (rowcand_kernel, extraction stream)
     int owner_cap;      // ints per owner array in dynamic shared memory
+    int key_cap;        // candidate keys that fit behind the two owner arrays
+    long long *dbg;     // clock64() trace of the map pass (LVT_B200_SYNC builds of the launch only)
 };
 
 struct TrackShared
 {
     double W[24]; // world->camera of the left [0..11] and right [12..23] camera
     PoseD pose;
-    int flag[4];
+    int flag[8];
     int scan[34];
     int ctrl[4];
 };
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     extern __shared__ int s_owner[];
     __shared__ TrackShared sh;
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap);
 
     TrackState &S = *a.st;
     FrameCtl &ctl = *a.ctl;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     const int R = tp.cam.tracking_radius;
     const CandLists no_lists{nullptr, nullptr, 0};
     int count = block_match_projected(a.sc.map_cand, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)(R * R), false, owner_a,
-                                      owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0]);
+                                      owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0], a.dbg, skeys, a.key_cap);
     int retried = 0;
     if (count < kNMatchesTh)
     {
@@ -330,6 +333,8 @@ struct PoseArgs
     PoseD *out;
     int *n_inliers;
     long long *dbg;
+    const TrackState *st; // with ctl: where a frame that skips the solver takes its pose from
+    EarlyResult *early;   // pose + state for a blocking caller (nullptr: not wanted)
 };
 
 __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_kernel(PoseArgs a)
@@ -343,8 +348,20 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
     int *n_inl = a.n_inliers;
     if (a.ctl)
     {
-        if (a.ctl->mode != 1)
+        const int mode = a.ctl->mode;
+        if (mode != 1)
+        {
+            // first frame: identity, tracking; lost: the last pose (lvt/src/lvt_system.cpp:159-166,185-193,199-204)
+            if (a.early && cluster.block_rank() == 0 && threadIdx.x == 0)
+            {
+                PoseD id;
+                id.q = Quat{1, 0, 0, 0};
+                id.t[0] = id.t[1] = id.t[2] = 0;
+                a.early->pose = mode == 2 ? id : a.st->last_pose;
+                a.early->state = mode == 2 ? 2 : 3;
+            }
             return; // uniform over the cluster
+        }
         m = a.ctl->n_matches;
         init = a.ctl->pred;
         out = &a.ctl->opt;
@@ -354,7 +371,14 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
     }
     cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl, a.dbg);
     if (a.ctl && cluster.block_rank() == 0 && threadIdx.x == 0)
+    {
         a.ctl->cyc[4] = clock64();
+        if (a.early)
+        {
+            a.early->pose = a.ctl->opt;
+            a.early->state = 2;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,6 +390,7 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
 __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, const FeatDev &fl, int nl, const FeatDev &fr,
                                        int nr, bool dont_stage, int *owner_a, int *owner_b, int &map_n, int &staged_n)
 {
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(owner_a + 2 * a.owner_cap);
     const TrackParams &tp = a.tp;
     const bool to_map = dont_stage || tp.staged_threshold == 0 || map_n < kNMapPoints;
     const PointStore &dst = to_map ? a.map : a.staged;
@@ -375,7 +400,7 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
     if (tp.sensor == 1)
     {
         const int np = block_row_match(a.row_cand, fl, nl, fr, nr, tp.cam, a.sc.row_choice, a.sc.ms.items, owner_a,
-                                       owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3]);
+                                       owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3], skeys, a.key_cap);
         if (np == 0)
             return 0;
         if (threadIdx.x == 0)
@@ -527,7 +552,8 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         const int Sn = staged_n;
         const int R = tp.cam.tracking_radius;
         block_match_projected(a.sc.map_cand, a.staged.desc, a.sc.ms, Sn, fl, nl, tp.cam, (float)(R * R), true, owner_a,
-                              owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[2]);
+                              owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[2], nullptr,
+                              reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap), a.key_cap);
         for (int j = threadIdx.x; j < nl; j += blockDim.x)
             if (owner_a[j] != kFree)
                 fl.matched[j] = 1;
@@ -643,20 +669,21 @@ struct MatchSeamArgs
     int *match_idx;
     float *d1, *d2;
     int *count_retried; // [2]
-    int owner_cap;
+    int owner_cap, key_cap;
 };
 
 __global__ void __launch_bounds__(kTrackThreads, 1) match_seam_kernel(MatchSeamArgs a)
 {
     extern __shared__ int s_owner[];
-    __shared__ int s_flag[4];
+    __shared__ int s_flag[8];
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
     const FeatDev f = *a.feat;
     const int n = min(*f.n, a.owner_cap);
     const int R = a.cam.tracking_radius;
     const CandLists no_lists{nullptr, nullptr, 0};
     int count = block_match_projected(a.lists, a.pdesc, a.ms, a.m, f, n, a.cam, (float)(R * R), true, owner_a, owner_b,
-                                      s_flag, a.d1, a.d2, nullptr);
+                                      s_flag, a.d1, a.d2, nullptr, nullptr,
+                                      reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap), a.key_cap);
     int retried = 0;
     if (count < a.retry_below)
     {
@@ -689,18 +716,19 @@ struct RowSeamArgs
     CamParams cam;
     CandLists lists;
     int *choice, *items, *query, *train, *count;
-    int owner_cap;
+    int owner_cap, key_cap;
 };
 
 __global__ void __launch_bounds__(kTrackThreads, 1) row_seam_kernel(RowSeamArgs a)
 {
     extern __shared__ int s_owner[];
-    __shared__ int s_flag[4];
+    __shared__ int s_flag[8];
     __shared__ int s_scan[34];
     const FeatDev fl = a.feats[0], fr = a.feats[1];
     const int nl = min(*fl.n, a.owner_cap), nr = min(*fr.n, a.owner_cap);
     const int np = block_row_match(a.lists, fl, nl, fr, nr, a.cam, a.choice, a.items, s_owner, s_owner + a.owner_cap,
-                                   s_flag, s_scan, a.query, a.train, nullptr);
+                                   s_flag, s_scan, a.query, a.train, nullptr,
+                                   reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap), a.key_cap);
     if (threadIdx.x == 0)
         *a.count = np;
 }
@@ -738,18 +766,28 @@ __global__ void tri_seam_kernel(TriSeamArgs a)
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
+// dynamic shared memory of the single-CTA kernels: two owner arrays + as many candidate keys as fit
+// next to them (block_rounds keeps the key lists of its queries there)
+static int g_key_cap = 0;
+static size_t track_smem_bytes(int owner_cap) { return (2 * (size_t)owner_cap + (size_t)g_key_cap) * sizeof(int); }
+
 static int ensure_smem(int owner_cap)
 {
     static int configured = 0;
-    const int bytes = 2 * owner_cap * (int)sizeof(int);
-    if (bytes > configured)
+    if (owner_cap > configured)
     {
+        int dev = 0, optin = 0;
+        LVT_CUDA_TRY(cudaGetDevice(&dev));
+        LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        const int avail = optin - 2048 /* static */ - 2 * owner_cap * (int)sizeof(int);
+        g_key_cap = avail > 0 ? (avail / (int)sizeof(int)) & ~3 : 0;
+        const int bytes = (int)track_smem_bytes(owner_cap);
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(match_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(row_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoseShared)));
-        configured = bytes;
+        configured = owner_cap;
     }
     return LVTK_OK;
 }
@@ -766,20 +804,24 @@ int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists
 
 int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
-                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready)
+                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready, int parts, EarlyResult *early)
 {
+    // parts: 1 = up to the pose (mapcand, track_a, pose), 2 = the rest (stagedcand, track_b), 3 = the whole frame
     if (int rc = ensure_smem(owner_cap))
         return rc;
     FrameCtl *ctl = static_cast<FrameCtl *>(ctl_v);
-    const size_t smem = 2 * (size_t)owner_cap * sizeof(int);
+    const size_t smem = track_smem_bytes(owner_cap);
+    TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, owner_cap, g_key_cap,
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr};
+    if (parts & 1)
+    {
     MapCandArgs mc{st, ctl, 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
     LVT_TIMED(stream, K_MAPCAND, (mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc)));
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
-    TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, owner_cap};
     LVT_TIMED(stream, K_TRACK_A, (track_a_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
-                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr};
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early};
     LVT_TIMED(stream, K_POSE, (pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(pa)));
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     if (pa.dbg && std::getenv("LVT_B200_POSEDBG"))
@@ -793,6 +835,26 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
                          h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
         }
     }
+    if (a.dbg && std::getenv("LVT_B200_TRACKDBG"))
+    {
+        static int calls = 0;
+        if (calls == 0)
+            cudaMemset(a.dbg, 0, 24 * sizeof(long long));
+        if (++calls == 8)
+        {
+            long long h[24];
+            cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "map pass: n_fast %lld n_slow %lld smem keys %lld sum counts %lld max count %lld from global %lld\n", h[16],
+                         h[17], h[18], h[19], h[20], h[21]);
+            std::fprintf(stderr, "map pass: lists %lld | cache+reset %lld | rounds", h[1] - h[0], h[2] - h[1]);
+            for (int r = 0; r < 12 && h[3 + r] > h[2] && h[3 + r] < h[15]; r++)
+                std::fprintf(stderr, " %lld", h[3 + r] - (r ? h[2 + r] : h[2]));
+            std::fprintf(stderr, " | total %lld cycles\n", h[15] - h[0]);
+        }
+    }
+    }
+    if (!(parts & 2))
+        return LVTK_OK;
     MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
     LVT_TIMED(stream, K_STAGEDCAND, (mapcand_kernel<<<148, kCandWarps * 32, 0, stream>>>(sc2)));
     LVT_LAUNCH_CHECK(stream, "stagedcand_kernel");
@@ -821,8 +883,8 @@ int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const
     MapCandArgs mc{nullptr, nullptr, 0, 0, pose, m, d_xyz, d_pdesc, d_feat, cam, ms, lists};
     mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc);
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
-    MatchSeamArgs a{d_pdesc, m, d_feat, cam, retry_below, ms, lists, d_match_idx, d_d1, d_d2, d_count_retried, owner_cap};
-    match_seam_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
+    MatchSeamArgs a{d_pdesc, m, d_feat, cam, retry_below, ms, lists, d_match_idx, d_d1, d_d2, d_count_retried, owner_cap, g_key_cap};
+    match_seam_kernel<<<1, kTrackThreads, track_smem_bytes(owner_cap), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "match_seam_kernel");
     return LVTK_OK;
 }
@@ -834,8 +896,8 @@ int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandList
         return rc;
     if (int rc = launch_rowcand(d_feats, cam, lists, stream))
         return rc;
-    RowSeamArgs a{d_feats, cam, lists, d_choice, d_items, d_query, d_train, d_count, owner_cap};
-    row_seam_kernel<<<1, kTrackThreads, 2 * owner_cap * sizeof(int), stream>>>(a);
+    RowSeamArgs a{d_feats, cam, lists, d_choice, d_items, d_query, d_train, d_count, owner_cap, g_key_cap};
+    row_seam_kernel<<<1, kTrackThreads, track_smem_bytes(owner_cap), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "row_seam_kernel");
     return LVTK_OK;
 }
@@ -845,7 +907,7 @@ int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD
 {
     if (int rc = ensure_smem(16))
         return rc;
-    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr};
+    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr, nullptr, nullptr};
     pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     return LVTK_OK;

@@ -50,6 +50,15 @@ struct FrameResult
     long long dbg[8];    // clock64() marks inside the map pass (profiling aid)
 };
 
+// what a blocking caller waits for: available as soon as the pose solver is through, while the map
+// maintenance of the frame (track_b) is still running
+struct EarlyResult
+{
+    PoseD pose;
+    int state;
+    int pad;
+};
+
 struct TrackParams
 {
     CamParams cam;

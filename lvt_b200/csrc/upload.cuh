@@ -1,15 +1,19 @@
 // Host -> HBM staging for the blocking entry points (lvt_track & co.).
 //
 // The caller's images are pageable (lvt/src/lvt_c.cpp:69-70 borrows them for the call), so each one
-// goes user memory -> pinned staging (same pitch as the pool) -> one contiguous
-// DMA per band.  Done by a single thread that is ~45 us of memcpy per 1241x376 image before the first DMA can start, i.e. ~20 % of a
-// frame.  Here the images are cut into row bands; a few lanes (the calling thread plus parked
-// workers) pull bands off an atomic counter, copy the band to its place in the staging buffer and
-// enqueue its DMA right away, so the copy engine runs while the other bands are still being staged.
-// All bands are enqueued on the context's stream before stage() returns, hence anything launched on
-// that stream afterwards sees the complete images.
+// goes user memory -> pinned staging (same pitch as the pool) -> one contiguous DMA per row band.
+// One thread needs ~50 us of memcpy per 1242x375 image before the first DMA can start, i.e. the
+// longest host item on the way to the pose.  Here the image is cut into row bands; a few lanes (the
+// calling thread plus helper threads) pull bands off an atomic counter and copy them into the
+// staging buffer, while the calling thread alone talks to the driver: it enqueues the DMA of band b
+// as soon as band b is staged (helpers never take the driver's locks, which the kernel launches
+// that follow need).  Helpers spin for a short while after a job -- a caller that tracks frame
+// after frame finds them awake -- and park on a condition variable when the stream of calls stops.
+// All bands are enqueued on the given stream before run() returns, hence anything launched on that
+// stream afterwards sees the complete images.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -36,6 +40,7 @@ class UploadLanes
 {
   public:
     static constexpr int kMaxBands = 32;
+    static constexpr int kSpinMicros = 500; // helpers stay awake this long after a job
 
     UploadLanes() = default;
     UploadLanes(const UploadLanes &) = delete;
@@ -43,7 +48,7 @@ class UploadLanes
 
     void start(int device, int n_workers)
     {
-        device_ = device;
+        (void)device;
         next_.store(1 << 30);
         for (int i = 0; i < n_workers; i++)
             workers_.emplace_back([this] { worker(); });
@@ -53,8 +58,8 @@ class UploadLanes
     {
         {
             std::lock_guard<std::mutex> lk(mu_);
-            quit_ = true;
-            generation_++;
+            quit_.store(true);
+            generation_.fetch_add(1);
         }
         cv_.notify_all();
         for (auto &t : workers_)
@@ -63,6 +68,8 @@ class UploadLanes
     }
 
     ~UploadLanes() { stop(); }
+
+    int lanes() const { return 1 + (int)workers_.size(); }
 
     // cut [rows x width_bytes] into `parts` row bands and append them to the pending job
     void add_image(const void *src, size_t src_stride, void *stage, void *dst, size_t pitch, size_t width_bytes, int rows,
@@ -85,80 +92,107 @@ class UploadLanes
     // stage + enqueue every pending band on `stream`; returns the first CUDA error (or cudaSuccess)
     cudaError_t run(cudaStream_t stream)
     {
-        stream_ = stream;
-        error_.store((int)cudaSuccess);
-        done_.store(0);
         const int n = n_bands_;
+        for (int i = 0; i < n; i++)
+            staged_[i].store(0, std::memory_order_relaxed);
         n_active_.store(n, std::memory_order_relaxed);
         next_.store(0, std::memory_order_release); // opens the job: bands_ / n_active_ are complete
         if (!workers_.empty() && n > 1)
         {
+            generation_.fetch_add(1);
+            if (parked_.load() > 0)
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                generation_++;
+                cv_.notify_all();
             }
-            cv_.notify_all();
         }
-        lane();
-        while (done_.load(std::memory_order_acquire) < n)
-            ; // the other lanes are at most one band behind
-        n_bands_ = 0;
-        return (cudaError_t)error_.load();
-    }
-
-  private:
-    void lane()
-    {
+        cudaError_t err = cudaSuccess;
+        int sent = 0;
+        auto send_ready = [&](bool wait) {
+            while (sent < n)
+            {
+                if (!staged_[sent].load(std::memory_order_acquire))
+                {
+                    if (!wait)
+                        return;
+                    continue; // a helper is at most one band behind
+                }
+                const UploadBand &b = bands_[sent];
+                // the staging buffer has the pool's pitch, so a band is one contiguous DMA (the
+                // padding columns travel along; nothing reads them)
+                const cudaError_t e = cudaMemcpyAsync(b.dst, b.stage, b.pitch * (size_t)(b.rows - 1) + b.width_bytes,
+                                                      cudaMemcpyHostToDevice, stream);
+                if (e != cudaSuccess)
+                    err = e;
+                sent++;
+            }
+        };
         for (;;)
         {
             const int i = next_.fetch_add(1, std::memory_order_acq_rel);
-            if (i >= n_active_.load(std::memory_order_relaxed) || i < 0)
-                return;
-            const UploadBand &b = bands_[i];
-            // the staging buffer has the pool's pitch, so a band is one contiguous DMA (the padding
-            // columns travel along; nothing reads them)
-            if (b.src_stride == b.pitch)
-                std::memcpy(b.stage, b.src, b.pitch * (size_t)(b.rows - 1) + b.width_bytes);
-            else
-                for (int y = 0; y < b.rows; y++)
-                    std::memcpy(b.stage + (size_t)y * b.pitch, b.src + (size_t)y * b.src_stride, b.width_bytes);
-            const cudaError_t e = cudaMemcpyAsync(b.dst, b.stage, b.pitch * (size_t)(b.rows - 1) + b.width_bytes,
-                                                  cudaMemcpyHostToDevice, stream_);
-            if (e != cudaSuccess)
-                error_.store((int)e);
-            done_.fetch_add(1, std::memory_order_release);
+            if (i >= n)
+                break;
+            copy_band(i);
+            send_ready(false);
         }
+        send_ready(true);
+        n_bands_ = 0;
+        return err;
+    }
+
+  private:
+    void copy_band(int i)
+    {
+        const UploadBand &b = bands_[i];
+        if (b.src_stride == b.pitch)
+            std::memcpy(b.stage, b.src, b.pitch * (size_t)(b.rows - 1) + b.width_bytes);
+        else
+            for (int y = 0; y < b.rows; y++)
+                std::memcpy(b.stage + (size_t)y * b.pitch, b.src + (size_t)y * b.src_stride, b.width_bytes);
+        staged_[i].store(1, std::memory_order_release);
     }
 
     void worker()
     {
-        cudaSetDevice(device_);
         uint64_t seen = 0;
+        auto last_job = std::chrono::steady_clock::now();
         for (;;)
         {
+            if (generation_.load(std::memory_order_acquire) == seen)
             {
+                if (std::chrono::steady_clock::now() - last_job < std::chrono::microseconds(kSpinMicros))
+                    continue; // spin: the next frame usually follows at once
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return generation_ != seen; });
-                seen = generation_;
-                if (quit_)
-                    return;
+                parked_.fetch_add(1);
+                cv_.wait(lk, [&] { return generation_.load() != seen; });
+                parked_.fetch_sub(1);
             }
-            lane();
+            seen = generation_.load(std::memory_order_acquire);
+            if (quit_.load())
+                return;
+            for (;;)
+            {
+                const int i = next_.fetch_add(1, std::memory_order_acq_rel);
+                if (i >= n_active_.load(std::memory_order_relaxed) || i < 0)
+                    break;
+                copy_band(i);
+            }
+            last_job = std::chrono::steady_clock::now();
         }
     }
 
-    int device_ = 0;
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_;
-    uint64_t generation_ = 0;
-    bool quit_ = false;
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<int> parked_{0};
+    std::atomic<bool> quit_{false};
 
     UploadBand bands_[kMaxBands];
     int n_bands_ = 0;
     std::atomic<int> n_active_{0}; // written before next_ is released
-    cudaStream_t stream_ = nullptr;
-    std::atomic<int> next_{1 << 30}, done_{0}, error_{0};
+    std::atomic<int> next_{1 << 30};
+    std::atomic<int> staged_[kMaxBands];
 };
 
 } // namespace lvtb

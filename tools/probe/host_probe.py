@@ -49,9 +49,10 @@ if stats_lib:
 
 lib = lvt_b200.load()
 lib.lib.lvt_debug_host_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-for threads, bands in [(1, 1), (1, 2), (1, 4), (2, 1), (2, 2), (2, 4), (3, 2), (4, 2), (4, 4)]:
-    os.environ["LVT_B200_UPLOAD_THREADS"] = str(threads)
-    os.environ["LVT_B200_UPLOAD_BANDS"] = str(bands)
+for threads, bands in [(0, 0), (1, 1), (2, 2), (3, 3), (4, 4), (4, 8), (6, 6)]:
+    if threads:
+        os.environ["LVT_B200_UPLOAD_THREADS"] = str(threads)
+        os.environ["LVT_B200_UPLOAD_BANDS"] = str(bands)
     vo = lib.create(p, 1)
     for t in range(10):
         vo.track(*frames[t])
