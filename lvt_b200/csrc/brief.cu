@@ -10,7 +10,7 @@
 // __ballot_sync per 32-bit descriptor word; the lane -> test mapping is chosen so that the
 // ballot word already has OpenCV's bit order (test 8b+j -> byte b, bit 7-j).
 // The next keypoint's patch is in flight while the current one is being integrated.
-#include "extract.cuh"
+#include "index.cuh"
 
 namespace lvtb
 {
@@ -53,12 +53,23 @@ struct BriefArgs
     const int *slots;
     const FeatDev *feats;
     int rows, cols;
+    int with_index; // 1: the last CTA of every image builds the feature index (index.cuh) instead of describing
+    CamParams cam;
 };
 
 __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_constant__ CUtensorMap tmap, BriefArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.with_index && blockIdx.x == gridDim.x - 1)
+    {
+        // the hash grid / row CSR need the keypoint positions only: built next to the descriptors
+        // instead of in a kernel of its own behind them
+        __shared__ int s_scan[34];
+        block_build_index(a.feats[blockIdx.y], a.cam, reinterpret_cast<int *>(smem), s_scan);
+        return;
+    }
     uint8_t *patch = smem + warp * (kPatchSlot + kIntegSlot);
     uint16_t *integ = reinterpret_cast<uint16_t *>(patch + kPatchSlot);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kBriefWarps * (kPatchSlot + kIntegSlot)) + warp;
@@ -67,7 +78,7 @@ __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_co
     const FeatDev f = a.feats[b];
     const int n = *f.n;
     const int slot = a.slots[b];
-    const int stride = gridDim.x * kBriefWarps;
+    const int stride = (gridDim.x - a.with_index) * kBriefWarps;
     int kp = blockIdx.x * kBriefWarps + warp;
 
     uint32_t offs[8];
@@ -231,7 +242,10 @@ int launch_border_filter(const float2 *src_xy, const float *src_resp, const int 
     return LVTK_OK;
 }
 
-int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream)
+bool brief_can_index(const CamParams &cam) { return index_smem_ints(cam) * (int)sizeof(int) <= kBriefSmem; }
+
+int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream,
+                 const CamParams *index_cam)
 {
     static bool smem_set = false;
     if (!smem_set)
@@ -239,9 +253,16 @@ int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const 
         LVT_CUDA_TRY(cudaFuncSetAttribute(brief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBriefSmem));
         smem_set = true;
     }
-    BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols};
+    BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols, 0, CamParams{}};
+    if (index_cam)
+    {
+        if (index_smem_ints(*index_cam) * (int)sizeof(int) > kBriefSmem)
+            return LVTK_ERR_ARG; // the caller launches index_kernel instead (brief_can_index)
+        ba.with_index = 1;
+        ba.cam = *index_cam;
+    }
     // persistent-style: 148 SMs x 4 CTAs of 4 warps per image; warps stride over the keypoints
-    LVT_TIMED(stream, K_BRIEF, (brief_kernel<<<dim3(148 * 2, n_images), kBriefWarps * 32, kBriefSmem, stream>>>(pool.tmap_patch, ba)));
+    LVT_TIMED(stream, K_BRIEF, launch_chained(brief_kernel, dim3(148 * 2 + ba.with_index, n_images), dim3(kBriefWarps * 32), kBriefSmem, stream, pool.tmap_patch, ba));
     LVT_LAUNCH_CHECK(stream, "brief_kernel");
     return LVTK_OK;
 }

@@ -48,6 +48,33 @@ void count_launch();
 long launch_count();
 void prof_begin(cudaStream_t s, int id);
 void prof_end(cudaStream_t s, int id);
+// Programmatic dependent launch: every kernel of the per-frame chain is launched with the
+// programmatic-stream-serialization attribute and starts with LVT_GRID_DEP_SYNC(), so its CTAs are
+// scheduled (and its launch latency is paid) while the previous kernel of the stream is still
+// running; griddepcontrol.wait returns once that kernel has completed and its writes are visible.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define LVT_GRID_DEP_SYNC()                                                                                           \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaGridDependencySynchronize();                                                                              \
+        cudaTriggerProgrammaticLaunchCompletion();                                                                    \
+    } while (0)
+
 #define LVT_TIMED(stream, id, launch)                                                                                 \
     do                                                                                                                \
     {                                                                                                                 \

@@ -383,6 +383,7 @@ struct lvtk_ctx
     uint8_t *h_stage = nullptr; // pinned, one image per pool slot, the pool's pitch
     UploadLanes lanes;          // host staging lanes of the blocking entry points
     int upload_bands = 1;       // row bands per image
+    int upload_dmas = 1;        // DMAs per image
     float *d_depth = nullptr, *h_depth = nullptr;
     // seam inputs
     float2 *d_in_xy = nullptr;
@@ -396,7 +397,9 @@ struct lvtk_ctx
     uint8_t *d_ctl = nullptr; // FrameCtl: hand-over between the kernels of the tracking chain
     FrameResult *d_result = nullptr, *h_result = nullptr;
     int *h_error = nullptr; // pinned copy of ws.error, fetched together with the result
-    EarlyResult *d_early = nullptr, *h_early = nullptr; // pose + state, copied out right behind the pose solver
+    EarlyResult *h_early = nullptr, *d_early = nullptr; // pose + state in mapped pinned memory (d_early: its device
+                                                        // address), written by the pose solver itself
+    int early_seq = 0;
     cudaEvent_t ev_pose = nullptr;      // h_early is valid
     cudaEvent_t ev_frame = nullptr;     // the whole frame (map maintenance, h_result, h_error) is through
     int parity = 0;                     // blocking stereo frames alternate between two sets of buffers
@@ -531,7 +534,6 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->d_state, 1);
     rc = rc ? rc : c->arena.alloc(&c->d_ctl, frame_ctl_bytes());
     rc = rc ? rc : c->arena.alloc(&c->d_result, 1);
-    rc = rc ? rc : c->arena.alloc(&c->d_early, 1);
     rc = rc ? rc : make_points(&c->map, c->arena, c->pcap);
     rc = rc ? rc : make_points(&c->staged, c->arena, c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.proj, (size_t)c->pcap);
@@ -567,7 +569,9 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     LVT_CUDA_TRY(cudaMallocHost(&c->h_depth, sizeof(float) * (size_t)p.img_width * p.img_height));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_result, sizeof(FrameResult)));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_error, sizeof(int)));
-    LVT_CUDA_TRY(cudaMallocHost(&c->h_early, sizeof(EarlyResult)));
+    LVT_CUDA_TRY(cudaHostAlloc(&c->h_early, sizeof(EarlyResult), cudaHostAllocMapped));
+    std::memset(c->h_early, 0, sizeof(EarlyResult));
+    LVT_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->d_early), c->h_early, 0));
     {
         // staging lanes (the calling thread + helpers, upload.cuh): LVT_B200_UPLOAD_THREADS; row bands
         // per image: LVT_B200_UPLOAD_BANDS.  Default: up to 4 lanes, a quarter of the host cores
@@ -578,9 +582,12 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
         int lanes = std::max(1, std::min(4, cores / (4 * std::max(1, ndev_all))));
         if (const char *e = std::getenv("LVT_B200_UPLOAD_THREADS"))
             lanes = std::max(1, std::min(16, std::atoi(e)));
-        c->upload_bands = lanes;
+        c->upload_bands = lanes > 1 ? 2 * lanes : 1;
         if (const char *e = std::getenv("LVT_B200_UPLOAD_BANDS"))
-            c->upload_bands = std::max(1, std::min(8, std::atoi(e)));
+            c->upload_bands = std::max(1, std::min(16, std::atoi(e)));
+        c->upload_dmas = 1; // one DMA per image measured best (tools/probe/timeline_probe.py)
+        if (const char *e = std::getenv("LVT_B200_UPLOAD_DMAS"))
+            c->upload_dmas = std::max(1, std::min(16, std::atoi(e)));
         c->lanes.start(c->device, lanes - 1);
     }
     if (!g_pairs_uploaded)
@@ -653,7 +660,8 @@ static void ctx_free(lvtk_ctx *c)
 static void ctx_stage_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows, int cols, int stride)
 {
     c->lanes.add_image(img, (size_t)stride, c->h_stage + (size_t)slot * rows * c->pool.pitch,
-                       c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, (size_t)cols, rows, c->upload_bands);
+                       c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, (size_t)cols, rows, c->upload_bands,
+                       c->upload_dmas);
 }
 
 static int ctx_stage_flush(lvtk_ctx *c, cudaStream_t stream = nullptr)
@@ -890,18 +898,19 @@ struct System
             cudaEventRecord(c->ev_tl[1], xl);
         if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, slots, 1, feats, kBriefBorder, 1, xl))
             return rc;
-        if (int rc = launch_brief(c->pool, slots, 1, feats, xl))
+        const bool fused_index = brief_can_index(c->cam);
+        if (int rc = launch_brief(c->pool, slots, 1, feats, xl, fused_index ? &c->cam : nullptr))
             return rc;
-        if (int rc = launch_index(feats, 1, c->cam, xl))
-            return rc;
+        if (!fused_index)
+            if (int rc = launch_index(feats, 1, c->cam, xl))
+                return rc;
         LVT_CUDA_TRY(cudaEventRecord(c->ev_left, xl));
         if (timeline)
             cudaEventRecord(c->ev_tl[2], xl);
         LVT_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_left, 0));
         if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc,
-                                        c->row_cand[s], c->fcap, st, nullptr, 1, c->d_early))
+                                        c->row_cand[s], c->fcap, st, nullptr, 1, c->d_early, ++c->early_seq))
             return rc;
-        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_early, c->d_early, sizeof(EarlyResult), cudaMemcpyDeviceToHost, st));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
         if (timeline)
             cudaEventRecord(c->ev_tl[3], st);
@@ -911,10 +920,11 @@ struct System
         host_mark(1);
         if (int rc = launch_detect(c->pool, c->wsx[1], c->dp, slots + 1, 1, feats + 1, kBriefBorder, 1, xr))
             return rc;
-        if (int rc = launch_brief(c->pool, slots + 1, 1, feats + 1, xr))
+        if (int rc = launch_brief(c->pool, slots + 1, 1, feats + 1, xr, fused_index ? &c->cam : nullptr))
             return rc;
-        if (int rc = launch_index(feats + 1, 1, c->cam, xr))
-            return rc;
+        if (!fused_index)
+            if (int rc = launch_index(feats + 1, 1, c->cam, xr))
+                return rc;
         LVT_CUDA_TRY(cudaStreamWaitEvent(xr, c->ev_left, 0)); // the candidates pair left with right descriptors
         if (int rc = launch_rowcand(feats, c->cam, c->row_cand[s], xr))
             return rc;
@@ -926,7 +936,23 @@ struct System
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_frame, st));
         host_mark(2);
-        LVT_CUDA_TRY(cudaEventSynchronize(c->ev_pose));
+        {
+            // the pose solver stores its result straight into pinned host memory, sequence number last
+            const int want = c->early_seq;
+            unsigned spins = 0;
+            while (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+                if ((++spins & 0xFFFu) == 0 && cudaEventQuery(c->ev_pose) != cudaErrorNotReady)
+                    break;
+            if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+            {
+                LVT_CUDA_TRY(cudaEventSynchronize(c->ev_pose));
+                if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+                {
+                    set_last_error(__FILE__, __LINE__, "the pose solver did not report");
+                    return LVTK_ERR_CUDA;
+                }
+            }
+        }
         host_mark(3);
         if (timeline)
         {
@@ -1083,10 +1109,12 @@ struct System
             FeatDev *feats = c->feats_d + 2 * set;
             if (int rc = launch_detect(c->rpool, c->wsx[x], c->dp, slots, 2, feats, kBriefBorder, 1, sx))
                 return rc;
-            if (int rc = launch_brief(c->rpool, slots, 2, feats, sx))
+            const bool fused_index = brief_can_index(c->cam);
+            if (int rc = launch_brief(c->rpool, slots, 2, feats, sx, fused_index ? &c->cam : nullptr))
                 return rc;
-            if (int rc = launch_index(feats, 2, c->cam, sx))
-                return rc;
+            if (!fused_index)
+                if (int rc = launch_index(feats, 2, c->cam, sx))
+                    return rc;
             if (int rc = launch_rowcand(feats, c->cam, c->row_cand[set], sx))
                 return rc;
             LVT_CUDA_TRY(cudaEventRecord(c->ev_extracted[set], sx));

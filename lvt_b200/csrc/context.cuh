@@ -12,7 +12,7 @@ int launch_depth_gate(const FeatDev &f, const float *d_depth, const lvt_params_c
 int launch_track_frame(TrackState *st, void *ctl, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
                        int owner_cap, cudaStream_t stream, cudaEvent_t right_ready = nullptr, int parts = 3,
-                       EarlyResult *early = nullptr);
+                       EarlyResult *early = nullptr, int early_seq = 0);
 size_t frame_ctl_bytes();
 int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists &L, cudaStream_t stream);
 int launch_reset_state(TrackState *st, cudaStream_t stream);

@@ -105,6 +105,7 @@ __device__ __forceinline__ int agast_score(const uint8_t *p)
 
 __global__ void __launch_bounds__(256) score_kernel(const __grid_constant__ CUtensorMap tmap, ScoreArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     __shared__ __align__(128) uint8_t tile[kScoreBoxH][kScoreBoxW];
     __shared__ __align__(8) uint64_t bar;
 
@@ -514,6 +515,7 @@ __device__ __forceinline__ long long nms_ns()
 
 __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
 #ifdef LVT_NMS_STATS
     __shared__ unsigned long long s_longest;
     if (threadIdx.x == 0)
@@ -1013,6 +1015,7 @@ constexpr int kTileBitmapBits = 65536; // raster ranks by bitmap for tiles of up
 
 __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t *s_keys = s_dyn, *s_rad = s_dyn + kTileSmemCap, *s_perm = s_dyn + 2 * kTileSmemCap;
     isort::LevelRange *s_q0 = reinterpret_cast<isort::LevelRange *>(s_dyn + 3 * kTileSmemCap), *s_q1 = s_q0 + kTileRanges;
@@ -1343,6 +1346,7 @@ struct GatherArgs
 
 __global__ void __launch_bounds__(1024) gather_kernel(GatherArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     __shared__ int s_pref[1025];
     __shared__ int s_scan[34];
     const int b = blockIdx.x;
@@ -1443,7 +1447,7 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold,
                  ws.tile_count, ws.tile_overflow, nt};
     dim3 sgrid((dp.cols + kScoreTileW - 1) / kScoreTileW, (dp.rows + kScoreTileH - 1) / kScoreTileH, n_images);
-    LVT_TIMED(stream, K_SCORE, (score_kernel<<<sgrid, 256, 0, stream>>>(pool.tmap_score, sa)));
+    LVT_TIMED(stream, K_SCORE, launch_chained(score_kernel, sgrid, dim3(256), 0, stream, pool.tmap_score, sa));
     LVT_LAUNCH_CHECK(stream, "score_kernel");
 
     // pass 1 (threshold halved, :161-169) is launched unconditionally and exits at once for images
@@ -1455,15 +1459,15 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
         NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, retry,      dp.grid,
                    dp.pitch, dp.rows,      dp.cols,       ws.tile_cap,      nt,       th,         nonmax};
         dim3 ngrid((dp.cols + kNmsTile - 1) / kNmsTile, (dp.rows + kNmsTile - 1) / kNmsTile, n_images);
-        LVT_TIMED(stream, K_NMS, (nms_tile_kernel<<<ngrid, 256, 0, stream>>>(na)));
+        LVT_TIMED(stream, K_NMS, launch_chained(nms_tile_kernel, ngrid, dim3(256), 0, stream, na));
         LVT_LAUNCH_CHECK(stream, "nms_tile_kernel");
         TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count,   ws.tile_out_count, retry,
                     dp.grid,      ws.tile_cap, nt,          dp.max_per_cell, na,                ws.parent};
-        LVT_TIMED(stream, K_TILE, (tile_kernel<<<dim3(nt, n_images), kTileThreads, kTileSmemBytes, stream>>>(ta)));
+        LVT_TIMED(stream, K_TILE, launch_chained(tile_kernel, dim3(nt, n_images), dim3(kTileThreads), kTileSmemBytes, stream, ta));
         LVT_LAUNCH_CHECK(stream, "tile_kernel");
         GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, ws.tile_count, ws.tile_overflow, d_feats, nt,
                       ws.tile_cap, dp.rows,           dp.cols,  border,   pass,          allow_retry ? kCornersLowTh : 0};
-        LVT_TIMED(stream, K_GATHER, (gather_kernel<<<n_images, 1024, 0, stream>>>(ga)));
+        LVT_TIMED(stream, K_GATHER, launch_chained(gather_kernel, dim3(n_images), dim3(1024), 0, stream, ga));
         LVT_LAUNCH_CHECK(stream, "gather_kernel");
     }
     LVT_CUDA_TRY(cudaGetLastError());

@@ -80,7 +80,11 @@ struct DetectParams
 int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const DetectParams &dp, const int *d_slots,
                   int n_images, FeatDev *d_feats /* device array [n_images] */, int border, int single_tile_nms,
                   cudaStream_t stream);
-int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream);
+// index_cam != nullptr: one extra CTA per image builds the feature index (hash grid, row CSR, cleared
+// marks) next to the descriptors, replacing a launch_index call; requires brief_can_index(cam)
+int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream,
+                 const CamParams *index_cam = nullptr);
+bool brief_can_index(const CamParams &cam);
 int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cudaStream_t stream);
 int upload_brief_pairs(const signed char pairs[256][4]);
 

@@ -89,6 +89,7 @@ struct MapCandArgs
 
 __global__ void __launch_bounds__(kCandWarps * 32) mapcand_kernel(MapCandArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     __shared__ double W[12];
     __shared__ uint32_t buf[kCandWarps][kMapCandCap];
     int m = a.m;
@@ -159,6 +160,7 @@ struct RowCandArgs
 
 __global__ void __launch_bounds__(kCandWarps * 32) rowcand_kernel(RowCandArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     __shared__ uint32_t buf[kCandWarps][kRowCandCap];
     const FeatDev fl = a.feats[0], fr = a.feats[1];
     const int nl = *fl.n;
@@ -198,6 +200,7 @@ __device__ void write_result(const TrackArgs &a, TrackState &S, const PoseD &pos
 
 __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     extern __shared__ int s_owner[];
     __shared__ TrackShared sh;
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
@@ -334,11 +337,13 @@ struct PoseArgs
     int *n_inliers;
     long long *dbg;
     const TrackState *st; // with ctl: where a frame that skips the solver takes its pose from
-    EarlyResult *early;   // pose + state for a blocking caller (nullptr: not wanted)
+    EarlyResult *early;   // pose + state for a blocking caller, in mapped host memory (nullptr: not wanted)
+    int early_seq;
 };
 
 __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_kernel(PoseArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     extern __shared__ __align__(16) unsigned char pose_smem[];
     PoseShared &s = *reinterpret_cast<PoseShared *>(pose_smem);
     cg::cluster_group cluster = cg::this_cluster();
@@ -359,6 +364,8 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
                 id.t[0] = id.t[1] = id.t[2] = 0;
                 a.early->pose = mode == 2 ? id : a.st->last_pose;
                 a.early->state = mode == 2 ? 2 : 3;
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(&a.early->seq) = a.early_seq;
             }
             return; // uniform over the cluster
         }
@@ -377,6 +384,8 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
         {
             a.early->pose = a.ctl->opt;
             a.early->state = 2;
+            __threadfence_system();
+            *reinterpret_cast<volatile int *>(&a.early->seq) = a.early_seq;
         }
     }
 }
@@ -480,6 +489,7 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
 
 __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
 {
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     extern __shared__ int s_owner[];
     __shared__ TrackShared sh;
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
@@ -797,14 +807,15 @@ size_t frame_ctl_bytes() { return sizeof(FrameCtl); }
 int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists &L, cudaStream_t stream)
 {
     RowCandArgs a{d_feats, cam, L};
-    LVT_TIMED(stream, K_ROWCAND, (rowcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(a)));
+    LVT_TIMED(stream, K_ROWCAND, launch_chained(rowcand_kernel, dim3(148 * 2), dim3(kCandWarps * 32), 0, stream, a));
     LVT_LAUNCH_CHECK(stream, "rowcand_kernel");
     return LVTK_OK;
 }
 
 int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
-                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready, int parts, EarlyResult *early)
+                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready, int parts, EarlyResult *early,
+                       int early_seq)
 {
     // parts: 1 = up to the pose (mapcand, track_a, pose), 2 = the rest (stagedcand, track_b), 3 = the whole frame
     if (int rc = ensure_smem(owner_cap))
@@ -816,13 +827,13 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     if (parts & 1)
     {
     MapCandArgs mc{st, ctl, 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
-    LVT_TIMED(stream, K_MAPCAND, (mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc)));
+    LVT_TIMED(stream, K_MAPCAND, launch_chained(mapcand_kernel, dim3(148 * 2), dim3(kCandWarps * 32), 0, stream, mc));
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
-    LVT_TIMED(stream, K_TRACK_A, (track_a_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
+    LVT_TIMED(stream, K_TRACK_A, launch_chained(track_a_kernel, dim3(1), dim3(kTrackThreads), smem, stream, a));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
-                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early};
-    LVT_TIMED(stream, K_POSE, (pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(pa)));
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early, early_seq};
+    LVT_TIMED(stream, K_POSE, launch_chained(pose_kernel, dim3(kPoseCluster), dim3(kPoseThreads), sizeof(PoseShared), stream, pa));
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     if (pa.dbg && std::getenv("LVT_B200_POSEDBG"))
     {
@@ -856,13 +867,13 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     if (!(parts & 2))
         return LVTK_OK;
     MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
-    LVT_TIMED(stream, K_STAGEDCAND, (mapcand_kernel<<<148, kCandWarps * 32, 0, stream>>>(sc2)));
+    LVT_TIMED(stream, K_STAGEDCAND, launch_chained(mapcand_kernel, dim3(148), dim3(kCandWarps * 32), 0, stream, sc2));
     LVT_LAUNCH_CHECK(stream, "stagedcand_kernel");
     // everything up to here needs the left image only; the right image's features and the row-matching
     // candidates (extracted on another stream by the blocking stereo path) join here
     if (right_ready)
         LVT_CUDA_TRY(cudaStreamWaitEvent(stream, right_ready, 0));
-    LVT_TIMED(stream, K_TRACK_B, (track_b_kernel<<<1, kTrackThreads, smem, stream>>>(a)));
+    LVT_TIMED(stream, K_TRACK_B, launch_chained(track_b_kernel, dim3(1), dim3(kTrackThreads), smem, stream, a));
     LVT_LAUNCH_CHECK(stream, "track_b_kernel");
     return LVTK_OK;
 }
@@ -907,7 +918,7 @@ int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD
 {
     if (int rc = ensure_smem(16))
         return rc;
-    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr, nullptr, nullptr};
+    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr, nullptr, nullptr, 0};
     pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     return LVTK_OK;

@@ -56,7 +56,7 @@ struct EarlyResult
 {
     PoseD pose;
     int state;
-    int pad;
+    int seq; // written last (after a system-wide fence): the caller polls it in pinned host memory
 };
 
 struct TrackParams

@@ -34,6 +34,8 @@ struct UploadBand
     size_t pitch;       // of stage and dst
     size_t width_bytes;
     int rows;
+    int dma_first; // first band of the DMA this band belongs to
+    bool dma_last; // the DMA is enqueued once this band (and the ones before it) are staged
 };
 
 class UploadLanes
@@ -72,13 +74,23 @@ class UploadLanes
     int lanes() const { return 1 + (int)workers_.size(); }
 
     // cut [rows x width_bytes] into `parts` row bands and append them to the pending job
+    // (the staging granularity) and `dmas` DMAs of consecutive bands (each DMA costs the calling thread
+    // ~3 us of driver time, so there are fewer of them than bands)
     void add_image(const void *src, size_t src_stride, void *stage, void *dst, size_t pitch, size_t width_bytes, int rows,
-                   int parts)
+                   int parts, int dmas = 1)
     {
         const int step = (rows + parts - 1) / parts;
-        for (int y = 0; y < rows && n_bands_ < kMaxBands; y += step)
+        const int n_parts = (rows + step - 1) / step;
+        dmas = dmas < 1 ? 1 : (dmas > n_parts ? n_parts : dmas);
+        const int per_dma = (n_parts + dmas - 1) / dmas;
+        int k = 0, first = n_bands_;
+        for (int y = 0; y < rows && n_bands_ < kMaxBands; y += step, k++)
         {
+            if (k % per_dma == 0)
+                first = n_bands_;
             UploadBand &b = bands_[n_bands_++];
+            b.dma_first = first;
+            b.dma_last = (k % per_dma == per_dma - 1) || y + step >= rows || n_bands_ == kMaxBands;
             b.src = (const uint8_t *)src + (size_t)y * src_stride;
             b.src_stride = src_stride;
             b.stage = (uint8_t *)stage + (size_t)y * pitch;
@@ -118,13 +130,16 @@ class UploadLanes
                     continue; // a helper is at most one band behind
                 }
                 const UploadBand &b = bands_[sent];
-                // the staging buffer has the pool's pitch, so a band is one contiguous DMA (the
-                // padding columns travel along; nothing reads them)
-                const cudaError_t e = cudaMemcpyAsync(b.dst, b.stage, b.pitch * (size_t)(b.rows - 1) + b.width_bytes,
-                                                      cudaMemcpyHostToDevice, stream);
+                sent++;
+                if (!b.dma_last)
+                    continue;
+                // the staging buffer has the pool's pitch, so consecutive bands are one contiguous DMA
+                // (the padding columns travel along; nothing reads them)
+                const UploadBand &f = bands_[b.dma_first];
+                const size_t bytes = (size_t)(b.stage - f.stage) + b.pitch * (size_t)(b.rows - 1) + b.width_bytes;
+                const cudaError_t e = cudaMemcpyAsync(f.dst, f.stage, bytes, cudaMemcpyHostToDevice, stream);
                 if (e != cudaSuccess)
                     err = e;
-                sent++;
             }
         };
         for (;;)
