@@ -150,28 +150,40 @@ __device__ __forceinline__ bool chol_solve6(const double *H, double lambda, cons
 constexpr int kPoseSums = 29;   // 21 (upper H) + 6 (b) + robust chi2 + number of active edges
 constexpr int kPoseCluster = 8; // CTAs (SMs) sharing the correspondences of one solve
 constexpr int kPoseThreads = 256;
-
-constexpr int kPoseAccStride = kPoseThreads + kPoseThreads / 32; // one pad per 32 entries: conflict-free column sums
+constexpr int kPoseMaxRanks = 16;
+constexpr int kPoseCached = 2; // edges per thread kept in registers across the evaluations
+constexpr int kPoseAccStride = kPoseThreads + kPoseThreads / 32; // one pad per 32 entries: conflict-free both ways
 
 struct PoseShared
 {
-    CamState cam;                                   // every CTA keeps its own copy of the camera under evaluation
-    double acc[kPoseSums][kPoseAccStride];          // per-thread partial sums, summed in a fixed order
-    double part[kPoseSums][kPoseThreads / 32];      // per-warp-slice sums
-    double cta_sums[2][kPoseSums];                  // this CTA's sums (double-buffered), read by every CTA through DSMEM
-    double sums[kPoseSums];                         // cluster totals (every CTA computes the same values)
-    int cont;                                       // 0 evaluate again, 1 end of pass
+    CamState cam;                          // every CTA keeps its own copy of the camera under evaluation
+    double acc[kPoseSums][kPoseAccStride]; // per-thread partial sums, one padded row per sum
+    double part[32];                       // scratch of the inlier count
+    double gather[2][kPoseMaxRanks][32];   // [parity][rank][sum]: every CTA's sums, pushed here by their owners (DSMEM)
+    double sums[32];                       // cluster totals (every CTA computes the same values)
+    double sys[27];                        // thread 0's LM state between evaluations: the system of the last accepted
+    double x[6];                           // state (upper H, b), the step on trial, the camera before it -- kept here
+    CamState backup;                       // rather than in registers, which all 256 threads would have to pay for
+    int cont;                              // 0 evaluate again, 1 end of pass
+};
+
+// One edge of a thread: fixed for the whole solve, so position, measurement, level and the last error
+// live in registers (the first kPoseCached edges of a thread; the rest stays in global memory).
+struct PoseEdge
+{
+    double X, Y, Z, zx, zy, e2;
+    int level; // -1: no edge
 };
 
 // One evaluation at s.cam over the active edges owned by this CTA: errors, robust cost, and the
 // linearisation (H, b) -- g2o recomputes both at every accepted state, so an accepted trial's
 // evaluation doubles as the next iteration's buildSystem.  Edge i is owned by thread
-// (i / blockDim) % nranks == rank, the same one in every evaluation.  Cluster totals end up in
-// rank 0's s.sums after one cluster barrier; the summation order is fixed (deterministic).
+// (i / blockDim) % nranks == rank, the same one in every evaluation.  Every CTA ends up with the
+// cluster totals in s.sums after one cluster barrier; the summation order is fixed (deterministic).
 template <class Cluster>
-__device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, const double *xyz, const float2 *uv,
-                                     const uint8_t *level, double *e2, int m, int rank, int nranks, int parity,
-                                     long long *dbg = nullptr)
+__device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, PoseEdge (&edge)[kPoseCached], const double *xyz,
+                                     const float2 *uv, const uint8_t *level, double *e2, int m, int rank, int nranks,
+                                     int parity, long long *dbg = nullptr)
 {
 #define LVT_PDBG(k)                                                                                                   \
     if (dbg && rank == 0 && threadIdx.x == 0)                                                                         \
@@ -183,41 +195,39 @@ __device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, const doub
 #pragma unroll
     for (int k = 0; k < kPoseSums; k++)
         acc[k] = 0.0;
+    const double w0 = c.w2n[0], w1 = c.w2n[1], w2 = c.w2n[2], w3 = c.w2n[3], w4 = c.w2n[4], w5 = c.w2n[5], w6 = c.w2n[6],
+                 w7 = c.w2n[7], w8 = c.w2n[8], w9 = c.w2n[9], w10 = c.w2n[10], w11 = c.w2n[11];
+    const double t0 = c.t[0], t1 = c.t[1], t2 = c.t[2], fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy;
 
-    for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
-    {
-        if (level[i])
-            continue;
-        const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
-        const double px = c.w2n[0] * X + c.w2n[1] * Y + c.w2n[2] * Z + c.w2n[3];
-        const double py = c.w2n[4] * X + c.w2n[5] * Y + c.w2n[6] * Z + c.w2n[7];
-        const double pz = c.w2n[8] * X + c.w2n[9] * Y + c.w2n[10] * Z + c.w2n[11];
+    // returns chi2 of the edge
+    auto one_edge = [&](double X, double Y, double Z, double zx, double zy) -> double {
+        const double px = fma(w0, X, fma(w1, Y, fma(w2, Z, w3)));
+        const double py = fma(w4, X, fma(w5, Y, fma(w6, Z, w7)));
+        const double pz = fma(w8, X, fma(w9, Y, fma(w10, Z, w11)));
         // EdgeProjectP2MC::computeError: (K w2n p).head<2>() / z - measurement
-        const float2 z = uv[i];
-        const double ex = (c.fx * px + c.cx * pz) / pz - (double)z.x;
-        const double ey = (c.fy * py + c.cy * pz) / pz - (double)z.y;
-        const double chi = ex * ex + ey * ey;
-        e2[i] = chi;
-        const double aux = dsqr_reci * chi + 1.0;
-        acc[27] += dsqr * log(aux); // RobustKernelCauchy rho[0]
+        const double ipz = 1.0 / pz;
+        const double ex = fma(fma(fx, px, cx * pz), ipz, -zx);
+        const double ey = fma(fma(fy, py, cy * pz), ipz, -zy);
+        const double chi = fma(ex, ex, ey * ey);
+        const double aux = fma(dsqr_reci, chi, 1.0);
+        acc[27] = fma(dsqr, log(aux), acc[27]); // RobustKernelCauchy rho[0]
         acc[28] += 1.0;
         const double w = 1.0 / aux; // rho[1]
         // EdgeProjectP2MC::linearizeOplus, camera block
-        const double ipz2 = 1.0 / (pz * pz);
-        const double ipz2fx = ipz2 * c.fx, ipz2fy = ipz2 * c.fy;
-        const double pw[3] = {X - c.t[0], Y - c.t[1], Z - c.t[2]};
+        const double ipz2 = ipz * ipz;
+        const double ipz2fx = ipz2 * fx, ipz2fy = ipz2 * fy;
+        const double pw0 = X - t0, pw1 = Y - t1, pw2 = Z - t2;
         double J0[6], J1[6];
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-        {
-            const double d0 = -c.w2n[k], d1 = -c.w2n[4 + k], d2 = -c.w2n[8 + k];
-            J0[k] = (pz * d0 - px * d2) * ipz2fx;
-            J1[k] = (pz * d1 - py * d2) * ipz2fy;
-        }
+        J0[0] = (px * w8 - pz * w0) * ipz2fx;
+        J0[1] = (px * w9 - pz * w1) * ipz2fx;
+        J0[2] = (px * w10 - pz * w2) * ipz2fx;
+        J1[0] = (py * w8 - pz * w4) * ipz2fy;
+        J1[1] = (py * w9 - pz * w5) * ipz2fy;
+        J1[2] = (py * w10 - pz * w6) * ipz2fy;
         // dRd{x,y,z} * (p - t), with dRidx = [0 0 0; 0 0 2; 0 -2 0] etc. applied to R^T
-        const double r0 = c.w2n[0] * pw[0] + c.w2n[1] * pw[1] + c.w2n[2] * pw[2];
-        const double r1 = c.w2n[4] * pw[0] + c.w2n[5] * pw[1] + c.w2n[6] * pw[2];
-        const double r2 = c.w2n[8] * pw[0] + c.w2n[9] * pw[1] + c.w2n[10] * pw[2];
+        const double r0 = fma(w0, pw0, fma(w1, pw1, w2 * pw2));
+        const double r1 = fma(w4, pw0, fma(w5, pw1, w6 * pw2));
+        const double r2 = fma(w8, pw0, fma(w9, pw1, w10 * pw2));
         const double q[3][3] = {{0.0, 2 * r2, -2 * r1}, {-2 * r2, 0.0, 2 * r0}, {2 * r1, -2 * r0, 0.0}};
 #pragma unroll
         for (int k = 0; k < 3; k++)
@@ -230,49 +240,85 @@ __device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, const doub
 #pragma unroll
         for (int a = 0; a < 6; a++)
         {
+            const double J0w = J0[a] * w, J1w = J1[a] * w;
 #pragma unroll
             for (int bcol = a; bcol < 6; bcol++)
-                acc[idx++] += (J0[a] * J0[bcol] + J1[a] * J1[bcol]) * w;
+            {
+                acc[idx] = fma(J0w, J0[bcol], fma(J1w, J1[bcol], acc[idx]));
+                idx++;
+            }
         }
 #pragma unroll
         for (int a = 0; a < 6; a++)
-            acc[21 + a] += J0[a] * g0 + J1[a] * g1;
+            acc[21 + a] = fma(J0[a], g0, fma(J1[a], g1, acc[21 + a]));
+        return chi;
+    };
+#pragma unroll
+    for (int k = 0; k < kPoseCached; k++)
+        if (edge[k].level == 0)
+            edge[k].e2 = one_edge(edge[k].X, edge[k].Y, edge[k].Z, edge[k].zx, edge[k].zy);
+    for (int i = (kPoseCached * nranks + rank) * (int)blockDim.x + (int)threadIdx.x; i < m; i += nranks * (int)blockDim.x)
+    {
+        if (level[i])
+            continue;
+        const float2 z = uv[i];
+        e2[i] = one_edge(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], (double)z.x, (double)z.y);
     }
-    // fixed-order reduction through shared memory: thread -> 32-entry slices -> CTA -> cluster (DSMEM)
     LVT_PDBG(1);
+    // CTA: every thread parks its sums in shared memory (row k = sum k), then all 256 threads add
+    // them up -- thread t takes row t / 8, columns (t % 8) * 32 .. + 32 in four independent chains,
+    // and the 8 threads of a row meet in three shuffle steps.  Cluster: the row leaders push the CTA's
+    // sums into every CTA's gather[parity][rank] (DSMEM stores); one cluster barrier; local reads.
     const int slot = threadIdx.x + (threadIdx.x >> 5);
 #pragma unroll
     for (int k = 0; k < kPoseSums; k++)
         s.acc[k][slot] = acc[k];
     __syncthreads();
-    constexpr int kSlices = kPoseThreads / 32;
-    if (threadIdx.x < kPoseSums * kSlices)
     {
+        constexpr int kSlices = kPoseThreads / 32; // 8
         const int k = threadIdx.x / kSlices, w = threadIdx.x % kSlices;
-        const double *src = &s.acc[k][w * 33];
         double v = 0.0;
-#pragma unroll 8
-        for (int j = 0; j < 32; j++)
-            v += src[j];
-        s.part[k][w] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kPoseSums)
-    {
-        double v = 0.0;
+        if (k < kPoseSums)
+        {
+            const double *src = &s.acc[k][w * 33];
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
-        for (int w = 0; w < kSlices; w++)
-            v += s.part[threadIdx.x][w];
-        s.cta_sums[parity][threadIdx.x] = v;
+            for (int j = 0; j < 32; j += 4)
+            {
+                c0 += src[j];
+                c1 += src[j + 1];
+                c2 += src[j + 2];
+                c3 += src[j + 3];
+            }
+            v = (c0 + c1) + (c2 + c3);
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (w == 0 && k < kPoseSums)
+        {
+            if (nranks == 1)
+                s.sums[k] = v;
+            else
+                for (int r = 0; r < nranks; r++)
+                    *cluster.map_shared_rank(&s.gather[parity][rank][k], r) = v;
+        }
     }
     LVT_PDBG(2);
+    if (nranks == 1)
+    {
+        __syncthreads();
+        LVT_PDBG(3);
+        LVT_PDBG(4);
+        return;
+    }
     cluster.sync();
     LVT_PDBG(3);
     if (threadIdx.x < kPoseSums)
     {
         double v = 0.0;
         for (int r = 0; r < nranks; r++)
-            v += *cluster.map_shared_rank(&s.cta_sums[parity][threadIdx.x], r);
+            v += s.gather[parity][r][threadIdx.x];
         s.sums[threadIdx.x] = v;
     }
     __syncthreads();
@@ -311,7 +357,25 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
         c.r = quat_normalized(q);
         cam_refresh(c);
     }
-    for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
+    PoseEdge edge[kPoseCached];
+#pragma unroll
+    for (int k = 0; k < kPoseCached; k++)
+    {
+        const int i = (k * nranks + rank) * (int)blockDim.x + (int)threadIdx.x;
+        edge[k].level = -1;
+        edge[k].e2 = 0.0;
+        if (i < m)
+        {
+            const float2 z = uv[i];
+            edge[k].X = xyz[3 * i];
+            edge[k].Y = xyz[3 * i + 1];
+            edge[k].Z = xyz[3 * i + 2];
+            edge[k].zx = (double)z.x;
+            edge[k].zy = (double)z.y;
+            edge[k].level = 0;
+        }
+    }
+    for (int i = (kPoseCached * nranks + rank) * (int)blockDim.x + (int)threadIdx.x; i < m; i += nranks * (int)blockDim.x)
     {
         level[i] = 0;
         inlier[i] = 1;
@@ -321,31 +385,34 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
 
     // LM state of rank 0 / thread 0 (OptimizationAlgorithmLevenberg::solve)
     double lambda = 0, ni = 2, current_chi = 0, rho = 0;
-    double H[36], bvec[6], x[6];
-    CamState backup;
     int qmax = 0, it = 0;
     const bool boss = threadIdx.x == 0; // in every CTA
     int parity = 0;
     auto load_system = [&]() {
-        int idx = 0;
 #pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int bcol = a; bcol < 6; bcol++)
-            {
-                H[6 * a + bcol] = s.sums[idx];
-                H[6 * bcol + a] = s.sums[idx];
-                idx++;
-            }
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-            bvec[a] = s.sums[21 + a];
+        for (int k = 0; k < 27; k++)
+            s.sys[k] = s.sums[k];
     };
     // one block-Jacobi preconditioned CG step on the single 6x6 block (LinearSolverPCG):
     // d = (H + lambda I)^-1 b, x = (b.d / d.Ad) d; then SBACam::update
     auto propose = [&]() {
-        backup = s.cam;
-        double d[6];
+        s.backup = s.cam;
+        double H[36], bvec[6], d[6], x[6];
+        {
+            int idx = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int bcol = a; bcol < 6; bcol++)
+                {
+                    const double v = s.sys[idx++];
+                    H[6 * a + bcol] = v;
+                    H[6 * bcol + a] = v;
+                }
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+                bvec[a] = s.sys[21 + a];
+        }
 #pragma unroll
         for (int j = 0; j < 6; j++)
             x[j] = 0.0;
@@ -367,13 +434,16 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
             for (int i = 0; i < 6; i++)
                 x[i] = d[i];
         }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            s.x[i] = x[i];
         cam_update(s.cam, x);
     };
 
     for (int pass = 0; pass < 2; pass++)
     {
         // errors + linearisation at the starting state of this optimize()
-        pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks, parity);
+        pose_evaluate(cluster, s, edge, xyz, uv, level, e2, m, rank, nranks, parity);
         parity ^= 1;
         if (boss)
         {
@@ -384,8 +454,13 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                 current_chi = s.sums[27];
                 load_system();
                 double max_diag = 0;
-                for (int j = 0; j < 6; j++)
-                    max_diag = fmax(fabs(H[7 * j]), max_diag);
+                {
+                    // diagonal of H inside the packed upper triangle: 0, 6, 11, 15, 18, 20
+                    const int diag[6] = {0, 6, 11, 15, 18, 20};
+#pragma unroll
+                    for (int j = 0; j < 6; j++)
+                        max_diag = fmax(fabs(s.sys[diag[j]]), max_diag);
+                }
                 lambda = 1e-5 * max_diag; // computeLambdaInit, _tau = 1e-5
                 ni = 2;
                 it = 0;
@@ -400,7 +475,7 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
             __syncthreads();
             if (s.cont != 0)
                 break;
-            pose_evaluate(cluster, s, xyz, uv, level, e2, m, rank, nranks, parity, dbg); // the trial state
+            pose_evaluate(cluster, s, edge, xyz, uv, level, e2, m, rank, nranks, parity, dbg); // the trial state
             parity ^= 1;
             if (boss)
             {
@@ -408,7 +483,7 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                 double scale = 0;
 #pragma unroll
                 for (int j = 0; j < 6; j++)
-                    scale += x[j] * (lambda * x[j] + bvec[j]);
+                    scale += s.x[j] * (lambda * s.x[j] + s.sys[21 + j]);
                 scale += 1e-3;
                 rho = (current_chi - temp_chi) / scale;
                 if (rho > 0 && isfinite(temp_chi))
@@ -425,7 +500,7 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                 {
                     lambda *= ni;
                     ni *= 2;
-                    s.cam = backup; // the edges keep the rejected trial's error
+                    s.cam = s.backup; // the edges keep the rejected trial's error
                 }
                 qmax++;
                 if (rho < 0 && qmax < 10)
@@ -448,7 +523,11 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
             }
         }
         // lvt_pnp_solver.cpp:109-116
-        for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < kPoseCached; k++)
+            if (edge[k].level == 0 && edge[k].e2 > kReprojectionTh2)
+                edge[k].level = 1;
+        for (int i = (kPoseCached * nranks + rank) * (int)blockDim.x + (int)threadIdx.x; i < m; i += nranks * (int)blockDim.x)
         {
             if (e2[i] > kReprojectionTh2)
             {
@@ -458,29 +537,44 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
         }
         __syncthreads();
     }
+    // the register-resident edges report their marks (and last errors) once
+#pragma unroll
+    for (int k = 0; k < kPoseCached; k++)
+    {
+        const int i = (k * nranks + rank) * (int)blockDim.x + (int)threadIdx.x;
+        if (i < m)
+        {
+            level[i] = (uint8_t)edge[k].level;
+            inlier[i] = edge[k].level == 0;
+            e2[i] = edge[k].e2;
+        }
+    }
     // inlier count: CTA sums exchanged through DSMEM
     {
         double cnt = 0;
-        for (int i = rank * blockDim.x + threadIdx.x; i < m; i += nranks * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < kPoseCached; k++)
+            cnt += edge[k].level == 0;
+        for (int i = (kPoseCached * nranks + rank) * (int)blockDim.x + (int)threadIdx.x; i < m; i += nranks * (int)blockDim.x)
             cnt += inlier[i];
         cnt = warp_sum(cnt);
         __syncthreads();
         if ((threadIdx.x & 31) == 0)
-            s.part[0][threadIdx.x >> 5] = cnt;
+            s.part[threadIdx.x >> 5] = cnt;
         __syncthreads();
         if (threadIdx.x == 0)
         {
             double v = 0;
             for (int w = 0; w < (int)(blockDim.x >> 5); w++)
-                v += s.part[0][w];
-            s.cta_sums[parity][0] = v;
+                v += s.part[w];
+            *cluster.map_shared_rank(&s.gather[parity][rank][0], 0) = v;
         }
         cluster.sync();
         if (rank == 0 && threadIdx.x == 0)
         {
             double v = 0;
             for (int r = 0; r < nranks; r++)
-                v += *cluster.map_shared_rank(&s.cta_sums[parity][0], r);
+                v += s.gather[parity][r][0];
             *n_inliers_out = (int)v;
             pose_out->q = s.cam.r;
             pose_out->t[0] = s.cam.t[0];
