@@ -128,6 +128,25 @@ LVT_API int lvt_debug_get_points(lvt_handle vo_system, int which, double *xyz, u
  * generated_32.i.  NULL restores the built-in table.  Returns 0 on success. */
 LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4]);
 
+/* ---- in-pipeline stereo rectification (new) ---------------------------
+ * The EuRoC driver rectifies every raw frame on the CPU before tracking it:
+ * cv::initUndistortRectifyMap(K, D, R, P(0:3,0:3), size, CV_32F, M1, M2) once per camera
+ * (examples/euroc/euroc_example.cpp:96-107) and cv::remap(raw, rect, M1, M2, cv::INTER_LINEAR) per
+ * frame and camera (:142-143).  After lvt_set_rectification the images handed to lvt_track /
+ * lvt_pool_upload are the RAW camera images: they are rectified on the way in (same arithmetic:
+ * float maps from fp64 pinhole + radial-tangential math, 1/32-pixel fixed-point bilinear taps with
+ * 15-bit weights, constant 0 outside the image) and tracking sees the rectified pair.
+ * K, R, P: row-major 3x3 (P = the left 3x3 block of the projection matrix); D = k1 k2 p1 p2 k3.
+ * Passing NULL for both cameras switches rectification off.  Returns 0 on success. */
+typedef struct lvt_rectify_c
+{
+    double K[9];
+    double D[5];
+    double R[9];
+    double P[9];
+} lvt_rectify_c;
+LVT_API int lvt_set_rectification(lvt_handle vo_system, const lvt_rectify_c *left, const lvt_rectify_c *right);
+
 /* ---- resident-frame streaming (new; throughput path) -------------------------------------
  * The reference processes one frame per call and blocks (lvt/src/lvt_c.cpp:63-88).  When the
  * frames are already in device memory the same per-frame pipeline can run back to back with the

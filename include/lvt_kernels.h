@@ -97,6 +97,17 @@ LVT_API int lvtk_solve_pose(lvtk_ctx *ctx, const double *pts_xyz, const float *u
 LVT_API int lvtk_triangulate(lvtk_ctx *ctx, const double q_wxyz[4], const double t[3], const float *uv_left,
                              const float *uv_right, int n, double *out_xyz, uint8_t *out_valid);
 
+/* cv::initUndistortRectifyMap(K, D, R, P, (cols, rows), CV_32F, map_x, map_y)
+ * (examples/euroc/euroc_example.cpp:106-107): for every rectified pixel the raw-image position it
+ * is sampled from.  map_x / map_y: rows x cols float, tightly packed. */
+LVT_API int lvtk_rectify_maps(lvtk_ctx *ctx, const lvt_rectify_c *r, int rows, int cols, float *map_x, float *map_y);
+
+/* cv::remap(raw, out, map_x, map_y, cv::INTER_LINEAR) with the maps of lvtk_rectify_maps
+ * (examples/euroc/euroc_example.cpp:142-143); the maps are never materialised.  out: rows x cols,
+ * tightly packed. */
+LVT_API int lvtk_rectify(lvtk_ctx *ctx, const uint8_t *raw, int rows, int cols, int stride, const lvt_rectify_c *r,
+                         uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

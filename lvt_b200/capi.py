@@ -70,6 +70,22 @@ class FrameInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Rectify(C.Structure):
+    """lvt_rectify_c: one camera's arguments of cv::initUndistortRectifyMap
+    (examples/euroc/euroc_example.cpp:96-107): K, D = k1 k2 p1 p2 k3, R, P(0:3,0:3), row-major."""
+
+    _fields_ = [("K", C.c_double * 9), ("D", C.c_double * 5), ("R", C.c_double * 9), ("P", C.c_double * 9)]
+
+    @classmethod
+    def make(cls, K, D, R, P):
+        r = cls()
+        r.K[:] = [float(v) for v in np.asarray(K, np.float64).reshape(9)]
+        r.D[:] = [float(v) for v in np.asarray(D, np.float64).reshape(5)]
+        r.R[:] = [float(v) for v in np.asarray(R, np.float64).reshape(9)]
+        r.P[:] = [float(v) for v in np.asarray(P, np.float64)[:3, :3].reshape(9)]
+        return r
+
+
 KP_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("response", np.float32)])
 
 STATE_NOT_INITIALIZED, STATE_TRACKING, STATE_LOST = 1, 2, 3
@@ -133,6 +149,10 @@ class Library:
                                        c_i32p, c_i32p, c_i32p]
         lib.lvtk_solve_pose.argtypes = [vp, c_f64p, c_f32p, C.c_int, c_f64p, c_f64p, c_f64p, c_f64p, c_u8p]
         lib.lvtk_triangulate.argtypes = [vp, c_f64p, c_f64p, c_f32p, c_f32p, C.c_int, c_f64p, c_u8p]
+        lib.lvt_set_rectification.argtypes = [vp, C.POINTER(Rectify), C.POINTER(Rectify)]
+        lib.lvt_set_rectification.restype = C.c_int
+        lib.lvtk_rectify_maps.argtypes = [vp, C.POINTER(Rectify), C.c_int, C.c_int, c_f32p, c_f32p]
+        lib.lvtk_rectify.argtypes = [vp, c_u8p, C.c_int, C.c_int, C.c_int, C.POINTER(Rectify), c_u8p]
         lib.lvt_pool_reserve.argtypes = [vp, C.c_int]
         lib.lvt_pool_upload.argtypes = [vp, C.c_int, c_u8p, c_u8p]
         lib.lvt_track_pool.argtypes = [vp, C.c_int, C.c_int, c_f64p, C.POINTER(FrameInfo)]
@@ -268,6 +288,11 @@ class System:
                                                  _ptr(self._R, c_f64p), _ptr(self._t, c_f64p))
         return self._pose_out()
 
+    def set_rectification(self, left=None, right=None):
+        """left / right: Rectify (raw images are rectified on the way in) or None, None (off)."""
+        _check(self.lib.lvt_set_rectification(self.h, C.byref(left) if left is not None else None,
+                                              C.byref(right) if right is not None else None), "lvt_set_rectification")
+
     def pool_reserve(self, n_frames):
         _check(self.lib.lvt_pool_reserve(self.h, n_frames), "lvt_pool_reserve")
 
@@ -344,6 +369,19 @@ class Context:
         img = np.asarray(img)
         assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
         return img, img.shape[0], img.shape[1], img.strides[0]
+
+    def rectify_maps(self, rect, rows, cols):
+        mx = np.zeros((rows, cols), np.float32)
+        my = np.zeros((rows, cols), np.float32)
+        _check(self.lib.lvtk_rectify_maps(self.h, C.byref(rect), rows, cols, _ptr(mx, c_f32p), _ptr(my, c_f32p)),
+               "lvtk_rectify_maps")
+        return mx, my
+
+    def rectify(self, img, rect):
+        img, rows, cols, stride = self._img(img)
+        out = np.zeros((rows, cols), np.uint8)
+        _check(self.lib.lvtk_rectify(self.h, _u8(img), rows, cols, stride, C.byref(rect), _u8(out)), "lvtk_rectify")
+        return out
 
     def agast(self, img, threshold, nonmax=True, cap=None):
         img, rows, cols, stride = self._img(img)

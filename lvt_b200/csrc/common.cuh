@@ -41,6 +41,7 @@ enum KernelId
     K_POSE,
     K_STAGEDCAND,
     K_TRACK_B,
+    K_RECTIFY,
     K_COUNT
 };
 bool prof_enabled();

@@ -403,6 +403,11 @@ struct lvtk_ctx
     cudaEvent_t ev_pose = nullptr;      // h_early is valid
     cudaEvent_t ev_frame = nullptr;     // the whole frame (map maintenance, h_result, h_error) is through
     int parity = 0;                     // blocking stereo frames alternate between two sets of buffers
+    // lvt_set_rectification: the images of lvt_track / lvt_pool_upload are raw; they land in `raw`
+    // (same geometry as the pool) and rectify_kernel writes the pool slot
+    bool rectify = false;
+    RectifyDev rect[2];
+    uint8_t *raw = nullptr;
     cudaEvent_t ev_tl[4] = {};          // LVT_B200_TIMELINE: call start, left image in HBM, left features, pose
     double tl_ms[3] = {0, 0, 0};
     long tl_n = 0;
@@ -484,6 +489,8 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming));
 
     if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
+        return rc;
+    if (int rc = c->arena.alloc(&c->raw, c->pool.slot_bytes() * n_slots))
         return rc;
     c->dp.grid = make_tile_grid(p.img_width, p.img_height, p.detection_cell_size);
     c->dp.threshold = p.agast_threshold;
@@ -657,11 +664,20 @@ static void ctx_free(lvtk_ctx *c)
 
 // host image (any stride) -> pinned staging -> pitched pool slot, in row bands (upload.cuh);
 // ctx_stage_image queues an image, ctx_stage_flush stages and enqueues everything queued
-static void ctx_stage_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows, int cols, int stride)
+static void ctx_stage_image(lvtk_ctx *c, int slot, const uint8_t *img, int rows, int cols, int stride, bool to_raw = false)
 {
     c->lanes.add_image(img, (size_t)stride, c->h_stage + (size_t)slot * rows * c->pool.pitch,
-                       c->pool.data + c->pool.slot_bytes() * slot, c->pool.pitch, (size_t)cols, rows, c->upload_bands,
-                       c->upload_dmas);
+                       (to_raw ? c->raw : c->pool.data) + c->pool.slot_bytes() * slot, c->pool.pitch, (size_t)cols, rows,
+                       c->upload_bands, c->upload_dmas);
+}
+
+// raw image in c->raw[slot] -> rectified image in the pool slot, as camera `cam` sees it
+static int ctx_rectify_slot(lvtk_ctx *c, int slot, int cam, cudaStream_t stream)
+{
+    const uint8_t *raw[2] = {c->raw + c->pool.slot_bytes() * slot, nullptr};
+    uint8_t *dst[2] = {c->pool.data + c->pool.slot_bytes() * slot, nullptr};
+    const RectifyDev *cams[2] = {&c->rect[cam], nullptr};
+    return launch_rectify(raw, dst, 1, cams, c->pool, stream);
 }
 
 static int ctx_stage_flush(lvtk_ctx *c, cudaStream_t stream = nullptr)
@@ -891,11 +907,14 @@ struct System
                     cudaEventCreate(&c->ev_tl[k]);
             cudaEventRecord(c->ev_tl[0], xl);
         }
-        ctx_stage_image(c, 2 * s, left, rows, cols, cols);
+        ctx_stage_image(c, 2 * s, left, rows, cols, cols, c->rectify);
         if (int rc = ctx_stage_flush(c, xl))
             return rc;
         if (timeline)
             cudaEventRecord(c->ev_tl[1], xl);
+        if (c->rectify)
+            if (int rc = ctx_rectify_slot(c, 2 * s, 0, xl))
+                return rc;
         if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, slots, 1, feats, kBriefBorder, 1, xl))
             return rc;
         const bool fused_index = brief_can_index(c->cam);
@@ -914,9 +933,12 @@ struct System
         LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
         if (timeline)
             cudaEventRecord(c->ev_tl[3], st);
-        ctx_stage_image(c, 2 * s + 1, right, rows, cols, cols);
+        ctx_stage_image(c, 2 * s + 1, right, rows, cols, cols, c->rectify);
         if (int rc = ctx_stage_flush(c, xr))
             return rc;
+        if (c->rectify)
+            if (int rc = ctx_rectify_slot(c, 2 * s + 1, 1, xr))
+                return rc;
         host_mark(1);
         if (int rc = launch_detect(c->pool, c->wsx[1], c->dp, slots + 1, 1, feats + 1, kBriefBorder, 1, xr))
             return rc;
@@ -1078,9 +1100,24 @@ struct System
             return LVTK_ERR_ARG;
         const int per = sensor == 1 ? 2 : 1, rows = c->params.img_height, cols = c->params.img_width;
         const uint8_t *src[2] = {left, right};
+        if (int rc = finish_pending())
+            return rc;
         for (int k = 0; k < per; k++)
-            LVT_CUDA_TRY(cudaMemcpy2DAsync(c->rpool.data + c->rpool.slot_bytes() * (size_t)(per * frame + k), c->rpool.pitch,
-                                           src[k], cols, cols, rows, cudaMemcpyHostToDevice, c->stream));
+        {
+            uint8_t *slot = c->rpool.data + c->rpool.slot_bytes() * (size_t)(per * frame + k);
+            uint8_t *dst = c->rectify && sensor == 1 ? c->raw + c->pool.slot_bytes() * k : slot;
+            LVT_CUDA_TRY(cudaMemcpy2DAsync(dst, c->rpool.pitch, src[k], cols, cols, rows, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (c->rectify && sensor == 1)
+        {
+            // raw frames are rectified once, on their way into the resident pool
+            const uint8_t *raw[2] = {c->raw, c->raw + c->pool.slot_bytes()};
+            uint8_t *dst[2] = {c->rpool.data + c->rpool.slot_bytes() * (size_t)(2 * frame),
+                               c->rpool.data + c->rpool.slot_bytes() * (size_t)(2 * frame + 1)};
+            const RectifyDev *cams[2] = {&c->rect[0], &c->rect[1]};
+            if (int rc = launch_rectify(raw, dst, 2, cams, c->rpool, c->stream))
+                return rc;
+        }
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
         return LVTK_OK;
     }
@@ -1391,6 +1428,27 @@ LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
 
 LVT_API const char *lvtk_last_error(void) { return last_error(); }
 
+LVT_API int lvt_set_rectification(lvt_handle h, const lvt_rectify_c *left, const lvt_rectify_c *right)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || (left == nullptr) != (right == nullptr))
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    vo->finish_pending();
+    lvtk_ctx *c = vo->ctx;
+    c->rectify = false;
+    if (left)
+    {
+        RectifyDev l, r;
+        if (make_rectify_dev(*left, &l) != LVTK_OK || make_rectify_dev(*right, &r) != LVTK_OK)
+            return LVTK_ERR_ARG;
+        c->rect[0] = l;
+        c->rect[1] = r;
+        c->rectify = true;
+    }
+    return LVTK_OK;
+}
+
 LVT_API int lvt_pool_reserve(lvt_handle h, int n_frames)
 {
     System *vo = static_cast<System *>(h);
@@ -1482,7 +1540,8 @@ LVT_API const char *lvt_kernel_name(int id)
 {
     static const char *names[K_COUNT] = {"score_kernel",   "nms_tile_kernel", "tile_kernel",    "gather_kernel",
                                          "brief_kernel",   "index_kernel",    "track_a_kernel", "mapcand_kernel",
-                                         "rowcand_kernel", "pose_kernel",     "stagedcand_kernel", "track_b_kernel"};
+                                         "rowcand_kernel", "pose_kernel",     "stagedcand_kernel", "track_b_kernel",
+                                         "rectify_kernel"};
     return id >= 0 && id < K_COUNT ? names[id] : "";
 }
 
@@ -1724,6 +1783,44 @@ LVT_API int lvtk_solve_pose(lvtk_ctx *c, const double *pts_xyz, const float *uv,
     t_out[0] = out.t[0];
     t_out[1] = out.t[1];
     t_out[2] = out.t[2];
+    return LVTK_OK;
+}
+
+LVT_API int lvtk_rectify_maps(lvtk_ctx *c, const lvt_rectify_c *r, int rows, int cols, float *map_x, float *map_y)
+{
+    if (!c || !r || !map_x || !map_y || rows <= 0 || cols <= 0)
+        return LVTK_ERR_ARG;
+    LVT_CUDA_TRY(cudaSetDevice(c->device));
+    RectifyDev dev;
+    if (int rc = make_rectify_dev(*r, &dev))
+        return rc;
+    float *d_maps = nullptr;
+    const size_t n = (size_t)rows * cols;
+    LVT_CUDA_TRY(cudaMalloc(&d_maps, 2 * n * sizeof(float)));
+    int rc = launch_rectify_maps(dev, rows, cols, d_maps, d_maps + n, c->stream);
+    if (rc == LVTK_OK && (cudaMemcpyAsync(map_x, d_maps, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                          cudaMemcpyAsync(map_y, d_maps + n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(c->stream) != cudaSuccess))
+        rc = LVTK_ERR_CUDA;
+    cudaFree(d_maps);
+    return rc;
+}
+
+LVT_API int lvtk_rectify(lvtk_ctx *c, const uint8_t *raw, int rows, int cols, int stride, const lvt_rectify_c *r,
+                         uint8_t *out)
+{
+    if (!c || !raw || !r || !out || rows != c->params.img_height || cols != c->params.img_width || stride < cols)
+        return LVTK_ERR_ARG;
+    LVT_CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = make_rectify_dev(*r, &c->rect[0]))
+        return rc;
+    ctx_stage_image(c, 0, raw, rows, cols, stride, true);
+    if (int rc = ctx_stage_flush(c))
+        return rc;
+    if (int rc = ctx_rectify_slot(c, 0, 0, c->stream))
+        return rc;
+    LVT_CUDA_TRY(cudaMemcpy2DAsync(out, cols, c->pool.data, c->pool.pitch, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return LVTK_OK;
 }
 

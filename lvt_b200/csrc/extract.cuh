@@ -19,6 +19,18 @@ struct ImagePool
     size_t slot_bytes() const { return (size_t)pitch * rows; }
 };
 
+// one camera of lvt_set_rectification, ready for the device: (P R)^-1, raw pinhole, distortion
+struct RectifyDev
+{
+    double ir[9];
+    double fx, fy, cx, cy, k1, k2, p1, p2, k3;
+};
+int make_rectify_dev(const lvt_rectify_c &r, RectifyDev *out);
+// n_images (1 or 2) raw images, pitched like the pool -> their pool slots; image i is seen by *cam[i]
+int launch_rectify(const uint8_t *const raw[2], uint8_t *const dst[2], int n_images, const RectifyDev *const cam[2],
+                   const ImagePool &pool, cudaStream_t stream);
+int launch_rectify_maps(const RectifyDev &r, int rows, int cols, float *d_map_x, float *d_map_y, cudaStream_t stream);
+
 constexpr int kScoreTileW = 64, kScoreTileH = 32;
 constexpr int kScoreBoxW = 96, kScoreBoxH = kScoreTileH + 6, kScoreBoxX = 16;
 constexpr int kPatchW = 80, kPatchH = 57;

@@ -32,6 +32,9 @@ struct System
     std::deque<int> last_matches;
     lvt_frame_info info;
     FeatureSet left, right; /* kept after the call for the debug getters */
+    bool rectify = false;   /* lvt_set_rectification: the images of lvt_track are raw */
+    lvt_rectify_c rect[2];
+    std::vector<uint8_t> rect_buf[2];
 
     explicit System(const lvt_params_c &p, int sensor_type) : params(p), sensor(sensor_type)
     {
@@ -331,7 +334,19 @@ LVT_API void lvt_track(lvt_handle h, unsigned char *left, unsigned char *right, 
     try
     {
         System *vo = static_cast<System *>(h);
-        const Image l{left, n_rows, n_cols, n_cols}, r{right, n_rows, n_cols, n_cols};
+        Image l{left, n_rows, n_cols, n_cols}, r{right, n_rows, n_cols, n_cols};
+        if (vo->rectify)
+        {
+            /* examples/euroc/euroc_example.cpp:142-143 */
+            const unsigned char *raw[2] = {left, right};
+            for (int k = 0; k < 2; k++)
+            {
+                vo->rect_buf[k].resize((size_t)n_rows * n_cols);
+                rectify_image(vo->rect[k], raw[k], n_rows, n_cols, n_cols, vo->rect_buf[k].data());
+            }
+            l.data = vo->rect_buf[0].data();
+            r.data = vo->rect_buf[1].data();
+        }
         write_pose(vo->track(l, r, nullptr), R, t);
     }
     catch (...)
@@ -465,6 +480,26 @@ LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
     return 0;
 }
 
+LVT_API int lvt_set_rectification(lvt_handle h, const lvt_rectify_c *left, const lvt_rectify_c *right)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || (left == nullptr) != (right == nullptr))
+        return -1;
+    vo->rectify = left != nullptr;
+    if (left)
+    {
+        double ir[9];
+        if (!rectify_inverse(*left, ir) || !rectify_inverse(*right, ir))
+        {
+            vo->rectify = false;
+            return -1;
+        }
+        vo->rect[0] = *left;
+        vo->rect[1] = *right;
+    }
+    return 0;
+}
+
 /* resident-frame streaming: the oracle keeps the "pool" in host memory and runs lvt_track per frame */
 LVT_API int lvt_pool_reserve(lvt_handle h, int n_frames)
 {
@@ -495,9 +530,8 @@ LVT_API int lvt_track_pool(lvt_handle h, int first, int n, double *poses, lvt_fr
     for (int i = 0; i < n; i++)
     {
         double R[3][3], t[3];
-        const Image l{it->second.left[first + i].data(), vo->params.img_height, vo->params.img_width, vo->params.img_width};
-        const Image r{it->second.right[first + i].data(), vo->params.img_height, vo->params.img_width, vo->params.img_width};
-        write_pose(vo->track(l, r, nullptr), R, t);
+        lvt_track(h, it->second.left[first + i].data(), it->second.right[first + i].data(), vo->params.img_height,
+                  vo->params.img_width, R, t); /* rectifies first when lvt_set_rectification is on */
         if (poses)
         {
             std::memcpy(poses + 12 * (size_t)i, R, sizeof(R));
@@ -725,6 +759,23 @@ LVT_API int lvtk_solve_pose(lvtk_ctx *ctx, const double *pts_xyz, const float *u
     t_out[2] = out.p.z;
     if (inlier_marks && m)
         std::memcpy(inlier_marks, marks.data(), m);
+    return LVTK_OK;
+}
+
+LVT_API int lvtk_rectify_maps(lvtk_ctx *ctx, const lvt_rectify_c *r, int rows, int cols, float *map_x, float *map_y)
+{
+    if (!ctx || !r || !map_x || !map_y || rows <= 0 || cols <= 0)
+        return LVTK_ERR_ARG;
+    rectify_maps(*r, rows, cols, map_x, map_y);
+    return LVTK_OK;
+}
+
+LVT_API int lvtk_rectify(lvtk_ctx *ctx, const uint8_t *raw, int rows, int cols, int stride, const lvt_rectify_c *r,
+                         uint8_t *out)
+{
+    if (!ctx || !raw || !r || !out || rows <= 0 || cols <= 0 || stride < cols)
+        return LVTK_ERR_ARG;
+    rectify_image(*r, raw, rows, cols, stride, out);
     return LVTK_OK;
 }
 

@@ -229,6 +229,11 @@ struct MotionModel
 };
 
 /* ---- params --------------------------------------------------------------------------- */
+/* ---- stereo rectification (rectify.cpp; examples/euroc/euroc_example.cpp:106-107,142-143) */
+bool rectify_inverse(const lvt_rectify_c &r, double ir[9]);
+void rectify_maps(const lvt_rectify_c &r, int rows, int cols, float *map_x, float *map_y);
+void rectify_image(const lvt_rectify_c &r, const uint8_t *raw, int rows, int cols, int stride, uint8_t *out);
+
 void params_default(lvt_params_c *p);
 int params_from_file(lvt_params_c *p, const char *file);
 
