@@ -37,6 +37,16 @@ METRIC = "stereo frames/sec at 1242x375"
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liblvt_oracle.so")
 
 
+def load_traffic():
+    """DRAM bytes (read + write) per launch from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by tools/summarize_profiles.py); {} when absent"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return {}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -252,9 +262,10 @@ def run_b200(args):
     # algorithmic bytes per launch; a launch covers the stereo pair
     alg = {
         "score_kernel": 2 * W * H,
-        "nms_kernel": 2 * W * H,
+        "nms_tile_kernel": 2 * W * H,
         "tile_kernel": 12 * 2 * 3900 + 12 * (n_l + n_r) / 0.8,
-        "brief_kernel": 8 * (n_l + n_r) + 32 * (n_l + n_r) + 57 * 57 * (n_l + n_r),
+        # descriptors + the feature index its extra CTA builds (positions in, two CSRs out)
+        "brief_kernel": 8 * (n_l + n_r) + 32 * (n_l + n_r) + 57 * 57 * (n_l + n_r) + 2 * 8 * (n_l + n_r) + 2 * 4 * (n_l + n_r),
         "index_kernel": 2 * 8 * (n_l + n_r) + 2 * 4 * (n_l + n_r),
         "mapcand_kernel": 32 * (m_map + n_l) + 8 * n_l + 24 * m_map + 12 * m_map,
         "rowcand_kernel": 2 * (32 + 8) * n_l,
@@ -271,14 +282,17 @@ def run_b200(args):
         v["share"] = v["share"] / tot
     dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["share"] * tot, default=None)
     roofline = None
+    traffic = load_traffic()
     if dom:
         achieved = alg[dom] / (per_kernel[dom]["avg_us"] * 1e-6) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                    "traffic": traffic.get(dom), "traffic_source": "profiles/traffic.json (ncu --set full, dram read + write per launch)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                     "avg_launch_us": per_kernel[dom]["avg_us"],
                     "note": "latency/ALU-bound at one stereo pair per launch (1.45 MB of traffic per frame); see DESIGN.md",
                     "per_kernel": {k: {"avg_us": round(v["avg_us"], 2), "share": round(v["share"], 4),
-                                       "GBps": round(alg[k] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None}
+                                       "GBps": round(alg[k] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None,
+                                       "traffic": traffic.get(k)}
                                    for k, v in per_kernel.items()}}
 
     # ---------------- e2e: lvt_track with host buffers, H2D + D2H inside the timed region -----------

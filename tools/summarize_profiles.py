@@ -55,27 +55,35 @@ def launches(tag):
     return "\n".join(out) + "\n"
 
 
-def full(rep):
+def full(rep, seen, traffic_out):
+    """every kernel of a report once (first launch captured): the judged metrics + DRAM traffic"""
     r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
     rows = list(csv.reader(io.StringIO(r.stdout)))
     if len(rows) < 3:
         return None
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-    name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
-    out = ["## %s  (%s)" % (name, os.path.basename(rep)), "", "| metric | value | unit |", "|---|---:|---|"]
-    for k in KEYS:
-        if k in d:
-            out.append("| %s | %s | %s |" % (k, d[k][0], d[k][1]))
-    try:
-        rd = float(d["dram__bytes_read.sum"][0].replace(",", ""))
-        wr = float(d["dram__bytes_write.sum"][0].replace(",", ""))
-        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = rd * mult.get(d["dram__bytes_read.sum"][1], 1) + wr * mult.get(d["dram__bytes_write.sum"][1], 1)
-        out.append("| **traffic = dram read + write** | %.0f | byte |" % traffic)
-    except Exception:
-        pass
-    return "\n".join(out) + "\n"
+    hdr, units = rows[0], rows[1]
+    parts = []
+    for vals in rows[2:]:
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        name = d.get("Kernel Name", ("?", ""))[0].split("(")[0].replace("lvtb::", "")
+        if name in seen:
+            continue
+        seen.add(name)
+        out = ["## %s  (%s)" % (name, os.path.basename(rep)), "", "| metric | value | unit |", "|---|---:|---|"]
+        for k in KEYS:
+            if k in d:
+                out.append("| %s | %s | %s |" % (k, d[k][0], d[k][1]))
+        try:
+            rd = float(d["dram__bytes_read.sum"][0].replace(",", ""))
+            wr = float(d["dram__bytes_write.sum"][0].replace(",", ""))
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = rd * mult.get(d["dram__bytes_read.sum"][1], 1) + wr * mult.get(d["dram__bytes_write.sum"][1], 1)
+            out.append("| **traffic = dram read + write** | %.0f | byte |" % traffic)
+            traffic_out[name] = traffic
+        except Exception:
+            pass
+        parts.append("\n".join(out) + "\n")
+    return "\n".join(parts)
 
 
 def main():
@@ -85,15 +93,21 @@ def main():
     if s:
         open(os.path.join(OUT, "%s_launches.md" % tag), "w").write(s)
         print(s)
-    parts = ["# ncu --set full captures (%s): `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 6 -c 1 "
-             "python tools/probe/phase_probe.py`\n" % tag]
+    parts = ["# ncu --set full captures (%s): `ncu --set full --clock-control none --import-source on -s <skip> -c <n> "
+             "python tools/probe/phase_probe.py` (steady-state frames of lvt_track_pool) and tools/probe/rectify_probe.py\n" % tag]
+    seen, traffic = set(), {}
     for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "%s_*.ncu-rep" % tag))):
-        f = full(rep)
+        f = full(rep, seen, traffic)
         if f:
             parts.append(f)
     if len(parts) > 1:
         open(os.path.join(OUT, "%s_ncu_full.md" % tag), "w").write("\n".join(parts))
         print("\n".join(parts)[:3000])
+    if traffic:
+        import json
+        # DRAM bytes (read + write) per launch of every captured kernel: bench.py's roofline.traffic
+        json.dump({"source": "%s_ncu_full.md" % tag, "dram_bytes_per_launch": traffic},
+                  open(os.path.join(OUT, "traffic.json"), "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
