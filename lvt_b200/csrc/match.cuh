@@ -240,12 +240,19 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     for (int q0 = 0; q0 < n_q; q0 += blockDim.x)
     {
         const int q = q0 + threadIdx.x;
-        int kind = 0; // 1 fast, 2 slow
+        int kind = 0, cnt = 0; // 1 fast, 2 slow
         if (q < n_q)
         {
             choice[q] = -1;
             if (active(q))
-                kind = (L.keys && L.count[q] <= L.cap) ? 1 : 2;
+            {
+                kind = 2;
+                if (L.keys)
+                {
+                    cnt = L.count[q];
+                    kind = cnt <= L.cap ? 1 : 2;
+                }
+            }
         }
 #pragma unroll
         for (int which = 1; which <= 2; which++)
@@ -257,8 +264,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             if (lane == __ffs(m) - 1)
                 base = atomicAdd(&s_flag[1 + which], __popc(m));
             base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (kind == which)
-                (which == 1 ? fast : slow_items)[base + __popc(m & ((1u << lane) - 1u))] = q;
+            if (kind == which) // fast entries carry the list length: (length << 20 | query)
+                (which == 1 ? fast : slow_items)[base + __popc(m & ((1u << lane) - 1u))] = which == 1 ? ((cnt << 20) | q) : q;
         }
     }
     __syncthreads();
@@ -310,20 +317,22 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     // then touches only shared memory.  A list that does not fit in skeys is read from global memory.
     constexpr int U = 4;
     int rq[U], rcnt[U], rprev[U], roff[U];
-#pragma unroll
-    for (int u = 0; u < U; u++)
-    {
-        const int it = threadIdx.x + u * blockDim.x;
-        rq[u] = it < n_fast ? fast[it] : -1;
-        rprev[u] = -1;
-    }
+    uint4 rk4[U]; // the first four keys of the list
     int max_cnt = 0;
 #pragma unroll
     for (int u = 0; u < U; u++)
     {
-        rcnt[u] = rq[u] >= 0 ? L.count[rq[u]] : 0;
+        const int it = threadIdx.x + u * blockDim.x;
+        const int e = it < n_fast ? fast[it] : -1;
+        rq[u] = e < 0 ? -1 : (e & 0xFFFFF);
+        rcnt[u] = e < 0 ? 0 : (int)((uint32_t)e >> 20);
+        rprev[u] = -1;
         max_cnt = max(max_cnt, rcnt[u]);
     }
+#pragma unroll
+    for (int u = 0; u < U; u++) // in flight while the slices are allocated and copied
+        rk4[u] = rcnt[u] > 0 ? *reinterpret_cast<const uint4 *>(L.keys + (size_t)rq[u] * L.cap)
+                             : make_uint4(kNoKey, kNoKey, kNoKey, kNoKey);
 #pragma unroll
     for (int u = 0; u < U; u++)
     {
@@ -352,8 +361,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         {
             const uint32_t *src = L.keys + (size_t)rq[u] * L.cap;
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(skeys + roff[u]);
-            for (int k = 0; k < rcnt[u]; k += 4)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * k), "l"(src + k) : "memory");
+            for (int k = 4; k < rcnt[u]; k += 4) // the first chunk lives in registers
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * k), "l"(src + k) : "memory");
         }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     if (dbg)
@@ -372,30 +381,32 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         if (threadIdx.x == 0)
             dbg[18] = s_flag[4];
     }
-    // the first two keys of a sorted list whose feature is not marked / taken by an earlier query;
-    // four keys per step: one 16-byte load, four independent owner look-ups, then the decision
-    auto best2 = [](const uint32_t *keys, int cnt, const int *cur_owner, int q, uint32_t &b1, uint32_t &b2) {
+    // The first two keys of a sorted list whose feature is not marked / taken by an earlier query.  Keys
+    // are unique and ascending, so these are the two SMALLEST open keys: every key goes through two
+    // min/max updates, closed ones as kNoKey -- no data-dependent branches inside a chunk.  A chunk is
+    // four keys (one 16-byte load, four independent owner look-ups); once two open keys are known no
+    // later chunk can change them.
+    auto best2 = [](const uint4 first, const uint32_t *keys, int cnt, const int *cur_owner, int q, uint32_t &b1,
+                    uint32_t &b2) {
         b1 = kNoKey;
         b2 = kNoKey;
-        for (int k = 0; k < cnt; k += 4)
+        uint4 c = first;
+        for (int k = 0;;)
         {
-            const uint4 c = *reinterpret_cast<const uint4 *>(keys + k);
             const uint32_t key[4] = {c.x, c.y, c.z, c.w};
-            bool open[4];
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                open[i] = (k + i < cnt) && cur_owner[key[i] & 0xFFFFFu] >= q; // keys past cnt: stale slots of the list row
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (open[i])
-                {
-                    if (b1 == kNoKey)
-                        b1 = key[i];
-                    else if (b2 == kNoKey)
-                        b2 = key[i];
-                }
-            if (b2 != kNoKey)
+            {
+                // keys past cnt are stale slots of the list row: never looked up
+                const int owner = (k + i < cnt) ? cur_owner[key[i] & 0xFFFFFu] : -2;
+                const uint32_t t = owner >= q ? key[i] : kNoKey;
+                b2 = min(b2, max(b1, t));
+                b1 = min(b1, t);
+            }
+            k += 4;
+            if (b2 != kNoKey || k >= cnt)
                 break;
+            c = *reinterpret_cast<const uint4 *>(keys + k);
         }
     };
 
@@ -418,16 +429,18 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
                 continue;
             uint32_t b1, b2;
             if (roff[u] >= 0)
-                best2(skeys + roff[u], rcnt[u], cur, rq[u], b1, b2);
+                best2(rk4[u], skeys + roff[u], rcnt[u], cur, rq[u], b1, b2);
             else
-                best2(L.keys + (size_t)rq[u] * L.cap, rcnt[u], cur, rq[u], b1, b2);
+                best2(rk4[u], L.keys + (size_t)rq[u] * L.cap, rcnt[u], cur, rq[u], b1, b2);
             publish_cached(rq[u], b1, b2, my_count, rprev[u]);
         }
         for (int it = threadIdx.x + U * blockDim.x; it < n_fast; it += blockDim.x)
         {
-            const int q = fast[it];
+            const int e = fast[it], q = e & 0xFFFFF, cnt = (int)((uint32_t)e >> 20);
+            const uint32_t *keys = L.keys + (size_t)q * L.cap;
             uint32_t b1, b2;
-            best2(L.keys + (size_t)q * L.cap, L.count[q], cur, q, b1, b2);
+            best2(cnt > 0 ? *reinterpret_cast<const uint4 *>(keys) : make_uint4(kNoKey, kNoKey, kNoKey, kNoKey), keys, cnt, cur, q,
+                  b1, b2);
             publish(q, b1, b2, my_count);
         }
         for (int it = warp; it < n_slow; it += nwarps)
