@@ -155,10 +155,19 @@ __global__ void __launch_bounds__(256) score_kernel(const __grid_constant__ CUte
 // ---------------------------------------------------------------------------------------------
 // K2: non-maximum suppression
 // ---------------------------------------------------------------------------------------------
+// tile_overflow[t] = number of "big" candidates queued for the tile (low bits) | kTileSequential.
+// A big candidate is a local maximum whose component outgrew the per-thread / per-warp replay buffers
+// (kCompCap pixels); tile_kernel floods it with the whole CTA (tile_big_candidates).  kTileSequential
+// sends the whole tile through the one-thread fallback (more than kBigCandCap big candidates, more
+// slow candidates than a CTA's lists hold, components beyond kBigMemberCap pixels).
+constexpr int kTileSequential = 0x40000000;
+constexpr int kBigCandCap = 64;
+
 struct NmsArgs
 {
     const uint8_t *score;
     uint32_t *tile_list;
+    uint32_t *big_list; // [batch][n_tiles][kBigCandCap]  (s << 24 | y << 12 | x)
     int *tile_count, *tile_overflow, *error;
     const int *retry; // nullptr on the first pass
     TileGrid grid;
@@ -169,6 +178,19 @@ struct NmsArgs
 
 
 constexpr int kCompCap = 96; // largest component replayed in registers/local memory
+
+__device__ __forceinline__ int tile_of(const NmsArgs &a, int x, int y) { return (y / a.grid.cell) * a.grid.nx + x / a.grid.cell; }
+
+// the component of the local maximum (x, y, s) is too large for this kernel's buffers: tile_kernel settles it
+__device__ void queue_big_candidate(const NmsArgs &a, int b, int x, int y, int s)
+{
+    const int t = b * a.n_tiles + tile_of(a, x, y);
+    const int pos = atomicAdd(&a.tile_overflow[t], 1) & (kTileSequential - 1);
+    if (pos < kBigCandCap)
+        a.big_list[(size_t)t * kBigCandCap + pos] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+    else
+        atomicOr(&a.tile_overflow[t], kTileSequential);
+}
 
 // Appends the CTA's survivors (s << 24 | y << 12 | x) to their detection tiles' lists.  Lanes of a
 // warp that hit the same tile reserve their slots with one atomicAdd (a few hot counters would
@@ -322,8 +344,7 @@ __device__ bool nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
                 continue;
             if (n == kCompCap)
             {
-                const int t = (y / a.grid.cell) * a.grid.nx + (x / a.grid.cell);
-                a.tile_overflow[b * a.n_tiles + t] = 1; // the tile is redone sequentially (nms_fallback_tile)
+                queue_big_candidate(a, b, x, y, s); // tile_kernel floods it with the whole CTA
                 return false;
             }
             tie |= (v == s);
@@ -664,7 +685,7 @@ __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
         if (pos < kNmsSlowCap)
             s_cand[pos] = ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x;
         else
-            a.tile_overflow[b * a.n_tiles + (y / a.grid.cell) * a.grid.nx + x / a.grid.cell] = 1;
+            atomicOr(&a.tile_overflow[b * a.n_tiles + tile_of(a, x, y)], kTileSequential);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < nl; k += blockDim.x)
@@ -679,7 +700,7 @@ __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
             {
                 // the component lies in one detection tile (tile borders carry no corners)
                 const int gx = x0 + i % kNmsWin, gy = y0 + i / kNmsWin;
-                a.tile_overflow[b * a.n_tiles + (gy / a.grid.cell) * a.grid.nx + gx / a.grid.cell] = 1;
+                atomicOr(&a.tile_overflow[b * a.n_tiles + tile_of(a, gx, gy)], kTileSequential);
             }
         }
     }
@@ -691,13 +712,24 @@ __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
         for (int j = warp; j < njob; j += 8)
         {
             const int h = s_job[j];
-            const int r = warp_replay_component(lab, win, kNmsWin * kNmsWin, kNmsWin, lab[h], s_comp[warp]);
-            if ((threadIdx.x & 31) == 0)
+            const uint32_t L = lab[h];
+            const int r = warp_replay_component(lab, win, kNmsWin * kNmsWin, kNmsWin, L, s_comp[warp]);
+            if (r < 0)
             {
-                const int q = r < 0 ? h : r, lx = q % kNmsWin, ly = q / kNmsWin;
-                if (r < 0)
-                    a.tile_overflow[b * a.n_tiles + ((y0 + ly) / a.grid.cell) * a.grid.nx + (x0 + lx) / a.grid.cell] = 1;
-                else if (lx >= kNmsHalo && lx < kNmsHalo + kNmsTile && ly >= kNmsHalo && ly < kNmsHalo + kNmsTile)
+                // more than kCompCap pixels: every interior pixel that carries the maximum becomes a big
+                // candidate; the one that turns out to be the root is emitted by tile_kernel
+                for (int i = threadIdx.x & 31; i < kNmsWin * kNmsWin; i += 32)
+                {
+                    const int lx = i % kNmsWin, ly = i / kNmsWin;
+                    if (lab[i] == L && win[i] == (L >> 12) && lx >= kNmsHalo && lx < kNmsHalo + kNmsTile && ly >= kNmsHalo &&
+                        ly < kNmsHalo + kNmsTile)
+                        queue_big_candidate(a, b, x0 + lx, y0 + ly, (int)win[i]);
+                }
+            }
+            else if ((threadIdx.x & 31) == 0)
+            {
+                const int q = r, lx = q % kNmsWin, ly = q / kNmsWin;
+                if (lx >= kNmsHalo && lx < kNmsHalo + kNmsTile && ly >= kNmsHalo && ly < kNmsHalo + kNmsTile)
                     s_surv[atomicAdd(&s_nsurv, 1)] = ((uint32_t)win[r] << 24) | ((uint32_t)(y0 + ly) << 12) | (uint32_t)(x0 + lx);
             }
             __syncwarp();
@@ -996,6 +1028,192 @@ __device__ void block_bitonic_sort(uint32_t *keys, int P)
     }
 }
 
+// Big candidates of one detection tile (queue_big_candidate), settled by the tile's whole CTA.
+// For each candidate c = (x, y, s): breadth-first flood of its 4-connected corner component through the
+// score map (one layer per step, all threads; visited = one bit per tile pixel in shared memory, the
+// members (raster << 8 | score) in a shared list whose layers are contiguous).  A larger score anywhere
+// suppresses c.  A unique maximum survives.  With several pixels at the maximum the members are sorted
+// to raster order and one thread replays OpenCV's merge sequence (the decisions of replay_component);
+// c survives iff it is the root.  Survivors are appended to the tile's list.  Components beyond
+// kBigMemberCap pixels send the tile to the one-thread fallback (returns false).
+constexpr int kBigMemberCap = 8192;
+
+__device__ bool tile_big_candidates(const NmsArgs &a, int t, int b, int n_big, uint32_t *s_members /* [kBigMemberCap] */,
+                                    uint32_t *s_bm /* [tw * th / 32 + 1] */, int16_t *s_parent /* [kBigMemberCap] */,
+                                    int *s_ctl /* [4] */)
+{
+    const uint8_t *sm = a.score + (size_t)b * a.rows * a.pitch;
+    const int tx = t % a.grid.nx, ty = t / a.grid.nx;
+    const int x0 = tx * a.grid.cell, y0 = ty * a.grid.cell, tw = a.grid.tile_w(tx), th = a.grid.tile_h(ty);
+    const int nw = (tw * th + 31) >> 5;
+    uint32_t *list = a.tile_list + ((size_t)b * a.n_tiles + t) * a.tile_cap;
+    auto score_at = [&](int lx, int ly) -> int {
+        if (lx < 3 || ly < 3 || lx > tw - 4 || ly > th - 4)
+            return 0; // a tile is an image of its own: no corners within 3 px of its border
+        const int v = sm[(size_t)(y0 + ly) * a.pitch + x0 + lx];
+        return v >= a.threshold ? v : 0;
+    };
+    for (int k = 0; k < n_big; k++)
+    {
+        const uint32_t c = a.big_list[((size_t)b * a.n_tiles + t) * kBigCandCap + k];
+        const int s = (int)(c >> 24), cx = (int)(c & 0xFFFu) - x0, cy = (int)((c >> 12) & 0xFFFu) - y0;
+        const uint32_t self = ((uint32_t)(cy * tw + cx) << 8) | (uint32_t)s;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x)
+            s_bm[i] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            s_members[0] = self;
+            s_bm[(cy * tw + cx) >> 5] = 1u << ((cy * tw + cx) & 31);
+            s_ctl[0] = 1; // members
+            s_ctl[1] = 0; // beaten
+            s_ctl[2] = 0; // maximum shared
+        }
+        __syncthreads();
+        int lo = 0;
+        for (;;)
+        {
+            const int hi = min(s_ctl[0], kBigMemberCap);
+            __syncthreads(); // everybody has read the layer bounds
+            for (int i = lo + threadIdx.x; i < hi; i += blockDim.x)
+            {
+                const int r = (int)(s_members[i] >> 8), py = r / tw, px = r - py * tw;
+                int vv[4];
+#pragma unroll
+                for (int d = 0; d < 4; d++) // independent loads, issued together
+                    vv[d] = score_at(px + (d == 0) - (d == 1), py + (d == 2) - (d == 3));
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                {
+                    const int v = vv[d];
+                    if (v == 0)
+                        continue;
+                    if (v > s)
+                    {
+                        s_ctl[1] = 1;
+                        continue;
+                    }
+                    const int qr = (py + (d == 2) - (d == 3)) * tw + px + (d == 0) - (d == 1);
+                    const uint32_t bit = 1u << (qr & 31);
+                    if (atomicOr(&s_bm[qr >> 5], bit) & bit)
+                        continue; // seen
+                    if (v == s)
+                        s_ctl[2] = 1;
+                    const int pos = atomicAdd(&s_ctl[0], 1);
+                    if (pos < kBigMemberCap)
+                        s_members[pos] = ((uint32_t)qr << 8) | (uint32_t)v;
+                }
+            }
+            __syncthreads();
+            if (s_ctl[1] || s_ctl[0] == hi || s_ctl[0] > kBigMemberCap)
+                break;
+            lo = hi;
+        }
+        const int n = s_ctl[0];
+        const bool beaten = s_ctl[1] != 0, tie = s_ctl[2] != 0;
+        __syncthreads();
+        if (beaten)
+            continue;
+        if (n > kBigMemberCap)
+            return false;
+        bool survives = true;
+        if (tie)
+        {
+            int P = 1;
+            while (P < n)
+                P <<= 1;
+            for (int i = n + threadIdx.x; i < P; i += blockDim.x)
+                s_members[i] = 0xFFFFFFFFu;
+            __syncthreads();
+            block_bitonic_sort(s_members, P); // raster order (keys are raster << 8 | score)
+            if (threadIdx.x == 0)
+            {
+                auto raster = [&](int i) { return (int)(s_members[i] >> 8); };
+                auto sc = [&](int i) { return (int)(s_members[i] & 0xFFu); };
+                auto find = [&](int i) {
+                    while (s_parent[i] != -1)
+                        i = s_parent[i];
+                    return i;
+                };
+                for (int i = 0; i < n; i++)
+                    s_parent[i] = -1;
+                for (int m = 0; m < n; m++)
+                {
+                    const int p = raster(m);
+                    // member directly above: raster p - tw, somewhere in [0, m)
+                    int above = -1;
+                    if (p >= tw)
+                    {
+                        int l = 0, h = m - 1;
+                        while (l < h)
+                        {
+                            const int mid = (l + h) >> 1;
+                            if (raster(mid) < p - tw)
+                                l = mid + 1;
+                            else
+                                h = mid;
+                        }
+                        if (m > 0 && raster(l) == p - tw)
+                            above = l;
+                    }
+                    if (above >= 0)
+                    {
+                        const int w = find(above);
+                        if (sc(m) < sc(w))
+                            s_parent[m] = (int16_t)w;
+                        else
+                            s_parent[w] = (int16_t)m;
+                    }
+                    if (m != 0 && raster(m - 1) + 1 == p && p % tw != 0)
+                    {
+                        const int pa = s_parent[m], l = find(m - 1);
+                        if (pa == -1)
+                        {
+                            if (l != m)
+                            {
+                                if (sc(m) < sc(l))
+                                    s_parent[m] = (int16_t)l;
+                                else
+                                    s_parent[l] = (int16_t)m;
+                            }
+                        }
+                        else if (l != pa)
+                        {
+                            if (sc(pa) < sc(l))
+                            {
+                                s_parent[pa] = (int16_t)l;
+                                s_parent[m] = (int16_t)l;
+                            }
+                            else
+                            {
+                                s_parent[l] = (int16_t)pa;
+                                s_parent[m] = (int16_t)pa;
+                            }
+                        }
+                    }
+                }
+                int root = 0;
+                for (int i = 0; i < n; i++)
+                    if (s_parent[i] == -1)
+                        root = i;
+                s_ctl[3] = s_members[root] == self;
+            }
+            __syncthreads();
+            survives = s_ctl[3] != 0;
+        }
+        if (survives && threadIdx.x == 0)
+        {
+            const int pos = atomicAdd(&a.tile_count[b * a.n_tiles + t], 1);
+            if (pos < a.tile_cap)
+                list[pos] = self;
+            else
+                *a.error = LVTK_ERR_CAPACITY;
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
 #ifdef LVT_NMS_STATS
 __device__ long long g_tile_trace[2048][12];
 #define TILE_TR(k, v)                                                                                                 \
@@ -1034,16 +1252,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
     long long tck = clock64(), tcn;
     TILE_TR(0, nms_ns());
 #endif
-    if (a.nms.tile_overflow[b * a.n_tiles + t])
     {
-        if (threadIdx.x == 0)
-            nms_fallback_tile(a.nms, a.parent, t, b);
-        __syncthreads();
-        TILE_TR(11, 1);
-    }
-    else
-    {
-        TILE_TR(11, 0);
+        __shared__ int s_big[4];
+        int ov = a.nms.tile_overflow[b * a.n_tiles + t];
+        const int n_big = ov & (kTileSequential - 1);
+        const int tpx = a.grid.tile_w(t % a.grid.nx) * a.grid.tile_h(t / a.grid.nx);
+        if (!(ov & kTileSequential) && n_big > 0)
+        {
+            // local maxima whose components outgrew the NMS kernel's buffers: flooded here by the whole CTA
+            if (tpx > kTileBitmapBits ||
+                !tile_big_candidates(a.nms, t, b, n_big, s_keys, s_rad, reinterpret_cast<int16_t *>(s_perm), s_big))
+                ov |= kTileSequential;
+            __threadfence_block();
+        }
+        if (ov & kTileSequential)
+        {
+            if (threadIdx.x == 0)
+                nms_fallback_tile(a.nms, a.parent, t, b);
+            __syncthreads();
+            TILE_TR(11, 1);
+        }
+        else
+        {
+            TILE_TR(11, n_big ? 2 : 0);
+        }
     }
     const int tx = t % a.grid.nx, ty = t / a.grid.nx;
     const int x0 = tx * a.grid.cell, y0 = ty * a.grid.cell, tw = a.grid.tile_w(tx), th = a.grid.tile_h(ty);
@@ -1456,7 +1688,7 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     {
         const int *retry = pass ? ws.retry : nullptr;
         const int th = pass ? dp.threshold_low : dp.threshold;
-        NmsArgs na{ws.score, ws.tile_list, ws.tile_count, ws.tile_overflow, ws.error, retry,      dp.grid,
+        NmsArgs na{ws.score, ws.tile_list, ws.big_list, ws.tile_count, ws.tile_overflow, ws.error, retry,      dp.grid,
                    dp.pitch, dp.rows,      dp.cols,       ws.tile_cap,      nt,       th,         nonmax};
         dim3 ngrid((dp.cols + kNmsTile - 1) / kNmsTile, (dp.rows + kNmsTile - 1) / kNmsTile, n_images);
         LVT_TIMED(stream, K_NMS, launch_chained(nms_tile_kernel, ngrid, dim3(256), 0, stream, na));

@@ -72,7 +72,8 @@ struct DetectWorkspace
     uint32_t *tile_aux = nullptr;    // [batch][n_tiles][2*tile_cap] large-tile scratch (radii, permutation)
     uint32_t *tile_out = nullptr;    // [batch][n_tiles][tile_cap]  ordered output, (y << 20 | x << 8 | response)
     int *tile_count = nullptr;       // [batch][n_tiles]
-    int *tile_overflow = nullptr;    // [batch][n_tiles]  component larger than the in-register cap
+    int *tile_overflow = nullptr;    // [batch][n_tiles]  big candidates queued for tile_kernel | sequential-fallback flag
+    uint32_t *big_list = nullptr;    // [batch][n_tiles][64] local maxima of components beyond the NMS kernel's buffers
     int *tile_out_count = nullptr;   // [batch][n_tiles]
     int *cand_count = nullptr;       // [batch] local maxima queued for nms_resolve_kernel (list lives in `parent`)
     int *retry = nullptr;            // [batch] fewer than 200 corners: redo at the lowered threshold

@@ -96,6 +96,55 @@ __device__ __forceinline__ void scan_projected_window(const FeatDev &f, const Ca
     const int sx = max(hx - cam.cell_search_radius, 0), ex = min(hx + cam.cell_search_radius + 1, cam.cells_x);
     if (sx >= ex)
         return;
+    const int n_rows = ey - sy;
+    if (n_rows <= 8)
+    {
+        // The cells of one grid row are contiguous in the CSR; the rows of the window are scanned as ONE
+        // concatenated candidate list, so the dependent loads (row bounds -> item -> position ->
+        // descriptor) are paid once per 32 candidates instead of once per grid row.
+        int s = 0, len = 0;
+        if (lane < n_rows)
+        {
+            s = f.cell_start[(sy + lane) * cam.cells_x + sx];
+            len = f.cell_start[(sy + lane) * cam.cells_x + ex] - s;
+        }
+        int incl = len; // inclusive prefix of the row lengths over lanes 0 .. 7
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1)
+        {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += nb;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 7);
+        int r_s[8], r_end[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+        {
+            r_s[r] = __shfl_sync(0xffffffffu, s, r);
+            r_end[r] = __shfl_sync(0xffffffffu, incl, r);
+        }
+        for (int base = 0; base < total; base += 32)
+        {
+            const int idx = base + lane;
+            bool ok = false;
+            int j = 0;
+            if (idx < total)
+            {
+                int pos = r_s[0] + idx;
+#pragma unroll
+                for (int r = 1; r < 8; r++)
+                    if (idx >= r_end[r - 1])
+                        pos = r_s[r] + (idx - r_end[r - 1]);
+                j = f.cell_items[pos];
+                const float2 k = f.xy[j];
+                const float dx = __fsub_rn(k.x, p.x), dy = __fsub_rn(k.y, p.y);
+                ok = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2;
+            }
+            visit(ok, ok ? (((uint32_t)hamming256(q0, q1, f.desc + 8 * (size_t)j) << 20) | (uint32_t)j) : kNoKey);
+        }
+        return;
+    }
     for (int cy = sy; cy < ey; cy++)
     {
         // cells of one grid row are contiguous in the CSR

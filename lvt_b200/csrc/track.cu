@@ -35,6 +35,7 @@ struct FrameCtl
     int inliers;
     int pad;
     PoseD pred, opt;
+    double opt_W[12]; // world->camera of opt, prepared by pose_kernel for the staged-point projection
     lvt_frame_info info;
     long long cyc[8];
     int rounds[4];
@@ -108,18 +109,15 @@ __global__ void __launch_bounds__(kCandWarps * 32) mapcand_kernel(MapCandArgs a)
             m = a.st->staged_n;
         }
     }
-    if (threadIdx.x == 0)
+    if (a.st)
     {
-        PoseD pose = a.pose;
-        if (a.st && a.which == 0)
-        {
-            MotionState mm = a.st->motion; // a copy: track_a performs the real update
-            pose = motion_predict(mm, a.st->last_pose);
-        }
-        else if (a.st)
-            pose = a.ctl->opt;
-        world_to_camera(pose, W);
+        // prepared by the kernel in front: track_b / reset (prediction for the map pass), pose_kernel (staged pass)
+        const double *src = a.which == 0 ? a.st->pred_W : a.ctl->opt_W;
+        if (threadIdx.x < 12)
+            W[threadIdx.x] = src[threadIdx.x];
     }
+    else if (threadIdx.x == 0)
+        world_to_camera(a.pose, W);
     __syncthreads();
     const FeatDev f = *a.feat;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -196,6 +194,14 @@ __device__ void write_result(const TrackArgs &a, TrackState &S, const PoseD &pos
         a.result->cycles[k] = c.cyc[k];
     for (int k = 0; k < 4; k++)
         a.result->rounds[k] = c.rounds[k];
+}
+
+// one thread: world->camera of the pose predicted for the next frame (see TrackState::pred_W)
+__device__ void prepare_prediction(TrackState &S)
+{
+    MotionState mm = S.motion; // a copy: track_a performs the real update
+    const PoseD pose = motion_predict(mm, S.last_pose);
+    world_to_camera(pose, S.pred_W);
 }
 
 __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
@@ -380,6 +386,7 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
     if (a.ctl && cluster.block_rank() == 0 && threadIdx.x == 0)
     {
         a.ctl->cyc[4] = clock64();
+        world_to_camera(a.ctl->opt, a.ctl->opt_W);
         if (a.early)
         {
             a.early->pose = a.ctl->opt;
@@ -531,6 +538,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
             S.map_n = map_n;
             S.staged_n = staged_n;
             S.last_matches[0] = map_n;
+            prepare_prediction(S);
             ctl.info.triangulated = 1;
             ctl.info.new_points = added;
             write_result(a, S, sh.pose, 2, map_n, staged_n);
@@ -646,6 +654,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         S.map_n = map_n;
         S.staged_n = staged_n;
         S.last_pose = sh.pose;
+        prepare_prediction(S);
         write_result(a, S, sh.pose, 2, map_n, staged_n);
     }
 }

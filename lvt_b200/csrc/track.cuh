@@ -39,6 +39,10 @@ struct TrackState
     int error;           // sticky LVTK_ERR_*
     PoseD last_pose;
     MotionState motion;
+    // world->camera of the pose the motion model predicts for the NEXT frame, prepared by the kernel
+    // that finishes a frame so that mapcand_kernel starts projecting at once (same arithmetic as
+    // track_a's own prediction: motion_predict on a copy of the motion state, world_to_camera)
+    double pred_W[12];
 };
 
 struct FrameResult

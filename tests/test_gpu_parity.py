@@ -52,6 +52,37 @@ def test_agast_huge_component_fallback(ctxs):
     assert kp_equal(g.agast(img, 10, True), o.agast(img, 10, True))
 
 
+def _blur_quant(seed, h, w, sigma, step):
+    """binary noise, blurred and quantised: corner components of hundreds of pixels, many with several
+    pixels at the maximum score (found with scipy.ndimage.label on the oracle's corner map: sigma 1.0 ->
+    components up to ~300 px, a dozen beyond the 96-px replay buffers, about half of them tied)"""
+    rng = np.random.default_rng(seed)
+    a = (rng.integers(0, 2, (h, w)) * 200).astype(np.float32)
+    k = np.arange(-4, 5)
+    g = np.exp(-k * k / (2.0 * sigma * sigma))
+    g /= g.sum()
+    a = np.apply_along_axis(lambda r: np.convolve(r, g, mode="same"), 1, a)
+    a = np.apply_along_axis(lambda c: np.convolve(c, g, mode="same"), 0, a)
+    return (np.clip(a, 0, 255).astype(np.uint8) // step * step).astype(np.uint8)
+
+
+def test_agast_big_components_settled_by_tile_kernel(ctxs, cuda, oracle):
+    """components beyond the NMS kernel's replay buffers (96 px) are flooded by the tile's CTA"""
+    g, o, _ = ctxs
+    cases = [(_blur_quant(1, 200, 240, 1.0, 16), 10), (_blur_quant(2, 250, 250, 1.2, 16), 8), (_blur_quant(3, 250, 250, 1.5, 8), 6),
+             (_blur_quant(4, 130, 250, 0.8, 32), 10), (synth.canvas(105, 250, 250, density=60, noise=6.0), 8)]
+    for img, th in cases:
+        img = np.ascontiguousarray(img)
+        assert kp_equal(g.agast(img, th, True), o.agast(img, th, True)), (img.shape, th)
+    # the same through the tiled detector (tiles of 250 px, several big components per tile)
+    p = configs.make_params("euroc_synth", agast_threshold=8)
+    cg, co = cuda.context(p), oracle.context(p)
+    img = np.ascontiguousarray(_blur_quant(7, p.img_height, p.img_width, 1.2, 16))
+    assert kp_equal(cg.detect(img), co.detect(img))
+    cg.destroy()
+    co.destroy()
+
+
 @pytest.mark.parametrize("name", ["kitti_synth", "kitti_stock", "euroc_synth", "tum_synth"])
 def test_extract_all_configs(cuda, oracle, name):
     p = configs.make_params(name)
