@@ -381,7 +381,12 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
         inlier[i] = 1;
         e2[i] = 0.0;
     }
-    __syncthreads();
+    // every CTA of the cluster must be executing before anybody stores into its shared memory
+    // (pose_evaluate pushes the CTA sums through DSMEM)
+    if (nranks > 1)
+        cluster.sync();
+    else
+        __syncthreads();
 
     // LM state of rank 0 / thread 0 (OptimizationAlgorithmLevenberg::solve)
     double lambda = 0, ni = 2, current_chi = 0, rho = 0;
