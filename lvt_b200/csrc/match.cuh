@@ -483,14 +483,38 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
                 best2(rk4[u], L.keys + (size_t)rq[u] * L.cap, rcnt[u], cur, rq[u], b1, b2);
             publish_cached(rq[u], b1, b2, my_count, rprev[u]);
         }
-        for (int it = threadIdx.x + U * blockDim.x; it < n_fast; it += blockDim.x)
+        // queries beyond the register-resident ones (maps of more than 4 x blockDim points): entries, first
+        // chunks and previous choices of four queries are fetched together, so a round pays the L2
+        // latency once per four queries
+        for (int base = threadIdx.x + U * blockDim.x; base < n_fast; base += U * blockDim.x)
         {
-            const int e = fast[it], q = e & 0xFFFFF, cnt = (int)((uint32_t)e >> 20);
-            const uint32_t *keys = L.keys + (size_t)q * L.cap;
-            uint32_t b1, b2;
-            best2(cnt > 0 ? *reinterpret_cast<const uint4 *>(keys) : make_uint4(kNoKey, kNoKey, kNoKey, kNoKey), keys, cnt, cur, q,
-                  b1, b2);
-            publish(q, b1, b2, my_count);
+            int e[U], prev[U];
+            uint4 k4[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const int it = base + u * blockDim.x;
+                e[u] = it < n_fast ? fast[it] : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const bool on = e[u] >= 0;
+                const int q = e[u] & 0xFFFFF;
+                k4[u] = on && (e[u] >> 20) > 0 ? *reinterpret_cast<const uint4 *>(L.keys + (size_t)q * L.cap)
+                                               : make_uint4(kNoKey, kNoKey, kNoKey, kNoKey);
+                prev[u] = on ? choice[q] : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                if (e[u] < 0)
+                    continue;
+                const int q = e[u] & 0xFFFFF, cnt = (int)((uint32_t)e[u] >> 20);
+                uint32_t b1, b2;
+                best2(k4[u], L.keys + (size_t)q * L.cap, cnt, cur, q, b1, b2);
+                publish_cached(q, b1, b2, my_count, prev[u]);
+            }
         }
         for (int it = warp; it < n_slow; it += nwarps)
         {
