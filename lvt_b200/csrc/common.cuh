@@ -53,21 +53,42 @@ void prof_end(cudaStream_t s, int id);
 // programmatic-stream-serialization attribute and starts with LVT_GRID_DEP_SYNC(), so its CTAs are
 // scheduled (and its launch latency is paid) while the previous kernel of the stream is still
 // running; griddepcontrol.wait returns once that kernel has completed and its writes are visible.
-template <class... KArgs, class... Args>
-inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                  Args &&...args)
+template <class... KArgs>
+inline cudaError_t launch_chained_impl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                       int cluster, KArgs... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (cluster > 1)
+    {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = (unsigned)cluster;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
+    cfg.attrs = attr;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args &&...args)
+{
+    return launch_chained_impl<KArgs...>(kernel, grid, block, smem, stream, 1, static_cast<KArgs>(args)...);
+}
+// the same as a launch of thread-block clusters of `cluster` CTAs along x
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                          int cluster, Args &&...args)
+{
+    return launch_chained_impl<KArgs...>(kernel, grid, block, smem, stream, cluster, static_cast<KArgs>(args)...);
 }
 #define LVT_GRID_DEP_SYNC()                                                                                           \
     do                                                                                                                \

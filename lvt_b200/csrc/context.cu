@@ -547,7 +547,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.proj, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.vis, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.ms.choice, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->sc.ms.items, (size_t)2 * c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.ms.items, (size_t)2 * c->pcap + 1024); // + the per-CTA rounding of the team's work lists
     rc = rc ? rc : c->arena.alloc(&c->sc.sol_xyz, (size_t)c->pcap * 3);
     rc = rc ? rc : c->arena.alloc(&c->sc.sol_uv, (size_t)c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->sc.level, (size_t)c->pcap);

@@ -20,6 +20,7 @@
 // the (small) staged set take the list-free path: one warp re-scans the window each round.
 #pragma once
 #include "extract.cuh"
+#include <cooperative_groups.h>
 
 namespace lvtb
 {
@@ -258,8 +259,22 @@ __device__ inline void block_project(const double *xyz, int m, const double *W /
     __syncthreads();
 }
 
+// The CTAs that share one pass of rounds.  nranks == 1: a single CTA (the seam kernels, track_b).
+// nranks > 1: the CTAs of a thread-block cluster split the queries (32 consecutive queries per
+// warp-slot, dealt round-robin) while every CTA keeps a full replica of the owner arrays in its own
+// shared memory: a choice is published with atomicMin into EVERY replica (distributed shared memory),
+// one cluster barrier ends a round, and the "changed" flag / match count of a round are collected
+// in rank 0's shared memory.  owner_c is the third owner array the rotation needs (the array of the
+// round after next is cleared while the current round runs, so one barrier per round suffices).
+struct RoundsTeam
+{
+    int rank = 0, nranks = 1;
+    int *owner_c = nullptr;
+    int *team_flags = nullptr; // [3][2] in shared memory (every CTA has the array; rank 0's copy is used)
+};
+
 // ---------------------------------------------------------------------------------------------
-// phase 2: the rounds.  All threads of the CTA call.
+// phase 2: the rounds.  All threads of the CTA (of every CTA of the team) call.
 //   n_q queries, active(q) says whether query q takes part; lists may be empty (keys == nullptr).
 //   slow(q, cur, b1, b2): warp-cooperative window scan restricted to features with cur[f] >= q.
 //   marks: initial marks of the n_f features (nullptr = all clear).
@@ -270,25 +285,43 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
                                    float dist_th, const uint8_t *marks, int *choice, int *items /* [2 * n_q] */,
                                    int *owner_a, int *owner_b, int *s_flag /* [8] */, float *out_d1, float *out_d2,
                                    int *rounds_out, long long *dbg = nullptr, uint32_t *skeys = nullptr,
-                                   int skey_cap = 0)
+                                   int skey_cap = 0, const RoundsTeam team = RoundsTeam())
 {
+    namespace cgr = cooperative_groups;
+    const int rank = team.rank, nranks = team.nranks;
+    // queries of this CTA: local slot j <-> query ((j / 32) * nranks + rank) * 32 + j % 32
+    const int n_loc = 32 * (((n_q + 31) / 32 + nranks - 1) / nranks);
+    auto query_of = [&](int j) { return ((j >> 5) * nranks + rank) * 32 + (j & 31); };
 #define LVT_RDBG(k)                                                                                                   \
     if (dbg && threadIdx.x == 0)                                                                                      \
     dbg[k] = clock64()
     LVT_RDBG(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int *cur = owner_a, *nxt = owner_b;
-    int *fast = items, *slow_items = items + n_q;
+    int *cur = owner_a, *nxt = owner_b, *spare = team.owner_c;
+    int *fast = items + (size_t)rank * n_loc, *slow_items = items + (size_t)(nranks + rank) * n_loc;
     if (threadIdx.x == 0)
+    {
         s_flag[2] = 0, s_flag[3] = 0, s_flag[4] = 0;
+        if (nranks > 1)
+            for (int k = 0; k < 6; k++)
+                team.team_flags[k] = 0;
+    }
     for (int j = threadIdx.x; j < n_f; j += blockDim.x)
-        cur[j] = (marks && marks[j]) ? kTaken : kFree;
-    __syncthreads();
+    {
+        const int v = (marks && marks[j]) ? kTaken : kFree;
+        cur[j] = v;
+        if (nranks > 1)
+            nxt[j] = v; // the first round finds its target array clean (later ones: the rotation below)
+    }
+    if (nranks > 1)
+        cgr::this_cluster().sync(); // every replica initialised (and every CTA running) before the first remote store
+    else
+        __syncthreads();
     // work lists, built once: queries served from their key list / by a warp re-scan (order is irrelevant)
     // (warp-aggregated appends: one shared-memory atomic per warp and list)
-    for (int q0 = 0; q0 < n_q; q0 += blockDim.x)
+    for (int j0 = 0; j0 < n_loc; j0 += blockDim.x)
     {
-        const int q = q0 + threadIdx.x;
+        const int q = query_of(j0 + threadIdx.x);
         int kind = 0, cnt = 0; // 1 fast, 2 slow
         if (q < n_q)
         {
@@ -321,6 +354,17 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     const int n_fast = s_flag[2], n_slow = s_flag[3];
     LVT_RDBG(1);
 
+    // feature c is wanted by query q: the smallest q wins, in every replica of the next owner array
+    auto claim = [&](int c, int q) {
+        if (nranks == 1)
+            atomicMin(&nxt[c], q);
+        else
+        {
+            cgr::cluster_group cl = cgr::this_cluster();
+            for (int r = 0; r < nranks; r++)
+                atomicMin(cl.map_shared_rank(&nxt[c], r), q);
+        }
+    };
     // `prev` = the query's choice of the previous round (a register copy for the cached queries)
     auto publish_cached = [&](int q, uint32_t b1, uint32_t b2, int &my_count, int &prev) {
         const int c = accept_match(b1, b2, ratio_th, dist_th);
@@ -332,7 +376,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
         if (c >= 0)
         {
-            atomicMin(&nxt[c], q);
+            claim(c, q);
             my_count++;
             if (out_d1)
             {
@@ -350,7 +394,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
         if (c >= 0)
         {
-            atomicMin(&nxt[c], q);
+            claim(c, q);
             my_count++;
             if (out_d1)
             {
@@ -462,8 +506,12 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     int count = 0, rounds = 0;
     for (;; rounds++)
     {
+        // single CTA: clear this round's target array.  Team: this round's target is clean already (see
+        // the rotation at the end of a round); clear the array of the round after this one meanwhile --
+        // nobody stores into it before the next cluster barrier.
+        int *wipe = nranks > 1 ? spare : nxt;
         for (int j = threadIdx.x; j < n_f; j += blockDim.x)
-            nxt[j] = cur[j] == kTaken ? kTaken : kFree;
+            wipe[j] = cur[j] == kTaken ? kTaken : kFree;
         if (threadIdx.x == 0)
             s_flag[0] = 0, s_flag[1] = 0;
         __syncthreads();
@@ -527,24 +575,61 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         if (my_count)
             atomicAdd(&s_flag[1], my_count);
         __syncthreads();
-        const int changed = s_flag[0];
-        count = s_flag[1];
-        int *t = cur;
-        cur = nxt;
-        nxt = t;
-        __syncthreads();
+        int changed;
+        if (nranks == 1)
+        {
+            changed = s_flag[0];
+            count = s_flag[1];
+            int *t = cur;
+            cur = nxt;
+            nxt = t;
+            __syncthreads();
+        }
+        else
+        {
+            // this CTA's share of the round goes to slot rounds % 3 of rank 0's team_flags.  Rank 0 clears
+            // the NEXT round's slot here: its last readers (two rounds ago) are past the previous barrier,
+            // its next writers come after the barrier below.
+            cgr::cluster_group cl = cgr::this_cluster();
+            int *slot = cl.map_shared_rank(team.team_flags + 2 * (rounds % 3), 0);
+            if (threadIdx.x == 0)
+            {
+                if (s_flag[0])
+                    atomicOr(slot, 1);
+                if (s_flag[1])
+                    atomicAdd(slot + 1, s_flag[1]);
+                if (rank == 0)
+                    team.team_flags[2 * ((rounds + 1) % 3)] = 0, team.team_flags[2 * ((rounds + 1) % 3) + 1] = 0;
+            }
+            cl.sync(); // every claim of the round has landed in every replica
+            if (threadIdx.x == 0)
+            {
+                s_flag[5] = slot[0];
+                s_flag[6] = slot[1];
+            }
+            __syncthreads();
+            changed = s_flag[5];
+            count = s_flag[6];
+            int *t = cur;
+            cur = nxt;
+            nxt = spare;
+            spare = t;
+            __syncthreads();
+        }
         if (rounds < 12)
             LVT_RDBG(3 + rounds);
         if (!changed)
             break;
     }
+    if (nranks > 1)
+        cgr::this_cluster().sync(); // rank 0's flags have been read by everybody; no remote access after this
     if (cur != owner_a)
     {
         for (int j = threadIdx.x; j < n_f; j += blockDim.x)
             owner_a[j] = cur[j];
         __syncthreads();
     }
-    if (rounds_out && threadIdx.x == 0)
+    if (rounds_out && threadIdx.x == 0 && rank == 0)
         *rounds_out = rounds + 1;
     LVT_RDBG(15);
 #undef LVT_RDBG
@@ -556,7 +641,7 @@ __device__ inline int block_match_projected(const CandLists &L, const uint32_t *
                                             const FeatDev &f, int n, const CamParams &cam, float r2, bool use_marks,
                                             int *owner_a, int *owner_b, int *s_flag, float *out_d1, float *out_d2,
                                             int *rounds_out, long long *dbg = nullptr, uint32_t *skeys = nullptr,
-                                            int skey_cap = 0)
+                                            int skey_cap = 0, const RoundsTeam team = RoundsTeam())
 {
     const int lane = threadIdx.x & 31;
     auto active = [&](int q) { return ms.vis[q] != 0; };
@@ -571,7 +656,7 @@ __device__ inline int block_match_projected(const CandLists &L, const uint32_t *
         warp_top2(k1, k2, b1, b2);
     };
     return block_rounds(L, m, n, active, slow, cam.tracking_ratio_th, cam.desc_dist_th, use_marks ? f.matched : nullptr,
-                        ms.choice, ms.items, owner_a, owner_b, s_flag, out_d1, out_d2, rounds_out, dbg, skeys, skey_cap);
+                        ms.choice, ms.items, owner_a, owner_b, s_flag, out_d1, out_d2, rounds_out, dbg, skeys, skey_cap, team);
 }
 
 // Stereo row matching pass (handler.cpp:302-323 + struct.cpp:122-148).  Queries = unmarked left

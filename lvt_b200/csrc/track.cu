@@ -24,6 +24,7 @@ namespace lvtb
 {
 
 constexpr int kTrackThreads = 1024;
+constexpr int kTrackCluster = 8; // CTAs sharing the rounds of the map pass (track_a_kernel)
 constexpr int kCandWarps = 8;
 
 // per-frame hand-over between the kernels of the chain (device memory)
@@ -207,10 +208,22 @@ __device__ void prepare_prediction(TrackState &S)
 __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
 {
     LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
+    // Launched as a cluster of kTrackCluster CTAs: all of them share the greedy rounds of the map pass
+    // (RoundsTeam, match.cuh); everything else is rank 0's.
     extern __shared__ int s_owner[];
     __shared__ TrackShared sh;
+    __shared__ int s_team_flags[6];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
-    uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap);
+    RoundsTeam team;
+    team.rank = rank;
+    team.nranks = nranks;
+    team.owner_c = s_owner + 2 * a.owner_cap;
+    team.team_flags = s_team_flags;
+    const int n_owner = nranks > 1 ? 3 : 2;
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + n_owner * a.owner_cap);
+    const int key_cap = a.key_cap - (n_owner - 2) * a.owner_cap;
 
     TrackState &S = *a.st;
     FrameCtl &ctl = *a.ctl;
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     const int map_n = S.map_n, staged_n = S.staged_n;
     const PoseD last_pose = S.last_pose;
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0 && rank == 0)
     {
         lvt_frame_info z = {};
         ctl.info = z;
@@ -238,7 +251,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     if (state0 == 3)
     {
         // lost: the last pose, nothing else (lvt/src/lvt_system.cpp:159-166)
-        if (threadIdx.x == 0)
+        if (threadIdx.x == 0 && rank == 0)
         {
             ctl.mode = 0;
             write_result(a, S, last_pose, 3, map_n, staged_n);
@@ -247,13 +260,13 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     }
     if (state0 == 1)
     {
-        if (threadIdx.x == 0)
+        if (threadIdx.x == 0 && rank == 0)
             ctl.mode = 2; // track_b seeds the map at the identity pose (lvt/src/lvt_system.cpp:185-193)
         return;
     }
 
     // ---- predict (lvt/src/lvt_system.cpp:196); mapcand_kernel projected with the same prediction
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0 && rank == 0)
     {
         sh.pose = motion_predict(S.motion, last_pose);
         ctl.pred = sh.pose;
@@ -265,14 +278,17 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     const int R = tp.cam.tracking_radius;
     const CandLists no_lists{nullptr, nullptr, 0};
     int count = block_match_projected(a.sc.map_cand, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)(R * R), false, owner_a,
-                                      owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0], a.dbg, skeys, a.key_cap);
+                                      owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0], rank == 0 ? a.dbg : nullptr, skeys,
+                                      key_cap, team);
     int retried = 0;
     if (count < kNMatchesTh)
     {
         retried = 1; // marks reset, radius doubled, cell window unchanged (lvt_local_map.cpp:173-199)
         count = block_match_projected(no_lists, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)((2 * R) * (2 * R)), false,
-                                      owner_a, owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[1]);
+                                      owner_a, owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[1], nullptr, nullptr, 0, team);
     }
+    if (rank != 0)
+        return; // the rounds are over (their last cluster barrier made every choice visible): the rest is rank 0's
     for (int j = threadIdx.x; j < nl; j += blockDim.x)
         fl.matched[j] = owner_a[j] != kFree;
     LVT_PHASE(1);
@@ -788,6 +804,7 @@ __global__ void tri_seam_kernel(TriSeamArgs a)
 // dynamic shared memory of the single-CTA kernels: two owner arrays + as many candidate keys as fit
 // next to them (block_rounds keeps the key lists of its queries there)
 static int g_key_cap = 0;
+static int g_track_cluster = 1; // CTAs of track_a_kernel's cluster (1 when three owner arrays do not fit in shared memory)
 static size_t track_smem_bytes(int owner_cap) { return (2 * (size_t)owner_cap + (size_t)g_key_cap) * sizeof(int); }
 
 static int ensure_smem(int owner_cap)
@@ -800,6 +817,7 @@ static int ensure_smem(int owner_cap)
         LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const int avail = optin - 2048 /* static */ - 2 * owner_cap * (int)sizeof(int);
         g_key_cap = avail > 0 ? (avail / (int)sizeof(int)) & ~3 : 0;
+        g_track_cluster = g_key_cap >= owner_cap + 4096 ? kTrackCluster : 1; // the team needs a third owner array
         const int bytes = (int)track_smem_bytes(owner_cap);
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -838,7 +856,7 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     MapCandArgs mc{st, ctl, 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
     LVT_TIMED(stream, K_MAPCAND, launch_chained(mapcand_kernel, dim3(148 * 2), dim3(kCandWarps * 32), 0, stream, mc));
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
-    LVT_TIMED(stream, K_TRACK_A, launch_chained(track_a_kernel, dim3(1), dim3(kTrackThreads), smem, stream, a));
+    LVT_TIMED(stream, K_TRACK_A, launch_chained_cluster(track_a_kernel, dim3(g_track_cluster), dim3(kTrackThreads), smem, stream, g_track_cluster, a));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
                 debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early, early_seq};
