@@ -259,17 +259,47 @@ __device__ inline void block_project(const double *xyz, int m, const double *W /
     __syncthreads();
 }
 
+// fire-and-forget reductions into the shared memory of CTA `rank` of the cluster (the same offset as
+// `local`): red.shared::cluster does not wait for the remote CTA's answer the way an atomic with a return
+// value does; the cluster barrier that ends a round makes them visible
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local, unsigned rank)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ int dsmem_load(const int *local, unsigned rank)
+{
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(dsmem_addr(local, rank)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsmem_red_min(int *local, unsigned rank, int v)
+{
+    asm volatile("red.relaxed.cluster.shared::cluster.min.s32 [%0], %1;" ::"r"(dsmem_addr(local, rank)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_red_add(int *local, unsigned rank, int v)
+{
+    asm volatile("red.relaxed.cluster.shared::cluster.add.s32 [%0], %1;" ::"r"(dsmem_addr(local, rank)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_red_or(int *local, unsigned rank, int v)
+{
+    asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(dsmem_addr(local, rank)), "r"(v) : "memory");
+}
+
 // The CTAs that share one pass of rounds.  nranks == 1: a single CTA (the seam kernels, track_b).
 // nranks > 1: the CTAs of a thread-block cluster split the queries (32 consecutive queries per
-// warp-slot, dealt round-robin) while every CTA keeps a full replica of the owner arrays in its own
-// shared memory: a choice is published with atomicMin into EVERY replica (distributed shared memory),
-// one cluster barrier ends a round, and the "changed" flag / match count of a round are collected
-// in rank 0's shared memory.  owner_c is the third owner array the rotation needs (the array of the
-// round after next is cleared while the current round runs, so one barrier per round suffices).
+// warp-slot, dealt round-robin).  Every CTA reads owners from a full replica of the owner array in its
+// own shared memory; the array a round WRITES is cut into nranks slices, each at home in one CTA: a
+// choice is published with one fire-and-forget red.min into the home slice of its feature
+// (distributed shared memory), a cluster barrier ends the round, and every CTA refreshes its replica
+// from the home slices (coalesced remote loads).  Three generations of home slices rotate, so the
+// slices of the next round are cleared while the current round runs and one barrier per round
+// suffices.  The "changed" flag / match count of a round are collected in rank 0's shared memory.
 struct RoundsTeam
 {
     int rank = 0, nranks = 1;
-    int *owner_c = nullptr;
     int *team_flags = nullptr; // [3][2] in shared memory (every CTA has the array; rank 0's copy is used)
 };
 
@@ -297,7 +327,10 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     dbg[k] = clock64()
     LVT_RDBG(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int *cur = owner_a, *nxt = owner_b, *spare = team.owner_c;
+    int *cur = owner_a, *nxt = owner_b;
+    // team: three generations of this CTA's home slice live where the single-CTA path keeps `nxt`
+    const int slice = (((n_f + nranks - 1) / nranks) + 31) & ~31, home0 = rank * slice;
+    int *home[3] = {owner_b, owner_b + slice, owner_b + 2 * slice};
     int *fast = items + (size_t)rank * n_loc, *slow_items = items + (size_t)(nranks + rank) * n_loc;
     if (threadIdx.x == 0)
     {
@@ -310,8 +343,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     {
         const int v = (marks && marks[j]) ? kTaken : kFree;
         cur[j] = v;
-        if (nranks > 1)
-            nxt[j] = v; // the first round finds its target array clean (later ones: the rotation below)
+        if (nranks > 1 && j >= home0 && j < home0 + slice)
+            home[0][j - home0] = v; // the first round finds its home slices clean (later ones: cleared a round ahead)
     }
     if (nranks > 1)
         cgr::this_cluster().sync(); // every replica initialised (and every CTA running) before the first remote store
@@ -354,15 +387,15 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     const int n_fast = s_flag[2], n_slow = s_flag[3];
     LVT_RDBG(1);
 
-    // feature c is wanted by query q: the smallest q wins, in every replica of the next owner array
+    int count = 0, rounds = 0;
+    // feature c is wanted by query q: the smallest q wins (team: in the home slice of c, this round's generation)
     auto claim = [&](int c, int q) {
         if (nranks == 1)
             atomicMin(&nxt[c], q);
         else
         {
-            cgr::cluster_group cl = cgr::this_cluster();
-            for (int r = 0; r < nranks; r++)
-                atomicMin(cl.map_shared_rank(&nxt[c], r), q);
+            const int h = c / slice;
+            dsmem_red_min(&home[rounds % 3][c - h * slice], (unsigned)h, q);
         }
     };
     // `prev` = the query's choice of the previous round (a register copy for the cached queries)
@@ -503,20 +536,24 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
     };
 
-    int count = 0, rounds = 0;
     for (;; rounds++)
     {
-        // single CTA: clear this round's target array.  Team: this round's target is clean already (see
-        // the rotation at the end of a round); clear the array of the round after this one meanwhile --
-        // nobody stores into it before the next cluster barrier.
-        int *wipe = nranks > 1 ? spare : nxt;
-        for (int j = threadIdx.x; j < n_f; j += blockDim.x)
-            wipe[j] = cur[j] == kTaken ? kTaken : kFree;
+        // single CTA: clear this round's target array.  Team: this round's home slices are clean already;
+        // clear the next round's generation meanwhile (last read two rounds ago, before the previous
+        // barrier; nobody stores into it before the next one).
+        if (nranks == 1)
+            for (int j = threadIdx.x; j < n_f; j += blockDim.x)
+                nxt[j] = cur[j] == kTaken ? kTaken : kFree;
+        else
+            for (int j = threadIdx.x; j < slice && home0 + j < n_f; j += blockDim.x)
+                home[(rounds + 1) % 3][j] = cur[home0 + j] == kTaken ? kTaken : kFree;
         if (threadIdx.x == 0)
             s_flag[0] = 0, s_flag[1] = 0;
         __syncthreads();
         if (rounds == 0)
             LVT_RDBG(2);
+        if (rounds == 2)
+            LVT_RDBG(24);
         int my_count = 0;
         // one thread per query; the first two keys not owned by an earlier query decide
 #pragma unroll
@@ -572,9 +609,17 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             if (lane == 0)
                 publish(q, b1, b2, my_count);
         }
-        if (my_count)
-            atomicAdd(&s_flag[1], my_count);
+        if (rounds == 2)
+            LVT_RDBG(25);
+        {
+            // one shared-memory atomic per warp: a thousand threads adding to one address serialise
+            const int warp_count = __reduce_add_sync(0xffffffffu, my_count);
+            if (lane == 0 && warp_count)
+                atomicAdd(&s_flag[1], warp_count);
+        }
         __syncthreads();
+        if (rounds == 2)
+            LVT_RDBG(26);
         int changed;
         if (nranks == 1)
         {
@@ -595,13 +640,23 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             if (threadIdx.x == 0)
             {
                 if (s_flag[0])
-                    atomicOr(slot, 1);
+                    dsmem_red_or(team.team_flags + 2 * (rounds % 3), 0, 1);
                 if (s_flag[1])
-                    atomicAdd(slot + 1, s_flag[1]);
+                    dsmem_red_add(team.team_flags + 2 * (rounds % 3) + 1, 0, s_flag[1]);
                 if (rank == 0)
                     team.team_flags[2 * ((rounds + 1) % 3)] = 0, team.team_flags[2 * ((rounds + 1) % 3) + 1] = 0;
             }
-            cl.sync(); // every claim of the round has landed in every replica
+            if (rounds == 2)
+                LVT_RDBG(27);
+            cl.sync(); // every claim of the round has landed in its home slice
+            if (rounds == 2)
+                LVT_RDBG(28);
+            // refresh the replica: warps read 32 consecutive owners of one home slice at a time
+            for (int f = threadIdx.x; f < n_f; f += blockDim.x)
+            {
+                const int h = f / slice;
+                cur[f] = dsmem_load(&home[rounds % 3][f - h * slice], (unsigned)h);
+            }
             if (threadIdx.x == 0)
             {
                 s_flag[5] = slot[0];
@@ -610,11 +665,6 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             __syncthreads();
             changed = s_flag[5];
             count = s_flag[6];
-            int *t = cur;
-            cur = nxt;
-            nxt = spare;
-            spare = t;
-            __syncthreads();
         }
         if (rounds < 12)
             LVT_RDBG(3 + rounds);

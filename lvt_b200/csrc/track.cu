@@ -15,6 +15,7 @@
 // (candidate generation, projection, Jacobians) is spread over many SMs.  No host round trip:
 // all control flow (first frame, lost, retry, policy) is decided on the device through FrameCtl.
 #include "track.cuh"
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -219,9 +220,8 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     RoundsTeam team;
     team.rank = rank;
     team.nranks = nranks;
-    team.owner_c = s_owner + 2 * a.owner_cap;
     team.team_flags = s_team_flags;
-    const int n_owner = nranks > 1 ? 3 : 2;
+    const int n_owner = 2;
     uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + n_owner * a.owner_cap);
     const int key_cap = a.key_cap - (n_owner - 2) * a.owner_cap;
 
@@ -817,7 +817,9 @@ static int ensure_smem(int owner_cap)
         LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const int avail = optin - 2048 /* static */ - 2 * owner_cap * (int)sizeof(int);
         g_key_cap = avail > 0 ? (avail / (int)sizeof(int)) & ~3 : 0;
-        g_track_cluster = g_key_cap >= owner_cap + 4096 ? kTrackCluster : 1; // the team needs a third owner array
+        g_track_cluster = kTrackCluster;
+        if (const char *e = std::getenv("LVT_B200_TRACK_CLUSTER")) // 1, 2, 4 or 8 (tuning aid)
+            g_track_cluster = std::max(1, std::min(8, std::atoi(e)));
         const int bytes = (int)track_smem_bytes(owner_cap);
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -877,11 +879,13 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     {
         static int calls = 0;
         if (calls == 0)
-            cudaMemset(a.dbg, 0, 24 * sizeof(long long));
+            cudaMemset(a.dbg, 0, 32 * sizeof(long long));
         if (++calls == 8)
         {
-            long long h[24];
+            long long h[32];
             cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "map pass round 2: wipe+sync %lld | evaluate %lld | count+sync %lld | forward flags %lld | cluster barrier %lld | read+rotate %lld\n",
+                         h[24] - h[4], h[25] - h[24], h[26] - h[25], h[27] - h[26], h[28] - h[27], h[5] - h[28]);
             std::fprintf(stderr, "map pass: n_fast %lld n_slow %lld smem keys %lld sum counts %lld max count %lld from global %lld\n", h[16],
                          h[17], h[18], h[19], h[20], h[21]);
             std::fprintf(stderr, "map pass: lists %lld | cache+reset %lld | rounds", h[1] - h[0], h[2] - h[1]);
