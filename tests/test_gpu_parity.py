@@ -367,3 +367,45 @@ def test_track_pool_equals_per_frame_calls(cuda, oracle):
     cuda.set_profiling(False)
     kt = cuda.kernel_times()
     assert kt["score_kernel"][1] == 2 and kt["track_a_kernel"][1] == 2 and kt["pose_kernel"][0] > 0
+
+
+@pytest.mark.gpu
+def test_blocking_calls_return_at_the_pose_and_stay_consistent(cuda, oracle):
+    """lvt_track returns when the pose is known and finishes the frame behind the call: status, lazily
+    collected frame info, interleaved handles, reset and a switch to the resident path must all agree
+    with the oracle"""
+    p = configs.make_params("kitti_synth")
+    n = 12
+    sa, sb = make_stream("kitti_synth", n, seed=1), make_stream("kitti_synth", n, seed=2)
+    ga, gb = cuda.create(p), cuda.create(p)      # two handles on one GPU, calls interleaved
+    oa, ob = oracle.create(p), oracle.create(p)
+    for t in range(n):
+        for g, o, st in ((ga, oa, sa), (gb, ob, sb)):
+            L, R = st.frame(t)
+            Rg, tg = g.track(L, R)
+            Ro, to = o.track(L, R)
+            assert g.get_state() == o.get_state()            # valid immediately
+            assert np.abs(tg - to).max() < 1e-6 and np.abs(Rg - Ro).max() < 1e-6
+            if t % 3 == 2:                                   # info only now and then: frames in between stay pending
+                assert g.frame_info() == o.frame_info(), t
+        if t == 6:                                           # reset one of them in mid-stream
+            ga.reset()
+            oa.reset()
+            assert ga.get_state() == capi.STATE_NOT_INITIALIZED
+    assert ga.frame_info() == oa.frame_info() and gb.frame_info() == ob.frame_info()
+    for g, o in ((ga, oa), (gb, ob)):
+        mg, mo = g.points(0), o.points(0)
+        assert np.array_equal(mg["desc"], mo["desc"]) and np.array_equal(mg["counter"], mo["counter"])
+        assert np.abs(mg["xyz"] - mo["xyz"]).max() < 1e-6
+    # continue handle b on the resident path: same map, same motion model
+    extra = make_stream("kitti_synth", n + 4, seed=2)
+    res = []
+    for vo in (gb, ob):
+        vo.pool_reserve(4)
+        for i in range(4):
+            vo.pool_upload(i, *extra.frame(n + i))
+        res.append(vo.track_pool(0, 4))
+    assert res[0][1] == res[1][1]
+    assert np.abs(res[0][0] - res[1][0]).max() < 1e-6
+    for vo in (ga, gb, oa, ob):
+        vo.destroy()
