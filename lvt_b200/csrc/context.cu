@@ -258,6 +258,7 @@ int make_detect_workspace(DetectWorkspace *ws, DeviceArena &arena, const TileGri
     rc = rc ? rc : arena.alloc(&ws->tile_overflow, nt);
     rc = rc ? rc : arena.alloc(&ws->big_list, nt * 64);
     rc = rc ? rc : arena.alloc(&ws->tile_out_count, nt);
+    rc = rc ? rc : arena.alloc(&ws->tiles_done, (size_t)batch);
     rc = rc ? rc : arena.alloc(&ws->cand_count, (size_t)batch);
     rc = rc ? rc : arena.alloc(&ws->retry, (size_t)batch);
     rc = rc ? rc : arena.alloc(&ws->error, 1);

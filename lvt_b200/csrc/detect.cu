@@ -38,6 +38,7 @@ struct ScoreArgs
     int pitch, rows, cols;
     int min_score; // scores below this are stored as 0
     int *tile_count, *tile_overflow; // [batch][n_tiles], zeroed here for the NMS that follows
+    int *tiles_done;                 // [batch], zeroed here: tile CTAs of the image that have finished
     int n_tiles;
 };
 
@@ -111,8 +112,12 @@ __global__ void __launch_bounds__(256) score_kernel(const __grid_constant__ CUte
 
     const int x0 = blockIdx.x * kScoreTileW, y0 = blockIdx.y * kScoreTileH, b = blockIdx.z;
     if (blockIdx.x == 0 && blockIdx.y == 0)
+    {
         for (int i = threadIdx.x; i < a.n_tiles; i += blockDim.x)
             a.tile_count[b * a.n_tiles + i] = a.tile_overflow[b * a.n_tiles + i] = 0;
+        if (threadIdx.x == 0)
+            a.tiles_done[b] = 0;
+    }
     if (threadIdx.x == 0)
     {
         mbar_init(&bar, 1);
@@ -841,6 +846,20 @@ __device__ void nms_fallback_tile(const NmsArgs &a, int *parent_all, int t, int 
 // ---------------------------------------------------------------------------------------------
 // K3: per-tile ordering + ANMS
 // ---------------------------------------------------------------------------------------------
+struct GatherArgs
+{
+    const uint32_t *tile_out;
+    const int *tile_out_count;
+    int *retry, *error;
+    int *tile_count, *tile_overflow; // zeroed for an image that goes into the lowered-threshold pass
+    int *tiles_done;                 // [batch] tile CTAs finished (the last one gathers)
+    FeatDev *feats;
+    int n_tiles, tile_cap, rows, cols;
+    int border;      // 28 = BRIEF filter, 0 = none
+    int pass;        // 0 first, 1 lowered threshold
+    int retry_below; // LVT_CORNERS_LOW_TH, or 0 to disable the retry
+};
+
 struct TileArgs
 {
     uint32_t *tile_list, *tile_aux, *tile_out;
@@ -851,6 +870,7 @@ struct TileArgs
     int tile_cap, n_tiles, max_per_cell;
     NmsArgs nms; // for the sequential NMS fallback
     int *parent;
+    GatherArgs gather; // the image's last tile CTA concatenates the tiles (gather_image)
 };
 
 constexpr int kTileSmemCap = 8192; // tiles with more survivors work out of global scratch
@@ -1229,11 +1249,121 @@ __device__ long long g_tile_trace[2048][12];
 #define TILE_PHASE(k)
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// K4: gather tiles -> image keypoint list (+ BRIEF border filter, + retry decision)
+// ---------------------------------------------------------------------------------------------
+
+// One CTA of 1024 threads per image: run by the LAST tile CTA of the image to finish (tile_kernel), so the
+// concatenation costs no launch of its own.  s_pref: 1025 ints, s_scan: 34 ints of shared memory.
+__device__ void gather_image(const GatherArgs &a, int b, int *s_pref, int *s_scan)
+{
+    const int nt = a.n_tiles; // <= 1024
+    if (threadIdx.x == 0)
+    {
+        int acc = 0;
+        for (int t = 0; t < nt; t++)
+        {
+            s_pref[t] = acc;
+            acc += a.tile_out_count[b * nt + t];
+        }
+        s_pref[nt] = acc;
+    }
+    __syncthreads();
+    const int total_in = s_pref[nt];
+    if (a.pass == 0)
+    {
+        const int redo = total_in < a.retry_below;
+        if (threadIdx.x == 0)
+            a.retry[b] = redo;
+        if (redo)
+        {
+            for (int t = threadIdx.x; t < nt; t += blockDim.x)
+                a.tile_count[b * nt + t] = a.tile_overflow[b * nt + t] = 0;
+            if (threadIdx.x == 0)
+                a.tiles_done[b] = 0; // the lowered-threshold pass counts its tiles again
+            return;
+        }
+    }
+    const FeatDev f = a.feats[b];
+    int running = 0;
+    for (int g0 = 0; g0 < total_in; g0 += blockDim.x)
+    {
+        const int g = g0 + threadIdx.x;
+        int keep = 0;
+        float x = 0, y = 0, r = 0;
+        if (g < total_in)
+        {
+            int lo = 0, hi = nt - 1; // last tile with s_pref[t] <= g
+            while (lo < hi)
+            {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_pref[mid] <= g)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const uint32_t e = a.tile_out[((size_t)b * nt + lo) * a.tile_cap + (g - s_pref[lo])];
+            const int xi = (e >> 8) & 0xFFF, yi = e >> 20;
+            x = (float)xi;
+            y = (float)yi;
+            r = (float)(e & 0xFF);
+            keep = a.border == 0 || (a.rows > 2 * a.border && a.cols > 2 * a.border && xi >= a.border &&
+                                     xi < a.cols - a.border && yi >= a.border && yi < a.rows - a.border);
+        }
+        int total;
+        const int pos = block_exclusive_scan(keep, s_scan, &total);
+        if (keep)
+        {
+            const int o = running + pos;
+            if (o < f.cap)
+            {
+                f.xy[o] = make_float2(x, y);
+                f.resp[o] = r;
+            }
+        }
+        running += total;
+    }
+    if (threadIdx.x == 0)
+    {
+        if (running > f.cap)
+        {
+            *a.error = LVTK_ERR_CAPACITY;
+            running = f.cap;
+        }
+        *f.n = running;
+    }
+}
+
+
 constexpr int kTileBitmapBits = 65536; // raster ranks by bitmap for tiles of up to 256 x 256 pixels
+
+__device__ void tile_body(const TileArgs &a);
 
 __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
 {
     LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
+    const int b = blockIdx.y;
+    if (a.retry && !a.retry[b])
+        return; // lowered-threshold pass of an image that does not need it
+    tile_body(a);
+    // the image's last tile CTA to get here concatenates the tiles (what used to be a kernel of its own)
+    __shared__ int s_last;
+    __shared__ int s_pref[1025];
+    __shared__ int s_gscan[34];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&a.gather.tiles_done[b], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last)
+    {
+        __threadfence();
+        gather_image(a.gather, b, s_pref, s_gscan);
+    }
+}
+
+__device__ void tile_body(const TileArgs &a)
+{
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t *s_keys = s_dyn, *s_rad = s_dyn + kTileSmemCap, *s_perm = s_dyn + 2 * kTileSmemCap;
     isort::LevelRange *s_q0 = reinterpret_cast<isort::LevelRange *>(s_dyn + 3 * kTileSmemCap), *s_q1 = s_q0 + kTileRanges;
@@ -1561,105 +1691,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: gather tiles -> image keypoint list (+ BRIEF border filter, + retry decision)
-// ---------------------------------------------------------------------------------------------
-struct GatherArgs
-{
-    const uint32_t *tile_out;
-    const int *tile_out_count;
-    int *retry, *error;
-    int *tile_count, *tile_overflow; // zeroed for an image that goes into the lowered-threshold pass
-    FeatDev *feats;
-    int n_tiles, tile_cap, rows, cols;
-    int border;      // 28 = BRIEF filter, 0 = none
-    int pass;        // 0 first, 1 lowered threshold
-    int retry_below; // LVT_CORNERS_LOW_TH, or 0 to disable the retry
-};
-
-__global__ void __launch_bounds__(1024) gather_kernel(GatherArgs a)
-{
-    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
-    __shared__ int s_pref[1025];
-    __shared__ int s_scan[34];
-    const int b = blockIdx.x;
-    if (a.pass == 1 && !a.retry[b])
-        return;
-    const int nt = a.n_tiles; // <= 1024
-    if (threadIdx.x == 0)
-    {
-        int acc = 0;
-        for (int t = 0; t < nt; t++)
-        {
-            s_pref[t] = acc;
-            acc += a.tile_out_count[b * nt + t];
-        }
-        s_pref[nt] = acc;
-    }
-    __syncthreads();
-    const int total_in = s_pref[nt];
-    if (a.pass == 0)
-    {
-        const int redo = total_in < a.retry_below;
-        if (threadIdx.x == 0)
-            a.retry[b] = redo;
-        if (redo)
-        {
-            for (int t = threadIdx.x; t < nt; t += blockDim.x)
-                a.tile_count[b * nt + t] = a.tile_overflow[b * nt + t] = 0;
-            return;
-        }
-    }
-    const FeatDev f = a.feats[b];
-    int running = 0;
-    for (int g0 = 0; g0 < total_in; g0 += blockDim.x)
-    {
-        const int g = g0 + threadIdx.x;
-        int keep = 0;
-        float x = 0, y = 0, r = 0;
-        if (g < total_in)
-        {
-            int lo = 0, hi = nt - 1; // last tile with s_pref[t] <= g
-            while (lo < hi)
-            {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_pref[mid] <= g)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const uint32_t e = a.tile_out[((size_t)b * nt + lo) * a.tile_cap + (g - s_pref[lo])];
-            const int xi = (e >> 8) & 0xFFF, yi = e >> 20;
-            x = (float)xi;
-            y = (float)yi;
-            r = (float)(e & 0xFF);
-            keep = a.border == 0 || (a.rows > 2 * a.border && a.cols > 2 * a.border && xi >= a.border &&
-                                     xi < a.cols - a.border && yi >= a.border && yi < a.rows - a.border);
-        }
-        int total;
-        const int pos = block_exclusive_scan(keep, s_scan, &total);
-        if (keep)
-        {
-            const int o = running + pos;
-            if (o < f.cap)
-            {
-                f.xy[o] = make_float2(x, y);
-                f.resp[o] = r;
-            }
-        }
-        running += total;
-    }
-    if (threadIdx.x == 0)
-    {
-        if (running > f.cap)
-        {
-            *a.error = LVTK_ERR_CAPACITY;
-            running = f.cap;
-        }
-        *f.n = running;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
 int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const DetectParams &dp, const int *d_slots,
@@ -1677,7 +1708,7 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     const bool allow_retry = dp.threshold_low < dp.threshold;
 
     ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold,
-                 ws.tile_count, ws.tile_overflow, nt};
+                 ws.tile_count, ws.tile_overflow, ws.tiles_done, nt};
     dim3 sgrid((dp.cols + kScoreTileW - 1) / kScoreTileW, (dp.rows + kScoreTileH - 1) / kScoreTileH, n_images);
     LVT_TIMED(stream, K_SCORE, launch_chained(score_kernel, sgrid, dim3(256), 0, stream, pool.tmap_score, sa));
     LVT_LAUNCH_CHECK(stream, "score_kernel");
@@ -1693,14 +1724,12 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
         dim3 ngrid((dp.cols + kNmsTile - 1) / kNmsTile, (dp.rows + kNmsTile - 1) / kNmsTile, n_images);
         LVT_TIMED(stream, K_NMS, launch_chained(nms_tile_kernel, ngrid, dim3(256), 0, stream, na));
         LVT_LAUNCH_CHECK(stream, "nms_tile_kernel");
+        GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, ws.tile_count, ws.tile_overflow, ws.tiles_done, d_feats,
+                      nt, ws.tile_cap, dp.rows, dp.cols, border, pass, allow_retry ? kCornersLowTh : 0};
         TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count,   ws.tile_out_count, retry,
-                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell, na,                ws.parent};
+                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell, na,                ws.parent, ga};
         LVT_TIMED(stream, K_TILE, launch_chained(tile_kernel, dim3(nt, n_images), dim3(kTileThreads), kTileSmemBytes, stream, ta));
         LVT_LAUNCH_CHECK(stream, "tile_kernel");
-        GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, ws.tile_count, ws.tile_overflow, d_feats, nt,
-                      ws.tile_cap, dp.rows,           dp.cols,  border,   pass,          allow_retry ? kCornersLowTh : 0};
-        LVT_TIMED(stream, K_GATHER, launch_chained(gather_kernel, dim3(n_images), dim3(1024), 0, stream, ga));
-        LVT_LAUNCH_CHECK(stream, "gather_kernel");
     }
     LVT_CUDA_TRY(cudaGetLastError());
     return LVTK_OK;

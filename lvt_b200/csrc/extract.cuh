@@ -75,6 +75,7 @@ struct DetectWorkspace
     int *tile_overflow = nullptr;    // [batch][n_tiles]  big candidates queued for tile_kernel | sequential-fallback flag
     uint32_t *big_list = nullptr;    // [batch][n_tiles][64] local maxima of components beyond the NMS kernel's buffers
     int *tile_out_count = nullptr;   // [batch][n_tiles]
+    int *tiles_done = nullptr;       // [batch] tile CTAs of the image that have finished (the last one gathers)
     int *cand_count = nullptr;       // [batch] local maxima queued for nms_resolve_kernel (list lives in `parent`)
     int *retry = nullptr;            // [batch] fewer than 200 corners: redo at the lowered threshold
     int *error = nullptr;            // [1] sticky capacity error flag

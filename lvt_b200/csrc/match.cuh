@@ -272,12 +272,14 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void *local, unsigned rank)
 __device__ __forceinline__ int dsmem_load(const int *local, unsigned rank)
 {
     int v;
-    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(dsmem_addr(local, rank)) : "memory");
+    // volatile keeps it in program order with the cluster barrier (also a volatile asm); no memory clobber, so
+    // that independent loads of one thread are in flight together
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(dsmem_addr(local, rank)));
     return v;
 }
 __device__ __forceinline__ void dsmem_red_min(int *local, unsigned rank, int v)
 {
-    asm volatile("red.relaxed.cluster.shared::cluster.min.s32 [%0], %1;" ::"r"(dsmem_addr(local, rank)), "r"(v) : "memory");
+    asm volatile("red.relaxed.cluster.shared::cluster.min.s32 [%0], %1;" ::"r"(dsmem_addr(local, rank)), "r"(v));
 }
 __device__ __forceinline__ void dsmem_red_add(int *local, unsigned rank, int v)
 {
@@ -329,8 +331,13 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int *cur = owner_a, *nxt = owner_b;
     // team: three generations of this CTA's home slice live where the single-CTA path keeps `nxt`
-    const int slice = (((n_f + nranks - 1) / nranks) + 31) & ~31, home0 = rank * slice;
-    int *home[3] = {owner_b, owner_b + slice, owner_b + 2 * slice};
+    // (slice length: a power of two >= 32, so that the home of a feature is a shift)
+    int slice_log2 = 5;
+    while ((nranks << slice_log2) < n_f)
+        slice_log2++;
+    const int slice = 1 << slice_log2, home0 = rank * slice;
+    auto home = [&](int generation) { return owner_b + (generation % 3) * slice; };
+    int *home_now = owner_b; // this round's generation (hoisted out of the per-query path)
     int *fast = items + (size_t)rank * n_loc, *slow_items = items + (size_t)(nranks + rank) * n_loc;
     if (threadIdx.x == 0)
     {
@@ -344,7 +351,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         const int v = (marks && marks[j]) ? kTaken : kFree;
         cur[j] = v;
         if (nranks > 1 && j >= home0 && j < home0 + slice)
-            home[0][j - home0] = v; // the first round finds its home slices clean (later ones: cleared a round ahead)
+            home(0)[j - home0] = v; // the first round finds its home slices clean (later ones: cleared a round ahead)
     }
     if (nranks > 1)
         cgr::this_cluster().sync(); // every replica initialised (and every CTA running) before the first remote store
@@ -394,8 +401,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             atomicMin(&nxt[c], q);
         else
         {
-            const int h = c / slice;
-            dsmem_red_min(&home[rounds % 3][c - h * slice], (unsigned)h, q);
+            const int h = c >> slice_log2;
+            dsmem_red_min(home_now + (c & (slice - 1)), (unsigned)h, q);
         }
     };
     // `prev` = the query's choice of the previous round (a register copy for the cached queries)
@@ -545,8 +552,12 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             for (int j = threadIdx.x; j < n_f; j += blockDim.x)
                 nxt[j] = cur[j] == kTaken ? kTaken : kFree;
         else
+        {
+            home_now = home(rounds);
+            int *next_gen = home(rounds + 1);
             for (int j = threadIdx.x; j < slice && home0 + j < n_f; j += blockDim.x)
-                home[(rounds + 1) % 3][j] = cur[home0 + j] == kTaken ? kTaken : kFree;
+                next_gen[j] = cur[home0 + j] == kTaken ? kTaken : kFree;
+        }
         if (threadIdx.x == 0)
             s_flag[0] = 0, s_flag[1] = 0;
         __syncthreads();
@@ -636,35 +647,33 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             // the NEXT round's slot here: its last readers (two rounds ago) are past the previous barrier,
             // its next writers come after the barrier below.
             cgr::cluster_group cl = cgr::this_cluster();
-            int *slot = cl.map_shared_rank(team.team_flags + 2 * (rounds % 3), 0);
+            int *slot = team.team_flags + 2 * (rounds % 3);
             if (threadIdx.x == 0)
             {
-                if (s_flag[0])
-                    dsmem_red_or(team.team_flags + 2 * (rounds % 3), 0, 1);
-                if (s_flag[1])
-                    dsmem_red_add(team.team_flags + 2 * (rounds % 3) + 1, 0, s_flag[1]);
+                // one reduction per CTA and round: (CTAs that saw a change) << 24 | matches
+                const int word = (s_flag[0] ? (1 << 24) : 0) + s_flag[1];
+                if (word)
+                    dsmem_red_add(slot, 0, word);
                 if (rank == 0)
-                    team.team_flags[2 * ((rounds + 1) % 3)] = 0, team.team_flags[2 * ((rounds + 1) % 3) + 1] = 0;
+                    team.team_flags[2 * ((rounds + 1) % 3)] = 0;
             }
             if (rounds == 2)
                 LVT_RDBG(27);
             cl.sync(); // every claim of the round has landed in its home slice
             if (rounds == 2)
                 LVT_RDBG(28);
-            // refresh the replica: warps read 32 consecutive owners of one home slice at a time
-            for (int f = threadIdx.x; f < n_f; f += blockDim.x)
-            {
-                const int h = f / slice;
-                cur[f] = dsmem_load(&home[rounds % 3][f - h * slice], (unsigned)h);
-            }
+            // the round's flags and the refresh of the replica (warps read 32 consecutive owners of one home
+            // slice at a time) travel together
+            int word = 0;
             if (threadIdx.x == 0)
-            {
-                s_flag[5] = slot[0];
-                s_flag[6] = slot[1];
-            }
+                word = dsmem_load(slot, 0);
+            for (int f = threadIdx.x; f < n_f; f += blockDim.x)
+                cur[f] = dsmem_load(home_now + (f & (slice - 1)), (unsigned)(f >> slice_log2));
+            if (threadIdx.x == 0)
+                s_flag[5] = word;
             __syncthreads();
-            changed = s_flag[5];
-            count = s_flag[6];
+            changed = s_flag[5] >> 24;
+            count = s_flag[5] & 0xFFFFFF;
         }
         if (rounds < 12)
             LVT_RDBG(3 + rounds);

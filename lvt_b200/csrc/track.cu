@@ -818,8 +818,8 @@ static int ensure_smem(int owner_cap)
         const int avail = optin - 2048 /* static */ - 2 * owner_cap * (int)sizeof(int);
         g_key_cap = avail > 0 ? (avail / (int)sizeof(int)) & ~3 : 0;
         g_track_cluster = kTrackCluster;
-        if (const char *e = std::getenv("LVT_B200_TRACK_CLUSTER")) // 1, 2, 4 or 8 (tuning aid)
-            g_track_cluster = std::max(1, std::min(8, std::atoi(e)));
+        if (const char *e = std::getenv("LVT_B200_TRACK_CLUSTER")) // 1 or 8 (tuning aid; the home slices of the
+            g_track_cluster = std::atoi(e) >= 8 ? 8 : 1;             // team are sized for 8 CTAs)
         const int bytes = (int)track_smem_bytes(owner_cap);
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
