@@ -871,6 +871,7 @@ struct TileArgs
     NmsArgs nms; // for the sequential NMS fallback
     int *parent;
     GatherArgs gather; // the image's last tile CTA concatenates the tiles (gather_image)
+    int grid_min;      // corners per tile from which the suppression radii use the cell grid
 };
 
 constexpr int kTileSmemCap = 8192; // tiles with more survivors work out of global scratch
@@ -1335,17 +1336,24 @@ __device__ void gather_image(const GatherArgs &a, int b, int *s_pref, int *s_sca
 }
 
 
+constexpr int kTileGridMin = 1024;      // corners per tile from which the suppression radii use the cell grid
+constexpr int kTileGridMinPrefix = 192; // ... for corners with at least this many stronger corners (shorter prefixes: direct scan)
 constexpr int kTileBitmapBits = 65536; // raster ranks by bitmap for tiles of up to 256 x 256 pixels
 
 __device__ void tile_body(const TileArgs &a);
 
 __global__ void __launch_bounds__(kTileThreads, 1) tile_kernel(TileArgs a)
 {
-    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
+    // Wait for the previous kernel, but do NOT release the next one yet: the kernel behind this one is the
+    // second NMS pass, hundreds of CTAs with 42 KB of shared memory each, which would sit on every SM
+    // (waiting for this grid to finish) for as long as the slowest tile takes and keep the other
+    // extraction pipelines of lvt_track_pool off the machine.  It is released after the tile work.
+    cudaGridDependencySynchronize();
     const int b = blockIdx.y;
     if (a.retry && !a.retry[b])
         return; // lowered-threshold pass of an image that does not need it
     tile_body(a);
+    cudaTriggerProgrammaticLaunchCompletion();
     // the image's last tile CTA to get here concatenates the tiles (what used to be a kernel of its own)
     __shared__ int s_last;
     __shared__ int s_pref[1025];
@@ -1548,6 +1556,45 @@ __device__ void tile_body(const TileArgs &a)
     }
     __syncthreads();
     TILE_PHASE(4);
+    // Tiles with many corners: a uniform grid over the tile (at most 32 x 32 cells of 2^gs >= 8 pixels; cell
+    // lists of sort positions, any order -- a minimum does not care) turns the search for the nearest
+    // stronger corner into a walk over rings of cells around the corner's own cell, which stops as soon as
+    // the best distance found cannot be beaten from outside the rings visited so far.  The memory of the
+    // introsort schedule is free by now: start[1025] | cursor[1024] | items u16[kTileSmemCap].
+    const bool use_grid = small && n >= a.grid_min;
+    int gs = 3; // cells of 8 pixels, or the smallest power of two that keeps the grid within 32 x 32 cells
+    while ((tw >> gs) >= 32 || (th >> gs) >= 32)
+        gs++;
+    const int gx = (tw >> gs) + 1, gy = (th >> gs) + 1, ncell = gx * gy;
+    int *g_start = reinterpret_cast<int *>(s_q0), *g_cursor = g_start + 1025;
+    uint16_t *g_items = reinterpret_cast<uint16_t *>(g_cursor + 1024);
+    if (use_grid)
+    {
+        auto cell_of = [&](uint32_t k) { return (int)((k >> 20) >> gs) * gx + (int)(((k >> 8) & 0xFFFu) >> gs); };
+        for (int c = threadIdx.x; c < 1024; c += blockDim.x)
+            g_cursor[c] = 0;
+        __syncthreads();
+        for (int p = threadIdx.x; p < n; p += blockDim.x)
+            atomicAdd(&g_cursor[cell_of(sorted_key(p))], 1);
+        __syncthreads();
+        {
+            // ncell <= 1024 == blockDim.x: one cell per thread
+            const int mine = (int)threadIdx.x < ncell ? g_cursor[threadIdx.x] : 0;
+            int total;
+            const int ex = block_exclusive_scan(mine, s_scan, &total);
+            if ((int)threadIdx.x < ncell)
+            {
+                g_start[threadIdx.x] = ex;
+                g_cursor[threadIdx.x] = ex;
+            }
+            if (threadIdx.x == 0)
+                g_start[ncell] = total;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < n; p += blockDim.x)
+            g_items[atomicAdd(&g_cursor[cell_of(sorted_key(p))], 1)] = (uint16_t)p;
+        __syncthreads();
+    }
     // :52-64  radius^2 = min squared distance to any corner with response > 1.11f * own.  In the sorted
     // order those corners are a prefix; eight lanes share one corner's prefix.
     for (int w = threadIdx.x; w < 8 * n; w += blockDim.x) // blockDim.x is a multiple of 8: whole groups stay together
@@ -1560,7 +1607,55 @@ __device__ void tile_body(const TileArgs &a)
         const int prefix_len = need > 255 ? 0 : s_hist[need];
         const int yi = (int)(ki >> 20), xi = (int)((ki >> 8) & 0xFFFu);
         uint32_t best = 0xFFFFFFFFu; // FLT_MAX
-        if (byte_xy)
+        const unsigned group8 = 0xFFu << ((threadIdx.x & 31) & ~7);
+        if (use_grid && prefix_len > kTileGridMinPrefix)
+        {
+            const int cxi = xi >> gs, cyi = yi >> gs;
+            for (int r = 0;; r++)
+            {
+                // ring r = border of the square of cells [cxi - r, cxi + r] x [cyi - r, cyi + r]; the lanes
+                // of the group take its cells in turn
+                const int side = 2 * r + 1, ring_cells = r == 0 ? 1 : 8 * r;
+                for (int c = part; c < ring_cells; c += 8)
+                {
+                    int ox = 0, oy = 0;
+                    if (r > 0)
+                    {
+                        if (c < side)
+                            ox = c - r, oy = -r;
+                        else if (c < 2 * side)
+                            ox = c - side - r, oy = r;
+                        else if (c < 3 * side - 2)
+                            ox = -r, oy = c - 2 * side - r + 1;
+                        else
+                            ox = r, oy = c - (3 * side - 2) - r + 1;
+                    }
+                    const int cx = cxi + ox, cy = cyi + oy;
+                    if ((unsigned)cx >= (unsigned)gx || (unsigned)cy >= (unsigned)gy)
+                        continue;
+                    const int t1 = g_start[cy * gx + cx + 1];
+                    for (int t = g_start[cy * gx + cx]; t < t1; t++)
+                    {
+                        const int j = g_items[t];
+                        if (j >= prefix_len)
+                            continue; // not stronger by the 1.11 margin
+                        const uint32_t kj = sorted_key(j);
+                        const int dx = xi - (int)((kj >> 8) & 0xFFFu), dy = yi - (int)(kj >> 20);
+                        best = min(best, (uint32_t)(dx * dx + dy * dy));
+                    }
+                }
+                uint32_t gbest = min(best, __shfl_xor_sync(group8, best, 1));
+                gbest = min(gbest, __shfl_xor_sync(group8, gbest, 2));
+                gbest = min(gbest, __shfl_xor_sync(group8, gbest, 4));
+                // a corner outside the rings visited so far is more than r cells away along x or y
+                const uint32_t reach = (uint32_t)r << gs;
+                if (gbest <= reach * reach)
+                    break;
+                if (cxi - r <= 0 && cyi - r <= 0 && cxi + r >= gx - 1 && cyi + r >= gy - 1)
+                    break; // the whole grid has been visited
+            }
+        }
+        else if (byte_xy)
         {
             const uint32_t me = xyb[p];
             auto dist2 = [me](uint32_t other) -> uint32_t {
@@ -1693,6 +1788,12 @@ __device__ void tile_body(const TileArgs &a)
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
+static int tile_grid_min()
+{
+    static const int v = std::getenv("LVT_B200_TILE_GRID_MIN") ? std::atoi(std::getenv("LVT_B200_TILE_GRID_MIN")) : kTileGridMin;
+    return v;
+}
+
 int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const DetectParams &dp, const int *d_slots,
                   int n_images, FeatDev *d_feats, int border, int nonmax, cudaStream_t stream)
 {
@@ -1727,7 +1828,7 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
         GatherArgs ga{ws.tile_out, ws.tile_out_count, ws.retry, ws.error, ws.tile_count, ws.tile_overflow, ws.tiles_done, d_feats,
                       nt, ws.tile_cap, dp.rows, dp.cols, border, pass, allow_retry ? kCornersLowTh : 0};
         TileArgs ta{ws.tile_list, ws.tile_aux, ws.tile_out, ws.tile_count,   ws.tile_out_count, retry,
-                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell, na,                ws.parent, ga};
+                    dp.grid,      ws.tile_cap, nt,          dp.max_per_cell, na,                ws.parent, ga, tile_grid_min()};
         LVT_TIMED(stream, K_TILE, launch_chained(tile_kernel, dim3(nt, n_images), dim3(kTileThreads), kTileSmemBytes, stream, ta));
         LVT_LAUNCH_CHECK(stream, "tile_kernel");
     }
