@@ -90,12 +90,16 @@ inline cudaError_t launch_chained_cluster(void (*kernel)(KArgs...), dim3 grid, d
 {
     return launch_chained_impl<KArgs...>(kernel, grid, block, smem, stream, cluster, static_cast<KArgs>(args)...);
 }
+#ifdef LVT_NO_EARLY_TRIGGER
+#define LVT_GRID_DEP_SYNC() cudaGridDependencySynchronize()
+#else
 #define LVT_GRID_DEP_SYNC()                                                                                           \
     do                                                                                                                \
     {                                                                                                                 \
         cudaGridDependencySynchronize();                                                                              \
         cudaTriggerProgrammaticLaunchCompletion();                                                                    \
     } while (0)
+#endif
 
 #define LVT_TIMED(stream, id, launch)                                                                                 \
     do                                                                                                                \
