@@ -965,8 +965,11 @@ struct System
             const int want = c->early_seq;
             unsigned spins = 0;
             while (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+            {
                 if ((++spins & 0xFFFu) == 0 && cudaEventQuery(c->ev_pose) != cudaErrorNotReady)
                     break;
+                LVT_CPU_RELAX();
+            }
             if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
             {
                 LVT_CUDA_TRY(cudaEventSynchronize(c->ev_pose));

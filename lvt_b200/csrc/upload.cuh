@@ -21,6 +21,12 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define LVT_CPU_RELAX() _mm_pause()
+#else
+#define LVT_CPU_RELAX() ((void)0)
+#endif
 
 namespace lvtb
 {
@@ -127,6 +133,7 @@ class UploadLanes
                 {
                     if (!wait)
                         return;
+                    LVT_CPU_RELAX();
                     continue; // a helper is at most one band behind
                 }
                 const UploadBand &b = bands_[sent];
@@ -176,7 +183,10 @@ class UploadLanes
             if (generation_.load(std::memory_order_acquire) == seen)
             {
                 if (std::chrono::steady_clock::now() - last_job < std::chrono::microseconds(kSpinMicros))
+                {
+                    LVT_CPU_RELAX();
                     continue; // spin: the next frame usually follows at once
+                }
                 std::unique_lock<std::mutex> lk(mu_);
                 parked_.fetch_add(1);
                 cv_.wait(lk, [&] { return generation_.load() != seen; });
