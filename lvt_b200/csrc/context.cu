@@ -531,7 +531,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
             return rc;
     int rc = c->arena.alloc(&c->feats_d, 2 * lvtk_ctx::kSets);
     rc = rc ? rc : c->arena.alloc(&c->d_slots, 4);
-    rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)p.img_width * p.img_height);
+    rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)2 * p.img_width * p.img_height); // two alternating frames
     rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->d_in_resp, (size_t)2 * c->pcap);
     rc = rc ? rc : c->arena.alloc(&c->d_in_n, 2);
@@ -575,7 +575,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     LVT_CUDA_TRY(cudaMemcpy(c->d_slots, slots, sizeof(slots), cudaMemcpyHostToDevice));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_stage, (size_t)n_slots * c->pool.pitch * p.img_height));
     std::memset(c->h_stage, 0, (size_t)n_slots * c->pool.pitch * p.img_height);
-    LVT_CUDA_TRY(cudaMallocHost(&c->h_depth, sizeof(float) * (size_t)p.img_width * p.img_height));
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_depth, sizeof(float) * (size_t)2 * p.img_width * p.img_height));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_result, sizeof(FrameResult)));
     LVT_CUDA_TRY(cudaMallocHost(&c->h_error, sizeof(int)));
     LVT_CUDA_TRY(cudaHostAlloc(&c->h_early, sizeof(EarlyResult), cudaHostAllocMapped));
@@ -872,6 +872,30 @@ struct System
         return LVTK_OK;
     }
 
+    // the pose solver stores its result straight into pinned host memory, sequence number last
+    int wait_for_pose()
+    {
+        lvtk_ctx *c = ctx;
+        const int want = c->early_seq;
+        unsigned spins = 0;
+        while (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+        {
+            if ((++spins & 0xFFFu) == 0 && cudaEventQuery(c->ev_pose) != cudaErrorNotReady)
+                break;
+            LVT_CPU_RELAX();
+        }
+        if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+        {
+            LVT_CUDA_TRY(cudaEventSynchronize(c->ev_pose));
+            if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
+            {
+                set_last_error(__FILE__, __LINE__, "the pose solver did not report");
+                return LVTK_ERR_CUDA;
+            }
+        }
+        return LVTK_OK;
+    }
+
     // Blocking stereo frame.  Only the left image is on the path to the pose (map matching and the
     // solver never look at the right one), so the two images go down two streams: the left one is
     // staged, uploaded and extracted first and the tracking kernels up to the pose solver are queued
@@ -960,26 +984,8 @@ struct System
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_frame, st));
         host_mark(2);
-        {
-            // the pose solver stores its result straight into pinned host memory, sequence number last
-            const int want = c->early_seq;
-            unsigned spins = 0;
-            while (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
-            {
-                if ((++spins & 0xFFFu) == 0 && cudaEventQuery(c->ev_pose) != cudaErrorNotReady)
-                    break;
-                LVT_CPU_RELAX();
-            }
-            if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
-            {
-                LVT_CUDA_TRY(cudaEventSynchronize(c->ev_pose));
-                if (__atomic_load_n(&c->h_early->seq, __ATOMIC_ACQUIRE) != want)
-                {
-                    set_last_error(__FILE__, __LINE__, "the pose solver did not report");
-                    return LVTK_ERR_CUDA;
-                }
-            }
-        }
+        if (int rc = wait_for_pose())
+            return rc;
         host_mark(3);
         if (timeline)
         {
@@ -1043,29 +1049,73 @@ struct System
         return finish(out);
     }
 
+    // Blocking RGB-D frame, the same shape as track_stereo: the gray image is staged, uploaded and
+    // extracted first; the depth image (4 bytes per pixel, the bulk of the upload) is staged and uploaded
+    // on a second stream meanwhile and is needed only by the depth gate behind the descriptors; the call
+    // returns at the pose, the map maintenance finishes behind it on alternating buffer sets.
     int track_rgbd(const uint8_t *gray, const float *depth, int rows, int cols, PoseD *out)
     {
         lvtk_ctx *c = ctx;
         if (rows != c->params.img_height || cols != c->params.img_width)
             return LVTK_ERR_ARG;
-        if (int rc = finish_pending())
-            return rc;
         if (lost_shortcut(out))
             return LVTK_OK;
+        const bool first_frame = state == 1;
+        if (pending && cudaEventQuery(c->ev_frame) == cudaSuccess)
+            if (int rc = finish_pending())
+                return rc;
+        const int s = c->parity;
+        c->parity ^= 1;
+        cudaStream_t xl = c->xs[0], xr = c->xs[1], st = c->stream;
+        FeatDev *feats = c->feats_d + 2 * s;
+        const int *slots = c->d_slots + 2 * s;
+        const size_t npx = (size_t)rows * cols;
+        float *h_depth = c->h_depth + s * npx, *d_depth = c->d_depth + s * npx;
         host_mark(0);
-        ctx_stage_image(c, 0, gray, rows, cols, cols);
-        c->lanes.add_image(depth, sizeof(float) * (size_t)cols, c->h_depth, c->d_depth, sizeof(float) * (size_t)cols,
-                           sizeof(float) * (size_t)cols, rows, 2 * c->upload_bands);
-        if (int rc = ctx_stage_flush(c))
+        c->last_set = s;
+        ctx_stage_image(c, 2 * s, gray, rows, cols, cols);
+        if (int rc = ctx_stage_flush(c, xl))
             return rc;
+        if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, slots, 1, feats, kBriefBorder, 1, xl))
+            return rc;
+        if (int rc = launch_brief(c->pool, slots, 1, feats, xl))
+            return rc;
+        c->lanes.add_image(depth, sizeof(float) * (size_t)cols, h_depth, d_depth, sizeof(float) * (size_t)cols,
+                           sizeof(float) * (size_t)cols, rows, 2 * c->upload_bands, 2);
+        if (int rc = ctx_stage_flush(c, xr))
+            return rc;
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_right, xr));
         host_mark(1);
-        if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, c->stream))
+        LVT_CUDA_TRY(cudaStreamWaitEvent(xl, c->ev_right, 0)); // the depth image has arrived
+        if (int rc = launch_depth_gate(c->feats_h[2 * s], d_depth, c->params, xl))
             return rc;
-        if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
+        if (int rc = launch_index(feats, 1, c->cam, xl))
             return rc;
-        if (int rc = launch_depth_gate(c->feats_h[0], c->d_depth, c->params, c->stream))
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_left, xl));
+        LVT_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_left, 0));
+        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc, c->row_cand[s],
+                                        c->fcap, st, nullptr, 1, c->d_early, ++c->early_seq))
             return rc;
-        return finish(out);
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
+        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc, c->row_cand[s],
+                                        c->fcap, st, nullptr, 2, nullptr))
+            return rc;
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_frame, st));
+        host_mark(2);
+        if (int rc = wait_for_pose())
+            return rc;
+        host_mark(3);
+        pending = true;
+        const PoseD pose = c->h_early->pose;
+        state = c->h_early->state;
+        info.state = state;
+        info.frame_number = frame_number;
+        if (!first_frame && state == 2)
+            last_pose = pose;
+        *out = pose;
+        return LVTK_OK;
     }
 
     // ---- resident pool: frames already in HBM, extraction of frame t+1 overlapped with tracking of t
