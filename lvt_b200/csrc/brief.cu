@@ -247,11 +247,13 @@ bool brief_can_index(const CamParams &cam) { return index_smem_ints(cam) * (int)
 int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream,
                  const CamParams *index_cam)
 {
-    static bool smem_set = false;
-    if (!smem_set)
+    static int smem_set_dev = -1; // function attributes are per device
+    int cur_dev = 0;
+    LVT_CUDA_TRY(cudaGetDevice(&cur_dev));
+    if (smem_set_dev != cur_dev)
     {
         LVT_CUDA_TRY(cudaFuncSetAttribute(brief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBriefSmem));
-        smem_set = true;
+        smem_set_dev = cur_dev;
     }
     BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols, 0, CamParams{}};
     if (index_cam)

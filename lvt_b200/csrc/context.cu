@@ -353,6 +353,7 @@ CamParams make_cam_params(const lvt_params_c &p)
     return c;
 }
 
+static int g_pairs_uploaded_dev = -1; // device whose __device__ table holds the current pairs
 static bool g_pairs_uploaded = false;
 static signed char g_pairs[256][4];
 static bool g_pairs_custom = false;
@@ -599,11 +600,12 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
             c->upload_dmas = std::max(1, std::min(16, std::atoi(e)));
         c->lanes.start(c->device, lanes - 1);
     }
-    if (!g_pairs_uploaded)
+    if (!g_pairs_uploaded || g_pairs_uploaded_dev != c->device)
     {
         if (int r2 = upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr))
             return r2;
         g_pairs_uploaded = true;
+        g_pairs_uploaded_dev = c->device;
     }
     LVT_CUDA_TRY(cudaDeviceSynchronize()); // the arena's memsets ran on the default stream
     if (int r3 = launch_reset_state(c->d_state, c->stream))

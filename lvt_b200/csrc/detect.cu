@@ -1800,11 +1800,13 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     if (n_images > ws.batch || dp.grid.count() != ws.n_tiles || ws.n_tiles > 1024)
         return LVTK_ERR_ARG;
     const int nt = ws.n_tiles;
-    static bool smem_set = false;
-    if (!smem_set)
+    static int smem_set_dev = -1; // function attributes are per device
+    int cur_dev = 0;
+    LVT_CUDA_TRY(cudaGetDevice(&cur_dev));
+    if (smem_set_dev != cur_dev)
     {
         LVT_CUDA_TRY(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-        smem_set = true;
+        smem_set_dev = cur_dev;
     }
     const bool allow_retry = dp.threshold_low < dp.threshold;
 

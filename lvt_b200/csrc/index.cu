@@ -24,7 +24,14 @@ __global__ void __launch_bounds__(1024) index_kernel(IndexArgs a)
 int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cudaStream_t stream)
 {
     const int bytes = index_smem_ints(cam) * (int)sizeof(int);
-    static int configured = 0;
+    static int configured = 0, configured_dev = -1; // function attributes are per device
+    int cur_dev = 0;
+    LVT_CUDA_TRY(cudaGetDevice(&cur_dev));
+    if (cur_dev != configured_dev)
+    {
+        configured = 0;
+        configured_dev = cur_dev;
+    }
     if (bytes > configured)
     {
         LVT_CUDA_TRY(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));

@@ -803,17 +803,24 @@ __global__ void tri_seam_kernel(TriSeamArgs a)
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory of the single-CTA kernels: two owner arrays + as many candidate keys as fit
 // next to them (block_rounds keeps the key lists of its queries there)
+// (function attributes are per device: the caches below are reset when the calling thread's device changes)
 static int g_key_cap = 0;
-static int g_track_cluster = 1; // CTAs of track_a_kernel's cluster (1 when three owner arrays do not fit in shared memory)
+static int g_track_cluster = 1; // CTAs of track_a_kernel's cluster
 static size_t track_smem_bytes(int owner_cap) { return (2 * (size_t)owner_cap + (size_t)g_key_cap) * sizeof(int); }
 
 static int ensure_smem(int owner_cap)
 {
-    static int configured = 0;
+    static int configured = 0, configured_dev = -1;
+    int dev = 0;
+    LVT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != configured_dev)
+    {
+        configured = 0;
+        configured_dev = dev;
+    }
     if (owner_cap > configured)
     {
-        int dev = 0, optin = 0;
-        LVT_CUDA_TRY(cudaGetDevice(&dev));
+        int optin = 0;
         LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const int avail = optin - 2048 /* static */ - 2 * owner_cap * (int)sizeof(int);
         g_key_cap = avail > 0 ? (avail / (int)sizeof(int)) & ~3 : 0;
