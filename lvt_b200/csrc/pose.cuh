@@ -295,12 +295,17 @@ __device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, PoseEdge (
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (w == 0 && k < kPoseSums)
+        // every lane of the row's group holds the row total: lane w serves destination CTA w, w + 8, ...
+        // (one DSMEM store per thread instead of nranks stores by the row leader)
+        if (k < kPoseSums)
         {
             if (nranks == 1)
-                s.sums[k] = v;
+            {
+                if (w == 0)
+                    s.sums[k] = v;
+            }
             else
-                for (int r = 0; r < nranks; r++)
+                for (int r = w; r < nranks; r += kSlices)
                     *cluster.map_shared_rank(&s.gather[parity][rank][k], r) = v;
         }
     }
