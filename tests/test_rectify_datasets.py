@@ -280,3 +280,49 @@ def test_gpu_pool_rectifies_on_upload(cuda, oracle):
         vo.destroy()
     assert res[0][1] == res[1][1]
     assert np.abs(res[0][0] - res[1][0]).max() < 1e-6
+
+
+def _make_euroc_tree(tmp_path, n, p):
+    se = make_stream("euroc_synth", n)
+    stamps = [1403636579763555584 + 50000000 * t for t in range(n)]
+    (tmp_path / "stamps").mkdir(exist_ok=True)
+    (tmp_path / "stamps" / "V1_01.txt").write_text("".join("%d\n" % s for s in stamps))
+    for t in range(n):
+        a, b = se.frame(t)
+        _write_png(str(tmp_path / "euroc" / "V1_01" / "mav0" / "cam0" / "data" / ("%d.png" % stamps[t])), a)
+        _write_png(str(tmp_path / "euroc" / "V1_01" / "mav0" / "cam1" / "data" / ("%d.png" % stamps[t])), b)
+    return _yaml(str(tmp_path / "euroc.yaml"), p)
+
+
+@pytest.mark.gpu
+def test_gpu_dataset_drivers_equal_oracle(cuda, oracle, tmp_path):
+    """the EuRoC and TUM drivers over the CUDA library give the oracle's trajectories (raw EuRoC frames are
+    rectified on the device with the genuine calibration)"""
+    pytest.importorskip("cv2")
+    n = 4
+    pe = configs.make_params("euroc_synth", max_keypoints_per_cell=200)
+    cfg_e = _make_euroc_tree(tmp_path, n, pe)
+    out = []
+    for lib, tag in ((cuda, "g"), (oracle, "o")):
+        poses, ts = datasets.run_euroc(lib, str(tmp_path / "euroc"), str(tmp_path / "stamps"), "V1_01", cfg_e,
+                                       str(tmp_path / ("V1_01_%s.txt" % tag)))
+        out.append(np.array([np.concatenate([R.ravel(), t]) for R, t in poses]))
+    assert np.abs(out[0] - out[1]).max() < 1e-6
+    assert np.allclose(np.loadtxt(str(tmp_path / "V1_01_g.txt")), np.loadtxt(str(tmp_path / "V1_01_o.txt")), atol=1e-6)
+
+    pt = configs.make_params("tum_synth", max_keypoints_per_cell=400)
+    stt = make_stream("tum_synth", n)
+    lines = []
+    for t in range(n):
+        g, d = stt.frame(t)
+        _write_png(str(tmp_path / "tum" / "fr3" / "rgb" / ("%d.png" % t)), np.repeat(g[:, :, None], 3, 2))
+        _write_png(str(tmp_path / "tum" / "fr3" / "depth" / ("%d.png" % t)), np.round(d * 5000).astype(np.uint16))
+        lines.append("%f rgb/%d.png %f depth/%d.png\n" % (1.0 + t, t, 1.0 + t, t))
+    (tmp_path / "assoc").mkdir()
+    (tmp_path / "assoc" / "fr3.txt").write_text("".join(lines))
+    cfg_t = _yaml(str(tmp_path / "tum.yaml"), pt)
+    out = []
+    for lib in (cuda, oracle):
+        poses, _ = datasets.run_tum_rgbd(lib, str(tmp_path / "tum"), str(tmp_path / "assoc"), "fr3", cfg_t)
+        out.append(np.array([np.concatenate([R.ravel(), t]) for R, t in poses]))
+    assert np.abs(out[0] - out[1]).max() < 1e-6
