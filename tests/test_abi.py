@@ -64,3 +64,16 @@ def test_cuda_library_reports_gpu_and_fails_without_device():
         from lvt_b200 import configs
         with pytest.raises(lvt_b200.LvtError):
             lib.create(configs.make_params("kitti_synth"))  # no silent CPU path
+
+
+def test_cxx_lvt_system_mirror_over_the_c_abi(oracle, tmp_path):
+    """include/lvt_system.hpp (the reference's lvt_system method names over the C ABI) compiles as C++11 and
+    tracks through the oracle library, which exports the same symbols as the CUDA build"""
+    import subprocess
+    exe = str(tmp_path / "cxx_smoke")
+    so_dir = os.path.dirname(oracle.path)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cxx_system_smoke.cpp"), "-o", exe, "-L", so_dir, "-llvt_oracle",
+                    "-Wl,-rpath," + so_dir], check=True)
+    r = subprocess.run([exe, "320", "200"], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
