@@ -79,6 +79,30 @@ def test_oracle_rectify_live_cv2(oracle):
         assert np.array_equal(ctx.rectify(img, r), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
 
 
+def _degenerate_calibrations():
+    """maps that leave every comfortable range: rays with w <= 0 (|map| up to 1e13 -> the short-range
+    saturation of cv::remap's fixed-point coordinates), distortion polynomials of thousands of pixels, and a
+    projection shifted 5000 px away (every tap outside)"""
+    K = np.array([[80.0, 0, 60], [0, 80.0, 45], [0, 0, 1]])
+    a = 1.45
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    return [(K, np.array([-0.2, 0.05, 0, 0, 0.0]), Ry, K),
+            (K, np.array([5.0, 20.0, 0.1, 0.1, 50.0]), np.eye(3), K),
+            (K, np.zeros(5), np.eye(3), np.array([[80.0, 0, -5000], [0, 80.0, 45], [0, 0, 1]]))]
+
+
+def test_oracle_rectify_degenerate_maps_live_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    w, h = 120, 90
+    ctx = oracle.context(configs.make_params("euroc_synth", img_width=w, img_height=h))
+    img = _test_image(3, w, h)
+    for K, D, R, P in _degenerate_calibrations():
+        m1, m2 = cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32FC1)
+        # (map values of 1e3 .. 1e13 differ from cv2's FMA-contracted ones in the last bits; the image must not)
+        assert np.array_equal(ctx.rectify(img, capi.Rectify.make(K, D, R, P)), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+    ctx.destroy()
+
+
 def test_rectify_bad_arguments(oracle):
     ctx = oracle.context(configs.make_params("euroc_synth"))
     vo = oracle.create(configs.make_params("euroc_synth"))
@@ -246,6 +270,11 @@ def test_gpu_rectify_equals_oracle_random(cuda, oracle):
         r = capi.Rectify.make(K, D, R, P)
         mg, mo = cg.rectify_maps(r, h, w), co.rectify_maps(r, h, w)
         assert np.array_equal(mg[0], mo[0]) and np.array_equal(mg[1], mo[1])
+        assert np.array_equal(cg.rectify(img, r), co.rectify(img, r))
+    for K, D, R, P in _degenerate_calibrations():
+        r = capi.Rectify.make(K, D, R, P)
+        mg, mo = cg.rectify_maps(r, h, w), co.rectify_maps(r, h, w)
+        assert np.array_equal(mg[0], mo[0], equal_nan=True) and np.array_equal(mg[1], mo[1], equal_nan=True)
         assert np.array_equal(cg.rectify(img, r), co.rectify(img, r))
     cg.destroy()
     co.destroy()
