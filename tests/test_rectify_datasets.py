@@ -355,3 +355,62 @@ def test_gpu_dataset_drivers_equal_oracle(cuda, oracle, tmp_path):
         poses, _ = datasets.run_tum_rgbd(lib, str(tmp_path / "tum"), str(tmp_path / "assoc"), "fr3", cfg_t)
         out.append(np.array([np.concatenate([R.ravel(), t]) for R, t in poses]))
     assert np.abs(out[0] - out[1]).max() < 1e-6
+
+
+# ---- RGB-D keypoint undistortion (lvt_image_features_handler.cpp:268-294, cv::undistortPoints) ----
+TUM_FR1_LIKE = dict(k1=0.2312, k2=-0.7849, p1=-0.0033, p2=-0.0001, k3=0.9172)
+
+
+def _undistorted_features(lib):
+    p = configs.make_params("tum_synth", max_keypoints_per_cell=400, **TUM_FR1_LIKE)
+    gray, depth = make_stream("tum_synth", 1, seed=2).frame(0)
+    vo = lib.create(p, capi.SENSOR_RGBD)
+    vo.track_rgbd(gray, depth)
+    xy, _ = vo.features(0)
+    vo.destroy()
+    ctx = lib.context(p)
+    k, _ = ctx.extract(gray)
+    ctx.destroy()
+    return np.stack([k["x"], k["y"]], 1).astype(np.float32), xy, p
+
+
+def test_oracle_undistortion_equals_cv2_fixture(oracle):
+    """the keypoints of an RGB-D frame after the reference's cv::undistortPoints call == the genuine OpenCV output
+    (tests/golden/undistort_cv2.npz, tools/make_golden_rectify.py --undistort)"""
+    g = np.load(os.path.join(GOLDEN, "undistort_cv2.npz"))
+    detected, xy, _ = _undistorted_features(oracle)
+    assert np.array_equal(detected, g["detected"])
+    assert np.array_equal(xy, g["undistorted"])
+    assert np.abs(xy - detected).max() > 1.0  # the distortion is not a no-op on this frame
+
+
+def test_oracle_undistortion_live_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    detected, xy, p = _undistorted_features(oracle)
+    K = np.array([[p.fx, 0, p.cx], [0, p.fy, p.cy], [0, 0, 1]], np.float64)
+    dist = np.array([p.k1, p.k2, p.p1, p.p2, p.k3], np.float64)
+    assert np.array_equal(xy, cv2.undistortPoints(detected.reshape(-1, 1, 2), K, dist, None, None, K).reshape(-1, 2))
+
+
+@pytest.mark.gpu
+def test_gpu_rgbd_with_lens_distortion(cuda, oracle):
+    """RGB-D frames with a distorted camera model: undistorted keypoints (== the cv2 fixture), visibility bounds from
+    the undistorted image corners, and everything downstream agree with the oracle"""
+    g = np.load(os.path.join(GOLDEN, "undistort_cv2.npz"))
+    detected, xy, p = _undistorted_features(cuda)
+    assert np.array_equal(detected, g["detected"]) and np.array_equal(xy, g["undistorted"])
+    n = 5
+    st = make_stream("tum_synth", n, seed=2)
+    vg, vo = cuda.create(p, capi.SENSOR_RGBD), oracle.create(p, capi.SENSOR_RGBD)
+    for t in range(n):
+        gray, depth = st.frame(t)
+        Rg, tg = vg.track_rgbd(gray, depth)
+        Ro, to = vo.track_rgbd(gray, depth)
+        fx, fd = vg.features(0)
+        ox, od = vo.features(0)
+        assert np.array_equal(fx, ox) and np.array_equal(fd, od), t
+        assert vg.frame_info() == vo.frame_info(), (t, vg.frame_info(), vo.frame_info())
+        assert np.abs(tg - to).max() < 1e-6 and np.abs(Rg - Ro).max() < 1e-6
+    assert vg.frame_info()["tracked"] > 100
+    vg.destroy()
+    vo.destroy()

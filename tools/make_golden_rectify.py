@@ -69,5 +69,39 @@ def main():
     print("written", os.path.join(OUT, "rectify_cv2.npz"))
 
 
+
+
+
+TUM_FR1_LIKE = dict(k1=0.2312, k2=-0.7849, p1=-0.0033, p2=-0.0001, k3=0.9172)  # examples/tum_rgbd/config_tum1.yaml:7-11 shape
+
+
+def undistort_fixture():
+    """tests/golden/undistort_cv2.npz: cv2.undistortPoints(kps, K, dist, None, None, K) -- the call of the RGB-D
+    path (lvt/src/lvt_image_features_handler.cpp:268-294) -- on the corners the oracle extracts from frame 0 of
+    the synthetic RGB-D stream (seed 2), with a TUM fr1-like distortion.  K and dist are the float parameters of
+    lvt_parameters widened to double, as the reference passes them."""
+    import subprocess
+    import cv2
+    from lvt_b200 import capi, configs, synth
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    orc = capi.Library(os.path.join(ROOT, "oracle", "_build", "liblvt_oracle.so"))
+    p = configs.make_params("tum_synth", max_keypoints_per_cell=400, **TUM_FR1_LIKE)
+    st = synth.RgbdStream(n_frames=1, seed=2, **configs.CONFIGS["tum_synth"]["stream"])
+    gray, _ = st.frame(0)
+    k, _ = orc.context(p).extract(gray)
+    K = np.array([[p.fx, 0, p.cx], [0, p.fy, p.cy], [0, 0, 1]], np.float64)
+    dist = np.array([p.k1, p.k2, p.p1, p.p2, p.k3], np.float64)
+    src = np.stack([k["x"], k["y"]], 1).astype(np.float32)
+    corners = np.array([[0, 0], [p.img_width, 0], [0, p.img_height], [p.img_width, p.img_height]], np.float32)
+    und = cv2.undistortPoints(src.reshape(-1, 1, 2), K, dist, None, None, K).reshape(-1, 2)
+    und_c = cv2.undistortPoints(corners.reshape(-1, 1, 2), K, dist, None, None, K).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "undistort_cv2.npz"), detected=src, undistorted=und, corners=corners,
+                        corners_undistorted=und_c, cv2_version=np.array(cv2.__version__))
+    print("written", os.path.join(OUT, "undistort_cv2.npz"), len(src), "points")
+
+
 if __name__ == "__main__":
-    main()
+    if "--undistort" in sys.argv:
+        undistort_fixture()
+    else:
+        main()
