@@ -112,6 +112,12 @@ typedef struct lvt_frame_info
 } lvt_frame_info;
 
 LVT_API int lvt_get_frame_info(lvt_handle vo_system, lvt_frame_info *out);
+/* The reference's tracking calls are void and swallow every failure (lvt/src/lvt_c.cpp:63-134:
+ * try { ... } catch (...) {}), leaving R / t untouched.  This returns the status of the last
+ * lvt_track* / lvt_track_pool / lvt_track_batch call on the handle: 0 = ok, <0 = LVTK_ERR_*
+ * (include/lvt_kernels.h): -1 wrong image size or an entry point that does not match the handle's
+ * sensor type, -2 CUDA error, -3 a fixed capacity was exceeded (see "capacities" below). */
+LVT_API int lvt_get_last_status(lvt_handle vo_system);
 /* quaternion (w,x,y,z) + position of the last returned pose */
 LVT_API int lvt_get_last_pose(lvt_handle vo_system, double q_wxyz[4], double t[3]);
 
@@ -123,9 +129,25 @@ LVT_API int lvt_debug_get_features(lvt_handle vo_system, int which, float *kps_x
 LVT_API int lvt_debug_get_points(lvt_handle vo_system, int which, double *xyz, unsigned char *desc,
                                  int *counters, int *ages, int *match_idx, int cap);
 
-/* Replace the 256 BRIEF test pairs (process-wide; call before lvt_create).
- * pairs[i] = {dy1, dx1, dy2, dx2}, |offset| <= 24, in the order of opencv_contrib's
- * generated_32.i.  NULL restores the built-in table.  Returns 0 on success. */
+/* ---- capacities ----------------------------------------------------------------------------
+ * The reference keeps keypoints and map points in std::vectors that grow without bound
+ * (lvt/src/lvt_local_map.cpp:331-353).  Here:
+ *  - the local map and the staged-point store GROW: a frame that could overflow them is refused on
+ *    the device before it changes anything, the stores are doubled (contents kept) and the frame
+ *    runs again -- invisible to the caller apart from the time it takes;
+ *  - keypoints per image are bounded by construction (ANMS keeps ~max_keypoints_per_cell + 1 per
+ *    detection tile): the feature capacity is 2 x tiles x (max_keypoints_per_cell + 1), at least
+ *    4096 and at most 24 576 (two owner arrays of the greedy matcher must fit in 227 KB of shared
+ *    memory).  An image that yields more features than that fails the call with status -3
+ *    (lvt_get_last_status), outputs untouched.
+ * lvt_debug_point_capacity: current capacity of the map / staged stores (0 for the oracle). */
+LVT_API int lvt_debug_point_capacity(lvt_handle vo_system);
+
+/* Replace the 256 BRIEF test pairs, process-wide.  pairs[i] = {dy1, dx1, dy2, dx2},
+ * |offset| <= 24, in the order of opencv_contrib's generated_32.i.  NULL restores the built-in
+ * table.  Handles created afterwards use the new table; live handles (on any device, driven from
+ * any thread) switch to it at their next tracking call -- do not call this while a tracking call
+ * is in flight on another thread.  Returns 0 on success. */
 LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4]);
 
 /* ---- in-pipeline stereo rectification (new) ---------------------------

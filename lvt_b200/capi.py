@@ -127,6 +127,10 @@ class Library:
                                                         c_f64p, C.c_int, c_f64p, c_f64p]
         lib.lvt_get_status.argtypes = [vp]
         lib.lvt_get_status.restype = C.c_int
+        lib.lvt_debug_point_capacity.argtypes = [vp]
+        lib.lvt_debug_point_capacity.restype = C.c_int
+        lib.lvt_get_last_status.argtypes = [vp]
+        lib.lvt_get_last_status.restype = C.c_int
         lib.lvt_params_default.argtypes = [C.POINTER(Params)]
         lib.lvt_params_from_file.argtypes = [C.POINTER(Params), C.c_char_p]
         lib.lvt_params_from_file.restype = C.c_int
@@ -240,6 +244,9 @@ class System:
         self.library, self.lib, self.h, self.params = library, library.lib, handle, params
         self._R = np.zeros((3, 3), np.float64)
         self._t = np.zeros(3, np.float64)
+        # raise when a (void) tracking call failed instead of handing back the previous pose;
+        # False reproduces the reference's behaviour (outputs untouched, nothing reported)
+        self.check_status = True
 
     def destroy(self):
         if self.h:
@@ -258,7 +265,15 @@ class System:
     def get_state(self):
         return self.lib.lvt_get_status(self.h)
 
+    def last_status(self):
+        """status of the last tracking call (the reference's calls are void): 0 ok, < 0 LVTK_ERR_*"""
+        return int(self.lib.lvt_get_last_status(self.h))
+
     def _pose_out(self):
+        if self.check_status:
+            rc = self.last_status()
+            if rc != 0:
+                raise LvtError("tracking call failed with status %d (%s)" % (rc, self.library.last_error()))
         return self._R.copy(), self._t.copy()
 
     def track(self, left, right):
@@ -310,6 +325,9 @@ class System:
 
     def last_batch_ms(self):
         return float(self.lib.lvt_last_batch_ms(self.h))
+
+    def point_capacity(self):
+        return int(self.lib.lvt_debug_point_capacity(self.h))
 
     def frame_info(self):
         fi = FrameInfo()

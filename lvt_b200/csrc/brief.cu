@@ -23,17 +23,17 @@ constexpr int kIntegSlot = (kIntegBytes + 127) / 128 * 128;            // 6784
 constexpr int kBriefWarps = 4;
 constexpr int kBriefSmem = kBriefWarps * (kPatchSlot + kIntegSlot) + 128;
 
-// per (word w, lane l): offsets of the two boxes' top-left integral corner, lo = first box
-__device__ uint32_t d_brief_offsets[8 * 32];
+// The test-pair table as the kernel wants it -- per (word w, lane l): offsets of the two boxes'
+// top-left integral corner, lo = first box.  Every context owns a copy in device memory (no
+// process-wide device symbol: contexts on any number of devices and threads stay independent).
 
 static const signed char kDefaultPairs[256][4] = {
 #include "brief_pairs.inc"
 };
 
-int upload_brief_pairs(const signed char pairs_in[256][4])
+void make_brief_offsets(const signed char pairs_in[256][4], uint32_t h[8 * 32])
 {
     const signed char(*pairs)[4] = pairs_in ? pairs_in : kDefaultPairs;
-    uint32_t h[8 * 32];
     for (int w = 0; w < 8; w++)
     {
         for (int l = 0; l < 32; l++)
@@ -44,8 +44,6 @@ int upload_brief_pairs(const signed char pairs_in[256][4])
             h[w * 32 + l] = (uint32_t)o1 | ((uint32_t)o2 << 16);
         }
     }
-    LVT_CUDA_TRY(cudaMemcpyToSymbol(d_brief_offsets, h, sizeof(h)));
-    return LVTK_OK;
 }
 
 struct BriefArgs
@@ -55,6 +53,7 @@ struct BriefArgs
     int rows, cols;
     int with_index; // 1: the last CTA of every image builds the feature index (index.cuh) instead of describing
     CamParams cam;
+    const uint32_t *offsets; // [8 * 32], make_brief_offsets
 };
 
 __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_constant__ CUtensorMap tmap, BriefArgs a)
@@ -84,7 +83,7 @@ __global__ void __launch_bounds__(kBriefWarps * 32) brief_kernel(const __grid_co
     uint32_t offs[8];
 #pragma unroll
     for (int w = 0; w < 8; w++)
-        offs[w] = d_brief_offsets[w * 32 + lane];
+        offs[w] = a.offsets[w * 32 + lane];
 
     if (lane == 0)
     {
@@ -244,18 +243,16 @@ int launch_border_filter(const float2 *src_xy, const float *src_resp, const int 
 
 bool brief_can_index(const CamParams &cam) { return index_smem_ints(cam) * (int)sizeof(int) <= kBriefSmem; }
 
-int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream,
-                 const CamParams *index_cam)
+int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, const uint32_t *d_offsets,
+                 cudaStream_t stream, const CamParams *index_cam)
 {
-    static int smem_set_dev = -1; // function attributes are per device
-    int cur_dev = 0;
-    LVT_CUDA_TRY(cudaGetDevice(&cur_dev));
-    if (smem_set_dev != cur_dev)
-    {
-        LVT_CUDA_TRY(cudaFuncSetAttribute(brief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBriefSmem));
-        smem_set_dev = cur_dev;
-    }
-    BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols, 0, CamParams{}};
+    static DeviceOnce once;
+    if (int rc = once.run([](int) {
+            LVT_CUDA_TRY(cudaFuncSetAttribute(brief_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBriefSmem));
+            return (int)LVTK_OK;
+        }))
+        return rc;
+    BriefArgs ba{d_slots, d_feats, pool.rows, pool.cols, 0, CamParams{}, d_offsets};
     if (index_cam)
     {
         if (index_smem_ints(*index_cam) * (int)sizeof(int) > kBriefSmem)

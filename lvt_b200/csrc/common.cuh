@@ -2,8 +2,10 @@
 #pragma once
 
 #include "../../include/lvt_kernels.h"
+#include <atomic>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 
 namespace lvtb
@@ -44,6 +46,38 @@ enum KernelId
     K_RECTIFY,
     K_COUNT
 };
+// Function attributes (opt-in shared memory) are per device and per process: every launcher sets
+// them once per device through one of these, from whichever thread gets there first.  Distinct
+// handles may be driven from distinct threads (lvt/src/lvt_c.cpp:33-148 has no shared state).
+struct DeviceOnce
+{
+    static constexpr int kMaxDevices = 64;
+    std::atomic<int> done[kMaxDevices];
+    std::mutex mu;
+    DeviceOnce()
+    {
+        for (auto &d : done)
+            d.store(0);
+    }
+    // f(device) -> LVTK_* ; runs once per device, other threads wait for it
+    template <class F>
+    int run(F f)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+            return LVTK_ERR_CUDA;
+        if (done[dev].load(std::memory_order_acquire))
+            return LVTK_OK;
+        std::lock_guard<std::mutex> lk(mu);
+        if (done[dev].load(std::memory_order_relaxed))
+            return LVTK_OK;
+        if (int rc = f(dev))
+            return rc;
+        done[dev].store(1, std::memory_order_release);
+        return LVTK_OK;
+    }
+};
+
 bool prof_enabled();
 void count_launch();
 long launch_count();

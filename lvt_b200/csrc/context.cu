@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 
 namespace lvtb
@@ -33,7 +34,8 @@ namespace
 {
 struct Profiler
 {
-    bool on = false;
+    std::atomic<bool> on{false};
+    std::mutex mu; // held from prof_begin to prof_end: with profiling on, launches of all threads serialise
     std::vector<cudaEvent_t> pool;
     std::vector<int> ids; // kernel id of pair i (events 2i, 2i+1)
     size_t used = 0;
@@ -41,12 +43,13 @@ struct Profiler
     long count[K_COUNT] = {};
 } g_prof;
 } // namespace
-static long g_launches = 0;
-void count_launch() { g_launches++; }
-long launch_count() { return g_launches; }
-bool prof_enabled() { return g_prof.on; }
+static std::atomic<long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+bool prof_enabled() { return g_prof.on.load(std::memory_order_relaxed); }
 void prof_begin(cudaStream_t s, int id)
 {
+    g_prof.mu.lock();
     if (g_prof.pool.size() < 2 * (g_prof.used + 1))
     {
         cudaEvent_t a, b;
@@ -63,9 +66,11 @@ void prof_end(cudaStream_t s, int)
 {
     cudaEventRecord(g_prof.pool[2 * g_prof.used + 1], s);
     g_prof.used++;
+    g_prof.mu.unlock();
 }
 static void prof_collect()
 {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
     for (size_t i = 0; i < g_prof.used; i++)
     {
         float t = 0;
@@ -353,10 +358,13 @@ CamParams make_cam_params(const lvt_params_c &p)
     return c;
 }
 
-static int g_pairs_uploaded_dev = -1; // device whose __device__ table holds the current pairs
-static bool g_pairs_uploaded = false;
+// BRIEF test pairs (lvt_set_brief_pairs): the process-wide choice and its version.  Every context
+// owns a device copy of the table and refreshes it (stream-ordered, on its own device, from its own
+// thread) when the version has moved on -- nothing device-side is shared between contexts.
+static std::mutex g_pairs_mu;
 static signed char g_pairs[256][4];
 static bool g_pairs_custom = false;
+static std::atomic<unsigned> g_pairs_version{1};
 
 } // namespace lvtb
 
@@ -376,7 +384,9 @@ struct lvtk_ctx
     DeviceArena arena;
     ImagePool pool;
     DetectWorkspace ws;
-    int fcap = 0, pcap = 0;
+    int fcap = 0, pcap = 0; // feature capacity per image (fixed) / capacity of the point stores (grows, ctx_grow_points)
+    int in_cap = 0;         // capacity of the seam / external-corner input buffers (= the initial pcap)
+    int n_grown = 0;        // times the point stores were doubled
     static constexpr int kXStreams = 4; // extraction pipelines in flight (lvt_track_pool)
     static constexpr int kSets = 6;     // feature sets (left, right) cycling through them
     FeatDev feats_h[2 * kSets];
@@ -431,7 +441,83 @@ struct lvtk_ctx
     PointStore map, staged;
     TrackScratch sc;
     CandLists row_cand[kSets]; // per feature set
+    TrackLaunchCfg tcfg;       // shared-memory layout of the tracking kernels for this context's capacities
+    uint32_t *d_brief_offsets = nullptr, *h_brief_offsets = nullptr; // [8 * 32] device copy / pinned source
+    unsigned pairs_version = 0;
 };
+
+// one frame's tracking kernels (parts: 1 up to the pose, 2 the rest, 3 both) on `st`
+static int ctx_launch_track(lvtk_ctx *c, FrameResult *result, const FeatDev *feats, const CandLists &row_cand, cudaStream_t st,
+                            cudaEvent_t right_ready = nullptr, int parts = 3, EarlyResult *early = nullptr, int early_seq = 0)
+{
+    return launch_track_frame(c->d_state, c->d_ctl, result, c->map, c->staged, feats, c->tp, c->sc, row_cand, c->tcfg,
+                              c->ws.error, st, right_ready, parts, early, early_seq);
+}
+
+// The reference's map and staged-point vectors grow without bound (lvt/src/lvt_local_map.cpp:331-353).
+// Here a frame that could overflow the stores is refused on the device before it touches anything
+// (TrackState::halt, track_a_kernel); the host then doubles every array sized by the point capacity,
+// keeps the contents, clears the halt and runs the frame again.  Rare (the default capacity holds
+// 8x the feature capacity), so it simply idles the device first.
+static int ctx_grow_points(lvtk_ctx *c)
+{
+    LVT_CUDA_TRY(cudaDeviceSynchronize());
+    const size_t o = (size_t)c->pcap, n = 2 * o;
+    if (n > ((size_t)1 << 26))
+    {
+        set_last_error(__FILE__, __LINE__, "point stores cannot grow beyond 2^26 points");
+        return LVTK_ERR_CAPACITY;
+    }
+    DeviceArena &A = c->arena;
+    int rc = LVTK_OK;
+    for (PointStore *ps : {&c->map, &c->staged})
+    {
+        rc = rc ? rc : A.regrow(&ps->xyz, o * 3, n * 3);
+        rc = rc ? rc : A.regrow(&ps->desc, o * 8, n * 8);
+        rc = rc ? rc : A.regrow(&ps->counter, o, n);
+        rc = rc ? rc : A.regrow(&ps->age, o, n);
+        rc = rc ? rc : A.regrow(&ps->match_idx, o, n);
+        ps->cap = (int)n;
+    }
+    rc = rc ? rc : A.regrow(&c->sc.ms.proj, 0, n); // scratch: nothing to keep
+    rc = rc ? rc : A.regrow(&c->sc.ms.vis, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.ms.choice, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.ms.items, 0, 2 * n + 1024);
+    rc = rc ? rc : A.regrow(&c->sc.sol_xyz, 0, n * 3);
+    rc = rc ? rc : A.regrow(&c->sc.sol_uv, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.level, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.inlier, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.e2, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.map_cand.keys, 0, n * kMapCandCap);
+    rc = rc ? rc : A.regrow(&c->sc.map_cand.count, 0, n);
+    if (rc)
+        return rc;
+    c->pcap = (int)n;
+    LVT_CUDA_TRY(cudaDeviceSynchronize()); // the arena's memsets / copies ran on the default stream
+    if (int r2 = launch_clear_halt(c->d_state, c->stream))
+        return r2;
+    LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->n_grown++;
+    return LVTK_OK;
+}
+
+// the context's copy of the BRIEF table follows lvt_set_brief_pairs; `stream` = where the next
+// brief_kernel of this context will run
+static int ctx_sync_pairs(lvtk_ctx *c, cudaStream_t stream)
+{
+    if (c->pairs_version == g_pairs_version.load(std::memory_order_acquire))
+        return LVTK_OK;
+    // the pinned source may still be read by an earlier refresh on another stream
+    LVT_CUDA_TRY(cudaDeviceSynchronize());
+    {
+        std::lock_guard<std::mutex> lk(g_pairs_mu);
+        make_brief_offsets(g_pairs_custom ? g_pairs : nullptr, c->h_brief_offsets);
+        c->pairs_version = g_pairs_version.load(std::memory_order_relaxed);
+    }
+    LVT_CUDA_TRY(cudaMemcpyAsync(c->d_brief_offsets, c->h_brief_offsets, sizeof(uint32_t) * 256, cudaMemcpyHostToDevice, stream));
+    LVT_CUDA_TRY(cudaStreamSynchronize(stream)); // every stream of the context sees the new table
+    return LVTK_OK;
+}
 
 static int ctx_check_error(lvtk_ctx *c)
 {
@@ -526,6 +612,9 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
         fcap = 24576; // two owner arrays must fit in 227 KB of shared memory
     c->fcap = (int)fcap;
     c->pcap = std::max(32768, 8 * c->fcap);
+    if (const char *e = std::getenv("LVT_B200_POINT_CAP")) // test aid: start small, exercise the growth path
+        c->pcap = std::max(256, std::atoi(e));
+    c->in_cap = std::max(c->pcap, 2 * c->fcap);
     const int n_cells = c->cam.cells_x * c->cam.cells_y;
     for (int i = 0; i < 2 * lvtk_ctx::kSets; i++)
         if (int rc = make_feat(&c->feats_h[i], c->arena, c->fcap, n_cells, p.img_height))
@@ -533,13 +622,13 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     int rc = c->arena.alloc(&c->feats_d, 2 * lvtk_ctx::kSets);
     rc = rc ? rc : c->arena.alloc(&c->d_slots, 4);
     rc = rc ? rc : c->arena.alloc(&c->d_depth, (size_t)2 * p.img_width * p.img_height); // two alternating frames
-    rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->d_in_resp, (size_t)2 * c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_in_xy, (size_t)2 * c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->d_in_resp, (size_t)2 * c->in_cap);
     rc = rc ? rc : c->arena.alloc(&c->d_in_n, 2);
-    rc = rc ? rc : c->arena.alloc(&c->d_int_a, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->d_int_b, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->d_f_a, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->d_f_b, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->d_int_a, (size_t)c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->d_int_b, (size_t)c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->d_f_a, (size_t)c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->d_f_b, (size_t)c->in_cap);
     rc = rc ? rc : c->arena.alloc(&c->d_pose_out, 1);
     rc = rc ? rc : c->arena.alloc(&c->d_state, 1);
     rc = rc ? rc : c->arena.alloc(&c->d_ctl, frame_ctl_bytes());
@@ -564,11 +653,11 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
         rc = rc ? rc : c->arena.alloc(&c->row_cand[i].count, (size_t)c->fcap);
         c->row_cand[i].cap = kRowCandCap;
     }
-    rc = rc ? rc : c->arena.alloc(&c->sc.row_choice, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->sc.pair_query, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->sc.pair_train, (size_t)c->pcap);
-    rc = rc ? rc : c->arena.alloc(&c->sc.tri_xyz, (size_t)c->pcap * 3);
-    rc = rc ? rc : c->arena.alloc(&c->sc.tri_ok, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.row_choice, (size_t)c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.pair_query, (size_t)c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.pair_train, (size_t)c->in_cap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.tri_xyz, (size_t)c->in_cap * 3);
+    rc = rc ? rc : c->arena.alloc(&c->sc.tri_ok, (size_t)c->in_cap);
     if (rc)
         return rc;
     LVT_CUDA_TRY(cudaMemcpy(c->feats_d, c->feats_h, sizeof(c->feats_h), cudaMemcpyHostToDevice));
@@ -600,14 +689,14 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
             c->upload_dmas = std::max(1, std::min(16, std::atoi(e)));
         c->lanes.start(c->device, lanes - 1);
     }
-    if (!g_pairs_uploaded || g_pairs_uploaded_dev != c->device)
-    {
-        if (int r2 = upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr))
-            return r2;
-        g_pairs_uploaded = true;
-        g_pairs_uploaded_dev = c->device;
-    }
+    if (int r2 = c->arena.alloc(&c->d_brief_offsets, 256))
+        return r2;
+    LVT_CUDA_TRY(cudaMallocHost(&c->h_brief_offsets, sizeof(uint32_t) * 256));
+    if (int r2 = track_configure(c->fcap, &c->tcfg))
+        return r2;
     LVT_CUDA_TRY(cudaDeviceSynchronize()); // the arena's memsets ran on the default stream
+    if (int r2 = ctx_sync_pairs(c, c->stream))
+        return r2;
     if (int r3 = launch_reset_state(c->d_state, c->stream))
         return r3;
     LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -663,6 +752,8 @@ static void ctx_free(lvtk_ctx *c)
         cudaFreeHost(c->h_result);
     if (c->h_error)
         cudaFreeHost(c->h_error);
+    if (c->h_brief_offsets)
+        cudaFreeHost(c->h_brief_offsets);
     delete c;
 }
 
@@ -773,6 +864,7 @@ struct System
     PoseD last_pose;
     lvt_frame_info info;
     bool pending = false; // the last blocking frame returned at its pose; info / error flag are still on their way
+    int last_status = LVTK_OK; // of the last tracking call on this handle (lvt_get_last_status)
 
     // host-side time of the blocking entry points: [0] staging + H2D enqueue, [1] kernel enqueue,
     // [2] waiting for the device, [3] calls  (lvt_debug_host_times)
@@ -845,10 +937,17 @@ struct System
         if (sensor == 1)
             if (int rc = launch_rowcand(c->feats_d, c->cam, c->row_cand[0], c->stream))
                 return rc;
-        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, c->feats_d, c->tp, c->sc,
-                                        c->row_cand[0], c->fcap, c->stream))
-            return rc;
-        return fetch_result(out);
+        for (;;)
+        {
+            if (int rc = ctx_launch_track(c, c->d_result, c->feats_d, c->row_cand[0], c->stream))
+                return rc;
+            if (int rc = fetch_result(out))
+                return rc;
+            if (c->h_result->info.state != 0)
+                return LVTK_OK;
+            if (int rc = ctx_grow_points(c)) // the frame was refused: the point stores could have overflowed
+                return rc;
+        }
     }
 
     // the frame's kernels are enqueued on ctx->stream: fetch the result (the one host<->device round trip)
@@ -867,10 +966,34 @@ struct System
             set_last_error(__FILE__, __LINE__, "device-side capacity error");
             return e;
         }
+        if (c->h_result->info.state == 0)
+            return LVTK_OK; // refused (TrackState::halt): the caller grows the point stores and runs the frame again
         info = c->h_result->info;
         info.frame_number = frame_number;
         state = info.state;
         *out = c->h_result->pose;
+        return LVTK_OK;
+    }
+
+    // A blocking frame came back refused (h_early->state == 0): its features are extracted and indexed,
+    // only the tracking kernels run again after the point stores have grown.
+    int rerun_refused(const FeatDev *feats, int s)
+    {
+        lvtk_ctx *c = ctx;
+        while (c->h_early->state == 0)
+        {
+            if (int rc = ctx_grow_points(c)) // idles the device first
+                return rc;
+            cudaStream_t st = c->stream;
+            if (int rc = ctx_launch_track(c, c->d_result, feats, c->row_cand[s], st, nullptr, 3, c->d_early, ++c->early_seq))
+                return rc;
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
+            LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
+            LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_frame, st));
+            if (int rc = wait_for_pose())
+                return rc;
+        }
         return LVTK_OK;
     }
 
@@ -908,14 +1031,16 @@ struct System
     int track_stereo(const uint8_t *left, const uint8_t *right, int rows, int cols, PoseD *out)
     {
         lvtk_ctx *c = ctx;
-        if (rows != c->params.img_height || cols != c->params.img_width)
+        if (sensor != 1 || rows != c->params.img_height || cols != c->params.img_width)
             return LVTK_ERR_ARG;
+        if (int rc = ctx_sync_pairs(c, c->xs[0]))
+            return rc;
+        if (pending && cudaEventQuery(c->ev_frame) == cudaSuccess)
+            if (int rc = finish_pending()) // surfaces an error of the previous frame's map maintenance
+                return rc;             // (before the frame counter moves: the new frame is not consumed)
         if (lost_shortcut(out))
             return LVTK_OK;
         const bool first_frame = state == 1;
-        if (pending && cudaEventQuery(c->ev_frame) == cudaSuccess)
-            if (int rc = finish_pending()) // surfaces a capacity error of the previous frame's map maintenance
-                return rc;
         // Buffers (pool slots, staging, feature sets, candidate lists) alternate between two sets, so
         // nothing of this frame waits for the previous frame's map maintenance except the map
         // matching itself.  The set used two frames ago is free: its track_b ran before the pose of
@@ -946,7 +1071,7 @@ struct System
         if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, slots, 1, feats, kBriefBorder, 1, xl))
             return rc;
         const bool fused_index = brief_can_index(c->cam);
-        if (int rc = launch_brief(c->pool, slots, 1, feats, xl, fused_index ? &c->cam : nullptr))
+        if (int rc = launch_brief(c->pool, slots, 1, feats, c->d_brief_offsets, xl, fused_index ? &c->cam : nullptr))
             return rc;
         if (!fused_index)
             if (int rc = launch_index(feats, 1, c->cam, xl))
@@ -955,8 +1080,7 @@ struct System
         if (timeline)
             cudaEventRecord(c->ev_tl[2], xl);
         LVT_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_left, 0));
-        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc,
-                                        c->row_cand[s], c->fcap, st, nullptr, 1, c->d_early, ++c->early_seq))
+        if (int rc = ctx_launch_track(c, c->d_result, feats, c->row_cand[s], st, nullptr, 1, c->d_early, ++c->early_seq))
             return rc;
         LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
         if (timeline)
@@ -970,7 +1094,7 @@ struct System
         host_mark(1);
         if (int rc = launch_detect(c->pool, c->wsx[1], c->dp, slots + 1, 1, feats + 1, kBriefBorder, 1, xr))
             return rc;
-        if (int rc = launch_brief(c->pool, slots + 1, 1, feats + 1, xr, fused_index ? &c->cam : nullptr))
+        if (int rc = launch_brief(c->pool, slots + 1, 1, feats + 1, c->d_brief_offsets, xr, fused_index ? &c->cam : nullptr))
             return rc;
         if (!fused_index)
             if (int rc = launch_index(feats + 1, 1, c->cam, xr))
@@ -979,8 +1103,7 @@ struct System
         if (int rc = launch_rowcand(feats, c->cam, c->row_cand[s], xr))
             return rc;
         LVT_CUDA_TRY(cudaEventRecord(c->ev_right, xr));
-        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc,
-                                        c->row_cand[s], c->fcap, st, c->ev_right, 2, nullptr))
+        if (int rc = ctx_launch_track(c, c->d_result, feats, c->row_cand[s], st, c->ev_right, 2))
             return rc;
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -988,6 +1111,9 @@ struct System
         host_mark(2);
         if (int rc = wait_for_pose())
             return rc;
+        if (c->h_early->state == 0)
+            if (int rc = rerun_refused(feats, s))
+                return rc;
         host_mark(3);
         if (timeline)
         {
@@ -1020,11 +1146,13 @@ struct System
                        const double (*cr)[2], int nr, PoseD *out)
     {
         lvtk_ctx *c = ctx;
-        if (rows != c->params.img_height || cols != c->params.img_width || nl < 0 || nr < 0)
+        if (sensor != 1 || rows != c->params.img_height || cols != c->params.img_width || nl < 0 || nr < 0)
             return LVTK_ERR_ARG;
-        if (nl > c->pcap || nr > c->pcap)
+        if (nl > c->in_cap || nr > c->in_cap)
             return LVTK_ERR_CAPACITY;
         if (int rc = finish_pending())
+            return rc;
+        if (int rc = ctx_sync_pairs(c, c->stream))
             return rc;
         if (lost_shortcut(out))
             return LVTK_OK;
@@ -1034,19 +1162,19 @@ struct System
         if (int rc = ctx_stage_flush(c))
             return rc;
         host_mark(1);
-        std::vector<float2> xy((size_t)2 * c->pcap);
+        std::vector<float2> xy((size_t)2 * c->in_cap);
         for (int i = 0; i < nl; i++)
             xy[i] = make_float2((float)cl[i][0], (float)cl[i][1]);
         for (int i = 0; i < nr; i++)
-            xy[c->pcap + i] = make_float2((float)cr[i][0], (float)cr[i][1]);
+            xy[c->in_cap + i] = make_float2((float)cr[i][0], (float)cr[i][1]);
         const int n_in[2] = {nl, nr};
         LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_xy, xy.data(), sizeof(float2) * xy.size(), cudaMemcpyHostToDevice, c->stream));
         LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_n, n_in, sizeof(n_in), cudaMemcpyHostToDevice, c->stream));
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (int rc = launch_border_filter(c->d_in_xy, nullptr, c->d_in_n, c->pcap, c->feats_d, 2, rows, cols, c->ws.error,
+        if (int rc = launch_border_filter(c->d_in_xy, nullptr, c->d_in_n, c->in_cap, c->feats_d, 2, rows, cols, c->ws.error,
                                           c->stream))
             return rc;
-        if (int rc = launch_brief(c->pool, c->d_slots, 2, c->feats_d, c->stream))
+        if (int rc = launch_brief(c->pool, c->d_slots, 2, c->feats_d, c->d_brief_offsets, c->stream))
             return rc;
         return finish(out);
     }
@@ -1058,14 +1186,16 @@ struct System
     int track_rgbd(const uint8_t *gray, const float *depth, int rows, int cols, PoseD *out)
     {
         lvtk_ctx *c = ctx;
-        if (rows != c->params.img_height || cols != c->params.img_width)
+        if (sensor != 2 || rows != c->params.img_height || cols != c->params.img_width)
             return LVTK_ERR_ARG;
-        if (lost_shortcut(out))
-            return LVTK_OK;
-        const bool first_frame = state == 1;
+        if (int rc = ctx_sync_pairs(c, c->xs[0]))
+            return rc;
         if (pending && cudaEventQuery(c->ev_frame) == cudaSuccess)
             if (int rc = finish_pending())
                 return rc;
+        if (lost_shortcut(out))
+            return LVTK_OK;
+        const bool first_frame = state == 1;
         const int s = c->parity;
         c->parity ^= 1;
         cudaStream_t xl = c->xs[0], xr = c->xs[1], st = c->stream;
@@ -1080,7 +1210,7 @@ struct System
             return rc;
         if (int rc = launch_detect(c->pool, c->wsx[0], c->dp, slots, 1, feats, kBriefBorder, 1, xl))
             return rc;
-        if (int rc = launch_brief(c->pool, slots, 1, feats, xl))
+        if (int rc = launch_brief(c->pool, slots, 1, feats, c->d_brief_offsets, xl))
             return rc;
         c->lanes.add_image(depth, sizeof(float) * (size_t)cols, h_depth, d_depth, sizeof(float) * (size_t)cols,
                            sizeof(float) * (size_t)cols, rows, 2 * c->upload_bands, 2);
@@ -1095,12 +1225,10 @@ struct System
             return rc;
         LVT_CUDA_TRY(cudaEventRecord(c->ev_left, xl));
         LVT_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_left, 0));
-        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc, c->row_cand[s],
-                                        c->fcap, st, nullptr, 1, c->d_early, ++c->early_seq))
+        if (int rc = ctx_launch_track(c, c->d_result, feats, c->row_cand[s], st, nullptr, 1, c->d_early, ++c->early_seq))
             return rc;
         LVT_CUDA_TRY(cudaEventRecord(c->ev_pose, st));
-        if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_result, c->map, c->staged, feats, c->tp, c->sc, c->row_cand[s],
-                                        c->fcap, st, nullptr, 2, nullptr))
+        if (int rc = ctx_launch_track(c, c->d_result, feats, c->row_cand[s], st, nullptr, 2))
             return rc;
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
         LVT_CUDA_TRY(cudaMemcpyAsync(c->h_error, c->ws.error, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1108,6 +1236,9 @@ struct System
         host_mark(2);
         if (int rc = wait_for_pose())
             return rc;
+        if (c->h_early->state == 0)
+            if (int rc = rerun_refused(feats, s))
+                return rc;
         host_mark(3);
         pending = true;
         const PoseD pose = c->h_early->pose;
@@ -1179,32 +1310,30 @@ struct System
         return LVTK_OK;
     }
 
-    int track_pool(int first, int n, double *poses /* n x 12: R row-major, t */, lvt_frame_info *infos)
+    // frames [start, n) of the batch that begins at pool frame `first`: enqueue, wait, fetch the results
+    int run_pool_range(int first, int start, int n)
     {
         lvtk_ctx *c = ctx;
-        if (sensor != 1 || first < 0 || n <= 0 || first + n > c->rpool_frames)
-            return LVTK_ERR_ARG;
-        if (int rc = finish_pending())
-            return rc;
-        // the batch is timed on the device: first extraction launch .. last result copy
+        // timed on the device: first extraction launch .. last result copy
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
         for (int x = 0; x < lvtk_ctx::kXStreams; x++)
             LVT_CUDA_TRY(cudaStreamWaitEvent(c->xs[x], c->ev_batch[0], 0));
-        for (int i = 0; i < n; i++)
+        for (int i = start; i < n; i++)
         {
-            // frame i: extraction pipeline i % kXStreams, feature set i % kSets.  Extraction is
+            // frame i: extraction pipeline k % kXStreams, feature set k % kSets.  Extraction is
             // state-free, so up to kXStreams frames are extracted concurrently while the tracking
             // stream consumes them in order; a set is reused only after its frame has been tracked.
-            const int set = i % lvtk_ctx::kSets, x = i % lvtk_ctx::kXStreams;
+            const int k = i - start;
+            const int set = k % lvtk_ctx::kSets, x = k % lvtk_ctx::kXStreams;
             cudaStream_t sx = c->xs[x];
-            if (i >= lvtk_ctx::kSets)
+            if (k >= lvtk_ctx::kSets)
                 LVT_CUDA_TRY(cudaStreamWaitEvent(sx, c->ev_tracked[set], 0));
             const int *slots = c->d_slot_table + 2 * (size_t)(first + i);
             FeatDev *feats = c->feats_d + 2 * set;
             if (int rc = launch_detect(c->rpool, c->wsx[x], c->dp, slots, 2, feats, kBriefBorder, 1, sx))
                 return rc;
             const bool fused_index = brief_can_index(c->cam);
-            if (int rc = launch_brief(c->rpool, slots, 2, feats, sx, fused_index ? &c->cam : nullptr))
+            if (int rc = launch_brief(c->rpool, slots, 2, feats, c->d_brief_offsets, sx, fused_index ? &c->cam : nullptr))
                 return rc;
             if (!fused_index)
                 if (int rc = launch_index(feats, 2, c->cam, sx))
@@ -1213,21 +1342,51 @@ struct System
                 return rc;
             LVT_CUDA_TRY(cudaEventRecord(c->ev_extracted[set], sx));
             LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_extracted[set], 0));
-            if (int rc = launch_track_frame(c->d_state, c->d_ctl, c->d_results + i, c->map, c->staged, feats, c->tp, c->sc,
-                                            c->row_cand[set], c->fcap, c->stream))
+            if (int rc = ctx_launch_track(c, c->d_results + i, feats, c->row_cand[set], c->stream))
                 return rc;
             LVT_CUDA_TRY(cudaEventRecord(c->ev_tracked[set], c->stream));
             c->last_set = set;
         }
-        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_results, c->d_results, sizeof(FrameResult) * (size_t)n, cudaMemcpyDeviceToHost,
-                                     c->stream));
+        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_results + start, c->d_results + start, sizeof(FrameResult) * (size_t)(n - start),
+                                     cudaMemcpyDeviceToHost, c->stream));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[1], c->stream));
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
         for (int x = 0; x < lvtk_ctx::kXStreams; x++)
             LVT_CUDA_TRY(cudaStreamSynchronize(c->xs[x]));
-        LVT_CUDA_TRY(cudaEventElapsedTime(&c->last_batch_ms, c->ev_batch[0], c->ev_batch[1]));
+        float ms = 0.f;
+        LVT_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_batch[0], c->ev_batch[1]));
+        c->last_batch_ms += ms;
         if (int e = ctx_check_error(c))
             return e;
+        return LVTK_OK;
+    }
+
+    int track_pool(int first, int n, double *poses /* n x 12: R row-major, t */, lvt_frame_info *infos)
+    {
+        lvtk_ctx *c = ctx;
+        if (sensor != 1 || first < 0 || n <= 0 || first + n > c->rpool_frames)
+            return LVTK_ERR_ARG;
+        if (int rc = finish_pending())
+            return rc;
+        if (int rc = ctx_sync_pairs(c, c->stream))
+            return rc;
+        // A frame that could overflow the point stores is refused on the device, and so is every frame
+        // behind it (TrackState::halt): grow the stores and run the rest of the batch again.
+        c->last_batch_ms = 0.f;
+        for (int start = 0; start < n;)
+        {
+            if (int rc = run_pool_range(first, start, n))
+                return rc;
+            int refused = n;
+            for (int i = start; i < n && refused == n; i++)
+                if (c->h_results[i].info.state == 0)
+                    refused = i;
+            if (refused == n)
+                break;
+            if (int rc = ctx_grow_points(c))
+                return rc;
+            start = refused;
+        }
         for (int i = 0; i < n; i++)
         {
             const FrameResult &r = c->h_results[i];
@@ -1345,7 +1504,7 @@ LVT_API void lvt_track(lvt_handle h, unsigned char *left, unsigned char *right, 
         return;
     cudaSetDevice(vo->ctx->device);
     PoseD pose;
-    if (vo->track_stereo(left, right, n_rows, n_cols, &pose) == LVTK_OK)
+    if ((vo->last_status = vo->track_stereo(left, right, n_rows, n_cols, &pose)) == LVTK_OK)
         write_pose(pose, R, t);
 }
 
@@ -1357,7 +1516,7 @@ LVT_API void lvt_track_rgbd(lvt_handle h, const unsigned char *gray, const float
         return;
     cudaSetDevice(vo->ctx->device);
     PoseD pose;
-    if (vo->track_rgbd(gray, depth_m, n_rows, n_cols, &pose) == LVTK_OK)
+    if ((vo->last_status = vo->track_rgbd(gray, depth_m, n_rows, n_cols, &pose)) == LVTK_OK)
         write_pose(pose, R, t);
 }
 
@@ -1370,7 +1529,8 @@ LVT_API void lvt_track_with_external_corners(lvt_handle h, unsigned char *left, 
         return;
     cudaSetDevice(vo->ctx->device);
     PoseD pose;
-    if (vo->track_external(left, right, n_rows, n_cols, corners_left, n_left, corners_right, n_right, &pose) == LVTK_OK)
+    if ((vo->last_status = vo->track_external(left, right, n_rows, n_cols, corners_left, n_left, corners_right, n_right,
+                                              &pose)) == LVTK_OK)
         write_pose(pose, R, t);
 }
 
@@ -1378,6 +1538,12 @@ LVT_API int lvt_get_status(lvt_handle h)
 {
     System *vo = static_cast<System *>(h);
     return vo ? vo->state : -1;
+}
+
+LVT_API int lvt_get_last_status(lvt_handle h)
+{
+    System *vo = static_cast<System *>(h);
+    return vo ? vo->last_status : LVTK_ERR_ARG;
 }
 
 // ---- extensions --------------------------------------------------------------------------------
@@ -1463,6 +1629,12 @@ LVT_API int lvt_debug_get_points(lvt_handle h, int which, double *xyz, unsigned 
     return n;
 }
 
+LVT_API int lvt_debug_point_capacity(lvt_handle h)
+{
+    System *vo = static_cast<System *>(h);
+    return vo ? vo->ctx->pcap : -1;
+}
+
 LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
 {
     if (pairs)
@@ -1471,15 +1643,13 @@ LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
             for (int j = 0; j < 4; j++)
                 if (pairs[i][j] < -24 || pairs[i][j] > 24)
                     return -1;
+    }
+    // live contexts (any device, any thread) pick the table up at their next extraction
+    std::lock_guard<std::mutex> lk(g_pairs_mu);
+    if (pairs)
         std::memcpy(g_pairs, pairs, sizeof(g_pairs));
-    }
     g_pairs_custom = pairs != nullptr;
-    if (g_pairs_uploaded) // a device is already in use: refresh its table
-    {
-        const int rc = upload_brief_pairs(g_pairs_custom ? g_pairs : nullptr);
-        cudaDeviceSynchronize();
-        return rc;
-    }
+    g_pairs_version.fetch_add(1, std::memory_order_release);
     return 0;
 }
 
@@ -1528,7 +1698,7 @@ LVT_API int lvt_track_pool(lvt_handle h, int first_frame, int n_frames, double *
     if (!vo)
         return LVTK_ERR_ARG;
     cudaSetDevice(vo->ctx->device);
-    const int rc = vo->track_pool(first_frame, n_frames, poses, infos);
+    const int rc = vo->last_status = vo->track_pool(first_frame, n_frames, poses, infos);
     if (prof_enabled())
         prof_collect();
     return rc;
@@ -1699,6 +1869,8 @@ LVT_API int lvtk_brief(lvtk_ctx *c, const uint8_t *img, int rows, int cols, int 
     if (n_in > c->fcap)
         return LVTK_ERR_CAPACITY;
     cudaSetDevice(c->device);
+    if (int rc = ctx_sync_pairs(c, c->stream))
+        return rc;
     if (int rc = ctx_upload_image(c, 0, img, rows, cols, stride))
         return rc;
     std::vector<float2> xy(std::max(n_in, 1));
@@ -1712,10 +1884,10 @@ LVT_API int lvtk_brief(lvtk_ctx *c, const uint8_t *img, int rows, int cols, int 
     LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_resp, resp.data(), sizeof(float) * std::max(n_in, 1), cudaMemcpyHostToDevice, c->stream));
     LVT_CUDA_TRY(cudaMemcpyAsync(c->d_in_n, &n_in, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (int rc = launch_border_filter(c->d_in_xy, c->d_in_resp, c->d_in_n, c->pcap, c->feats_d, 1, rows, cols, c->ws.error,
+    if (int rc = launch_border_filter(c->d_in_xy, c->d_in_resp, c->d_in_n, c->in_cap, c->feats_d, 1, rows, cols, c->ws.error,
                                       c->stream))
         return rc;
-    if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
+    if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->d_brief_offsets, c->stream))
         return rc;
     if (int e = ctx_check_error(c))
         return e;
@@ -1728,11 +1900,13 @@ LVT_API int lvtk_extract(lvtk_ctx *c, const uint8_t *img, int rows, int cols, in
     if (!c || !img || !n_out || rows != c->params.img_height || cols != c->params.img_width || stride < cols)
         return LVTK_ERR_ARG;
     cudaSetDevice(c->device);
+    if (int rc = ctx_sync_pairs(c, c->stream))
+        return rc;
     if (int rc = ctx_upload_image(c, 0, img, rows, cols, stride))
         return rc;
     if (int rc = launch_detect(c->pool, c->ws, c->dp, c->d_slots, 1, c->feats_d, kBriefBorder, 1, c->stream))
         return rc;
-    if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->stream))
+    if (int rc = launch_brief(c->pool, c->d_slots, 1, c->feats_d, c->d_brief_offsets, c->stream))
         return rc;
     if (int e = ctx_check_error(c))
         return e;
@@ -1746,7 +1920,7 @@ LVT_API int lvtk_match_projected(lvtk_ctx *c, const double *pts_xyz, const uint8
 {
     if (!c || m < 0 || n < 0 || !out_match_idx || !q || !t)
         return LVTK_ERR_ARG;
-    if (m > c->pcap || n > c->fcap)
+    if (m > std::min(c->in_cap, c->pcap) || n > c->fcap)
         return LVTK_ERR_CAPACITY;
     cudaSetDevice(c->device);
     if (int rc = ctx_upload_features(c, 0, kps, desc, n, matched_flags))
@@ -1757,7 +1931,7 @@ LVT_API int lvtk_match_projected(lvtk_ctx *c, const double *pts_xyz, const uint8
         LVT_CUDA_TRY(cudaMemcpyAsync(c->map.desc, pts_desc, (size_t)32 * m, cudaMemcpyHostToDevice, c->stream));
     }
     if (int rc = launch_match_seam(c->map.xyz, c->map.desc, m, make_pose(q, t), c->feats_d, c->cam, retry_below, c->sc.ms,
-                                   c->sc.map_cand, c->d_int_a, c->d_f_a, c->d_f_b, c->d_int_b, c->fcap, c->stream))
+                                   c->sc.map_cand, c->d_int_a, c->d_f_a, c->d_f_b, c->d_int_b, c->tcfg, c->stream))
         return rc;
     int cr[2] = {0, 0};
     if (m)
@@ -1793,7 +1967,7 @@ LVT_API int lvtk_row_match(lvtk_ctx *c, const lvtk_keypoint *kl, const uint8_t *
     if (int rc = ctx_upload_features(c, 1, kr, dr, nr, mr))
         return rc;
     if (int rc = launch_row_seam(c->feats_d, c->cam, c->row_cand[0], c->sc.row_choice, c->sc.ms.items, c->sc.pair_query,
-                                 c->sc.pair_train, c->d_int_b, c->fcap, c->stream))
+                                 c->sc.pair_train, c->d_int_b, c->tcfg, c->stream))
         return rc;
     int np = 0;
     LVT_CUDA_TRY(cudaMemcpyAsync(&np, c->d_int_b, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1817,7 +1991,7 @@ LVT_API int lvtk_solve_pose(lvtk_ctx *c, const double *pts_xyz, const float *uv,
 {
     if (!c || m < 0 || !q_in || !t_in || !q_out || !t_out)
         return LVTK_ERR_ARG;
-    if (m > c->pcap)
+    if (m > std::min(c->in_cap, c->pcap))
         return LVTK_ERR_CAPACITY;
     cudaSetDevice(c->device);
     if (m)
@@ -1886,7 +2060,7 @@ LVT_API int lvtk_triangulate(lvtk_ctx *c, const double q[4], const double t[3], 
 {
     if (!c || n < 0 || !q || !t)
         return LVTK_ERR_ARG;
-    if (n > c->pcap)
+    if (n > std::min(c->in_cap, c->pcap))
         return LVTK_ERR_CAPACITY;
     if (n == 0)
         return LVTK_OK;

@@ -9,18 +9,21 @@ namespace lvtb
 int launch_border_filter(const float2 *src_xy, const float *src_resp, const int *src_n, int src_stride,
                          const FeatDev *d_feats, int n_images, int rows, int cols, int *error, cudaStream_t stream);
 int launch_depth_gate(const FeatDev &f, const float *d_depth, const lvt_params_c &p, cudaStream_t stream);
+int track_configure(int owner_cap, TrackLaunchCfg *cfg);
 int launch_track_frame(TrackState *st, void *ctl, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
-                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready = nullptr, int parts = 3,
-                       EarlyResult *early = nullptr, int early_seq = 0);
+                       const TrackLaunchCfg &cfg, int *d_error, cudaStream_t stream, cudaEvent_t right_ready = nullptr,
+                       int parts = 3, EarlyResult *early = nullptr, int early_seq = 0);
+int launch_clear_halt(TrackState *st, cudaStream_t stream);
 size_t frame_ctl_bytes();
 int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists &L, cudaStream_t stream);
 int launch_reset_state(TrackState *st, cudaStream_t stream);
 int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const PoseD &pose, const FeatDev *d_feat,
                       const CamParams &cam, int retry_below, const MatchScratch &ms, const CandLists &lists,
-                      int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream);
+                      int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, const TrackLaunchCfg &cfg,
+                      cudaStream_t stream);
 int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandLists &lists, int *d_choice, int *d_items,
-                    int *d_query, int *d_train, int *d_count, int owner_cap, cudaStream_t stream);
+                    int *d_query, int *d_train, int *d_count, const TrackLaunchCfg &cfg, cudaStream_t stream);
 int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD &init, const CamParams &cam,
                      uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, int *d_n_inliers, cudaStream_t stream);
 int launch_tri_seam(const PoseD &pose, const CamParams &cam, const float2 *d_uvl, const float2 *d_uvr, int n,
@@ -45,6 +48,29 @@ struct DeviceArena
         blocks.push_back(q);
         total += bytes;
         *p = static_cast<T *>(q);
+        return LVTK_OK;
+    }
+    // move an allocation to a new size (contents copied, the rest zeroed); everything on the device is idle
+    template <class T>
+    int regrow(T **p, size_t old_count, size_t new_count)
+    {
+        T *old = *p, *q = nullptr;
+        if (int rc = alloc(&q, new_count))
+            return rc;
+        if (old && old_count)
+            if (cudaMemcpy(q, old, sizeof(T) * (old_count < new_count ? old_count : new_count), cudaMemcpyDeviceToDevice) != cudaSuccess)
+            {
+                set_last_error(__FILE__, __LINE__, "cudaMemcpy failed");
+                return LVTK_ERR_CUDA;
+            }
+        for (size_t i = 0; i < blocks.size(); i++)
+            if (blocks[i] == old)
+            {
+                blocks.erase(blocks.begin() + i);
+                break;
+            }
+        cudaFree(old);
+        *p = q;
         return LVTK_OK;
     }
     void release()

@@ -1800,14 +1800,12 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
     if (n_images > ws.batch || dp.grid.count() != ws.n_tiles || ws.n_tiles > 1024)
         return LVTK_ERR_ARG;
     const int nt = ws.n_tiles;
-    static int smem_set_dev = -1; // function attributes are per device
-    int cur_dev = 0;
-    LVT_CUDA_TRY(cudaGetDevice(&cur_dev));
-    if (smem_set_dev != cur_dev)
-    {
-        LVT_CUDA_TRY(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-        smem_set_dev = cur_dev;
-    }
+    static DeviceOnce once;
+    if (int rc = once.run([](int) {
+            LVT_CUDA_TRY(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+            return (int)LVTK_OK;
+        }))
+        return rc;
     const bool allow_retry = dp.threshold_low < dp.threshold;
 
     ScoreArgs sa{d_slots, ws.score, dp.grid, dp.pitch, dp.rows, dp.cols, allow_retry ? dp.threshold_low : dp.threshold,

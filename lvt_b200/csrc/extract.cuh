@@ -96,10 +96,11 @@ int launch_detect(const ImagePool &pool, const DetectWorkspace &ws, const Detect
                   cudaStream_t stream);
 // index_cam != nullptr: one extra CTA per image builds the feature index (hash grid, row CSR, cleared
 // marks) next to the descriptors, replacing a launch_index call; requires brief_can_index(cam)
-int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, cudaStream_t stream,
-                 const CamParams *index_cam = nullptr);
+int launch_brief(const ImagePool &pool, const int *d_slots, int n_images, const FeatDev *d_feats, const uint32_t *d_offsets,
+                 cudaStream_t stream, const CamParams *index_cam = nullptr);
 bool brief_can_index(const CamParams &cam);
 int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cudaStream_t stream);
-int upload_brief_pairs(const signed char pairs[256][4]);
+// pairs == nullptr: the built-in table (brief_pairs.inc); h: what brief_kernel reads (BriefArgs::offsets)
+void make_brief_offsets(const signed char pairs[256][4], uint32_t h[8 * 32]);
 
 } // namespace lvtb

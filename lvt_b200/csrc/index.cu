@@ -24,19 +24,18 @@ __global__ void __launch_bounds__(1024) index_kernel(IndexArgs a)
 int launch_index(const FeatDev *d_feats, int n_images, const CamParams &cam, cudaStream_t stream)
 {
     const int bytes = index_smem_ints(cam) * (int)sizeof(int);
-    static int configured = 0, configured_dev = -1; // function attributes are per device
-    int cur_dev = 0;
-    LVT_CUDA_TRY(cudaGetDevice(&cur_dev));
-    if (cur_dev != configured_dev)
-    {
-        configured = 0;
-        configured_dev = cur_dev;
-    }
-    if (bytes > configured)
-    {
-        LVT_CUDA_TRY(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        configured = bytes;
-    }
+    // once per device: the largest dynamic size the device allows (the size of a launch depends on the image)
+    static DeviceOnce once;
+    if (int rc = once.run([](int dev) {
+            int optin = 0;
+            LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            cudaFuncAttributes fa;
+            LVT_CUDA_TRY(cudaFuncGetAttributes(&fa, index_kernel));
+            LVT_CUDA_TRY(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              optin - (int)fa.sharedSizeBytes));
+            return (int)LVTK_OK;
+        }))
+        return rc;
     IndexArgs ia{d_feats, cam};
     LVT_TIMED(stream, K_INDEX, launch_chained(index_kernel, dim3(n_images), dim3(1024), bytes, stream, ia));
     LVT_LAUNCH_CHECK(stream, "index_kernel");

@@ -32,7 +32,8 @@ constexpr int kCandWarps = 8;
 struct FrameCtl
 {
     int mode; // 0 frame finished by track_a (was lost already), 1 tracking continues, 2 first frame (track_b seeds
-              // the map), 3 lost in this frame (track_b, which may read the right image's features, reports)
+              // the map), 3 lost in this frame (track_b, which may read the right image's features, reports),
+              // 4 refused: the point stores could overflow in this frame (TrackState::halt), nothing was touched
     int n_matches;
     int inliers;
     int pad;
@@ -56,6 +57,7 @@ struct TrackArgs
     int owner_cap;      // ints per owner array in dynamic shared memory
     int key_cap;        // candidate keys that fit behind the two owner arrays
     long long *dbg;     // clock64() trace of the map pass (LVT_B200_SYNC builds of the launch only)
+    int *error;         // the context's sticky error flag (the one the host fetches with every result)
 };
 
 struct TrackShared
@@ -233,7 +235,27 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     const int nl = state0 == 3 ? 0 : min(*fl.n, a.owner_cap);
     const int map_n = S.map_n, staged_n = S.staged_n;
     const PoseD last_pose = S.last_pose;
+    // The reference's point vectors grow without bound (lvt/src/lvt_local_map.cpp:331-353); the stores here
+    // have a capacity.  A frame adds at most nl points to either store and promotes at most staged_n, so a frame
+    // that could overflow is refused BEFORE anything is touched (this kernel is the first of the chain that
+    // writes state); the host grows the stores and runs the frame again.  Uniform over the cluster: rank 0
+    // writes S.halt only where this predicate already holds.
+    const bool refused = S.halt != 0 || (state0 != 3 && ((long)map_n + staged_n + nl > a.map.cap || (long)staged_n + nl > a.staged.cap));
     __syncthreads();
+    if (refused)
+    {
+        if (threadIdx.x == 0 && rank == 0)
+        {
+            if (S.halt == 0)
+                S.halt = S.frame_number + 1;
+            lvt_frame_info z = {};
+            ctl.info = z; // state 0: not processed
+            ctl.mode = 4;
+            a.result->info = z;
+            a.result->pose = last_pose;
+        }
+        return;
+    }
     if (threadIdx.x == 0 && rank == 0)
     {
         lvt_frame_info z = {};
@@ -385,7 +407,7 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
                 id.q = Quat{1, 0, 0, 0};
                 id.t[0] = id.t[1] = id.t[2] = 0;
                 a.early->pose = mode == 2 ? id : a.st->last_pose;
-                a.early->state = mode == 2 ? 2 : 3;
+                a.early->state = mode == 2 ? 2 : (mode == 4 ? 0 /* refused: grow the stores, run again */ : 3);
                 __threadfence_system();
                 *reinterpret_cast<volatile int *>(&a.early->seq) = a.early_seq;
             }
@@ -498,8 +520,8 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
     }
     if (base + added > dst.cap)
     {
-        if (threadIdx.x == 0)
-            a.st->error = LVTK_ERR_CAPACITY;
+        if (threadIdx.x == 0) // unreachable since track_a refuses frames that could overflow; reported if it ever is
+            *a.error = a.st->error = LVTK_ERR_CAPACITY;
         added = dst.cap - base;
     }
     if (to_map)
@@ -521,8 +543,8 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
     FrameCtl &ctl = *a.ctl;
     const TrackParams &tp = a.tp;
     const int mode = ctl.mode;
-    if (mode == 0)
-        return; // track_a finished the frame (lost)
+    if (mode == 0 || mode == 4)
+        return; // track_a finished the frame (lost) or refused it (TrackState::halt)
     const FeatDev fl = a.feats[0], fr = a.feats[1];
     const int nl = min(*fl.n, a.owner_cap);
     const int nr = tp.sensor == 1 ? min(*fr.n, a.owner_cap) : 0;
@@ -630,7 +652,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         if (map_n > a.map.cap)
         {
             if (threadIdx.x == 0)
-                S.error = LVTK_ERR_CAPACITY;
+                *a.error = S.error = LVTK_ERR_CAPACITY;
             map_n = a.map.cap;
         }
         staged_n = block_compact_points(a.staged, Sn, [flag](int i) { return flag[i] == 1; }, sh.scan);
@@ -684,10 +706,13 @@ __global__ void reset_state_kernel(TrackState *st)
     S.map_n = S.staged_n = 0;
     S.last_matches[0] = S.last_matches[1] = S.last_matches[2] = 0x7FFFFFFF;
     S.error = 0;
+    S.halt = 0;
     S.last_pose.q = Quat{1, 0, 0, 0};
     S.last_pose.t[0] = S.last_pose.t[1] = S.last_pose.t[2] = 0;
     motion_reset(S.motion);
 }
+
+__global__ void clear_halt_kernel(TrackState *st) { st->halt = 0; }
 
 // ---------------------------------------------------------------------------------------------
 // seam kernels
@@ -802,39 +827,47 @@ __global__ void tri_seam_kernel(TriSeamArgs a)
 // host launchers
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory of the single-CTA kernels: two owner arrays + as many candidate keys as fit
-// next to them (block_rounds keeps the key lists of its queries there)
-// (function attributes are per device: the caches below are reset when the calling thread's device changes)
-static int g_key_cap = 0;
-static int g_track_cluster = 1; // CTAs of track_a_kernel's cluster
-static size_t track_smem_bytes(int owner_cap) { return (2 * (size_t)owner_cap + (size_t)g_key_cap) * sizeof(int); }
+// next to them (block_rounds keeps the key lists of its queries there).  Function attributes are per
+// device: set once per device to the most a launch can ask for; what a context actually uses is in its
+// TrackLaunchCfg (no process-wide mutable state: handles on any device / thread are independent).
+constexpr int kTrackStaticSmem = 2048; // static shared memory of the tracking kernels, rounded up
 
-static int ensure_smem(int owner_cap)
+static size_t track_smem_bytes(const TrackLaunchCfg &cfg) { return (2 * (size_t)cfg.owner_cap + (size_t)cfg.key_cap) * sizeof(int); }
+
+static int ensure_smem()
 {
-    static int configured = 0, configured_dev = -1;
-    int dev = 0;
-    LVT_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev != configured_dev)
-    {
-        configured = 0;
-        configured_dev = dev;
-    }
-    if (owner_cap > configured)
-    {
+    static DeviceOnce once;
+    return once.run([](int dev) {
         int optin = 0;
         LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        const int avail = optin - 2048 /* static */ - 2 * owner_cap * (int)sizeof(int);
-        g_key_cap = avail > 0 ? (avail / (int)sizeof(int)) & ~3 : 0;
-        g_track_cluster = kTrackCluster;
-        if (const char *e = std::getenv("LVT_B200_TRACK_CLUSTER")) // 1 or 8 (tuning aid; the home slices of the
-            g_track_cluster = std::atoi(e) >= 8 ? 8 : 1;             // team are sized for 8 CTAs)
-        const int bytes = (int)track_smem_bytes(owner_cap);
+        const int bytes = optin - kTrackStaticSmem;
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(match_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(row_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoseShared)));
-        configured = owner_cap;
+        return (int)LVTK_OK;
+    });
+}
+
+int track_configure(int owner_cap, TrackLaunchCfg *cfg)
+{
+    if (int rc = ensure_smem())
+        return rc;
+    int dev = 0, optin = 0;
+    LVT_CUDA_TRY(cudaGetDevice(&dev));
+    LVT_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int avail = optin - kTrackStaticSmem - 2 * owner_cap * (int)sizeof(int);
+    if (avail < 0)
+    {
+        set_last_error(__FILE__, __LINE__, "the owner arrays do not fit in shared memory");
+        return LVTK_ERR_ARG;
     }
+    cfg->owner_cap = owner_cap;
+    cfg->key_cap = (avail / (int)sizeof(int)) & ~3;
+    cfg->cluster = kTrackCluster;
+    if (const char *e = std::getenv("LVT_B200_TRACK_CLUSTER")) // 1 or 8 (tuning aid; the home slices of the
+        cfg->cluster = std::atoi(e) >= 8 ? 8 : 1;              // team are sized for 8 CTAs)
     return LVTK_OK;
 }
 
@@ -850,22 +883,20 @@ int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists
 
 int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
-                       int owner_cap, cudaStream_t stream, cudaEvent_t right_ready, int parts, EarlyResult *early,
-                       int early_seq)
+                       const TrackLaunchCfg &cfg, int *d_error, cudaStream_t stream, cudaEvent_t right_ready, int parts,
+                       EarlyResult *early, int early_seq)
 {
     // parts: 1 = up to the pose (mapcand, track_a, pose), 2 = the rest (stagedcand, track_b), 3 = the whole frame
-    if (int rc = ensure_smem(owner_cap))
-        return rc;
     FrameCtl *ctl = static_cast<FrameCtl *>(ctl_v);
-    const size_t smem = track_smem_bytes(owner_cap);
-    TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, owner_cap, g_key_cap,
-                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr};
+    const size_t smem = track_smem_bytes(cfg);
+    TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, cfg.owner_cap, cfg.key_cap,
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr, d_error};
     if (parts & 1)
     {
     MapCandArgs mc{st, ctl, 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
     LVT_TIMED(stream, K_MAPCAND, launch_chained(mapcand_kernel, dim3(148 * 2), dim3(kCandWarps * 32), 0, stream, mc));
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
-    LVT_TIMED(stream, K_TRACK_A, launch_chained_cluster(track_a_kernel, dim3(g_track_cluster), dim3(kTrackThreads), smem, stream, g_track_cluster, a));
+    LVT_TIMED(stream, K_TRACK_A, launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
                 debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early, early_seq};
@@ -916,6 +947,13 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     return LVTK_OK;
 }
 
+int launch_clear_halt(TrackState *st, cudaStream_t stream)
+{
+    clear_halt_kernel<<<1, 1, 0, stream>>>(st);
+    LVT_LAUNCH_CHECK(stream, "clear_halt_kernel");
+    return LVTK_OK;
+}
+
 int launch_reset_state(TrackState *st, cudaStream_t stream)
 {
     reset_state_kernel<<<1, 1, 0, stream>>>(st);
@@ -925,28 +963,25 @@ int launch_reset_state(TrackState *st, cudaStream_t stream)
 
 int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const PoseD &pose, const FeatDev *d_feat,
                       const CamParams &cam, int retry_below, const MatchScratch &ms, const CandLists &lists,
-                      int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, int owner_cap, cudaStream_t stream)
+                      int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, const TrackLaunchCfg &cfg,
+                      cudaStream_t stream)
 {
-    if (int rc = ensure_smem(owner_cap))
-        return rc;
     MapCandArgs mc{nullptr, nullptr, 0, 0, pose, m, d_xyz, d_pdesc, d_feat, cam, ms, lists};
     mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc);
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
-    MatchSeamArgs a{d_pdesc, m, d_feat, cam, retry_below, ms, lists, d_match_idx, d_d1, d_d2, d_count_retried, owner_cap, g_key_cap};
-    match_seam_kernel<<<1, kTrackThreads, track_smem_bytes(owner_cap), stream>>>(a);
+    MatchSeamArgs a{d_pdesc, m, d_feat, cam, retry_below, ms, lists, d_match_idx, d_d1, d_d2, d_count_retried, cfg.owner_cap, cfg.key_cap};
+    match_seam_kernel<<<1, kTrackThreads, track_smem_bytes(cfg), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "match_seam_kernel");
     return LVTK_OK;
 }
 
 int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandLists &lists, int *d_choice, int *d_items,
-                    int *d_query, int *d_train, int *d_count, int owner_cap, cudaStream_t stream)
+                    int *d_query, int *d_train, int *d_count, const TrackLaunchCfg &cfg, cudaStream_t stream)
 {
-    if (int rc = ensure_smem(owner_cap))
-        return rc;
     if (int rc = launch_rowcand(d_feats, cam, lists, stream))
         return rc;
-    RowSeamArgs a{d_feats, cam, lists, d_choice, d_items, d_query, d_train, d_count, owner_cap, g_key_cap};
-    row_seam_kernel<<<1, kTrackThreads, track_smem_bytes(owner_cap), stream>>>(a);
+    RowSeamArgs a{d_feats, cam, lists, d_choice, d_items, d_query, d_train, d_count, cfg.owner_cap, cfg.key_cap};
+    row_seam_kernel<<<1, kTrackThreads, track_smem_bytes(cfg), stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "row_seam_kernel");
     return LVTK_OK;
 }
@@ -954,7 +989,7 @@ int launch_row_seam(const FeatDev *d_feats, const CamParams &cam, const CandList
 int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD &init, const CamParams &cam,
                      uint8_t *d_level, uint8_t *d_inlier, double *d_e2, PoseD *d_out, int *d_n_inliers, cudaStream_t stream)
 {
-    if (int rc = ensure_smem(16))
+    if (int rc = ensure_smem())
         return rc;
     PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr, nullptr, nullptr, 0};
     pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(a);

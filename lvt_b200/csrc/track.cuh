@@ -37,6 +37,9 @@ struct TrackState
     int map_n, staged_n;
     int last_matches[3]; // lvt/src/lvt_system.cpp:37, N_MATCHES_WINDOWS = 3
     int error;           // sticky LVTK_ERR_*
+    int halt;            // != 0: frame number (1-based) of the first frame refused because the point stores could
+                         // overflow; that frame and every later one leave the state untouched until the host has
+                         // grown the stores and cleared this (lvtk_ctx: ctx_grow_points)
     PoseD last_pose;
     MotionState motion;
     // world->camera of the pose the motion model predicts for the NEXT frame, prepared by the kernel
@@ -71,6 +74,15 @@ struct TrackParams
     int untracked_threshold; // untracked_threshold
     int staged_threshold;
     int triangulation_policy;
+};
+
+// shared-memory layout of the tracking kernels for one context (track_configure: per-device function
+// attributes set once, thread-safe; nothing process-wide is consulted at launch time)
+struct TrackLaunchCfg
+{
+    int owner_cap = 0; // ints per owner array (= feature capacity)
+    int key_cap = 0;   // candidate keys that fit behind the two owner arrays
+    int cluster = 1;   // CTAs of track_a_kernel's cluster
 };
 
 // scratch for one tracking CTA (global memory, sized for the point / feature capacities)

@@ -57,7 +57,6 @@ class UploadLanes
     void start(int device, int n_workers)
     {
         (void)device;
-        next_.store(1 << 30);
         for (int i = 0; i < n_workers; i++)
             workers_.emplace_back([this] { worker(); });
     }
@@ -113,8 +112,11 @@ class UploadLanes
         const int n = n_bands_;
         for (int i = 0; i < n; i++)
             staged_[i].store(0, std::memory_order_relaxed);
-        n_active_.store(n, std::memory_order_relaxed);
-        next_.store(0, std::memory_order_release); // opens the job: bands_ / n_active_ are complete
+        // Jobs carry an epoch: a helper that drew its index from the previous job's (exhausted) counter
+        // sees a job word of another epoch and drops it, so no band is ever copied twice.
+        const uint64_t epoch = ++epoch_;
+        job_.store(epoch << 32 | (uint32_t)n, std::memory_order_relaxed);
+        next_.store(epoch << 32, std::memory_order_release); // opens the job: bands_ / job_ are complete
         if (!workers_.empty() && n > 1)
         {
             generation_.fetch_add(1);
@@ -151,7 +153,7 @@ class UploadLanes
         };
         for (;;)
         {
-            const int i = next_.fetch_add(1, std::memory_order_acq_rel);
+            const int i = (int)(uint32_t)next_.fetch_add(1, std::memory_order_acq_rel); // the epoch is this job's
             if (i >= n)
                 break;
             copy_band(i);
@@ -197,10 +199,11 @@ class UploadLanes
                 return;
             for (;;)
             {
-                const int i = next_.fetch_add(1, std::memory_order_acq_rel);
-                if (i >= n_active_.load(std::memory_order_relaxed) || i < 0)
-                    break;
-                copy_band(i);
+                const uint64_t v = next_.fetch_add(1, std::memory_order_acq_rel);
+                const uint64_t job = job_.load(std::memory_order_acquire);
+                if ((v >> 32) != (job >> 32) || (uint32_t)v >= (uint32_t)job)
+                    break; // exhausted, or an index of a job that is over
+                copy_band((int)(uint32_t)v);
             }
             last_job = std::chrono::steady_clock::now();
         }
@@ -215,8 +218,9 @@ class UploadLanes
 
     UploadBand bands_[kMaxBands];
     int n_bands_ = 0;
-    std::atomic<int> n_active_{0}; // written before next_ is released
-    std::atomic<int> next_{1 << 30};
+    uint64_t epoch_ = 0;               // of the calling thread
+    std::atomic<uint64_t> job_{0};     // epoch << 32 | bands of the job; written before next_ is released
+    std::atomic<uint64_t> next_{~0ull >> 1}; // epoch << 32 | next band to hand out
     std::atomic<int> staged_[kMaxBands];
 };
 

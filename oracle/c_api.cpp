@@ -395,6 +395,9 @@ LVT_API int lvt_get_status(lvt_handle h)
     return -1;
 }
 
+/* the oracle has no failure mode of its own: a call that went wrong threw and left the outputs untouched */
+LVT_API int lvt_get_last_status(lvt_handle h) { return h ? 0 : -1; }
+
 /* ---- extensions ------------------------------------------------------------------------ */
 LVT_API void lvt_params_default(lvt_params_c *p) { params_default(p); }
 LVT_API int lvt_params_from_file(lvt_params_c *p, const char *f) { return params_from_file(p, f); }
@@ -468,6 +471,8 @@ LVT_API int lvt_debug_get_points(lvt_handle h, int which, double *xyz, unsigned 
     }
     return n;
 }
+
+LVT_API int lvt_debug_point_capacity(lvt_handle) { return 0; } /* std::vector: unbounded */
 
 LVT_API int lvt_set_brief_pairs(const signed char pairs[256][4])
 {

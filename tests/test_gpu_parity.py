@@ -337,9 +337,24 @@ def test_create_from_yaml_and_bad_args(cuda, tmp_path):
     assert vo is not None and vo.get_state() == 1
     assert cuda.create_from_file(str(tmp_path / "nope.yaml")) is None
     assert cuda.lib.lvt_create(str(f).encode(), 7) is None
-    # wrong image size: outputs untouched (the reference swallows the failure, lvt_c.cpp:63-88)
+    # wrong image size: outputs untouched (the reference swallows the failure, lvt_c.cpp:63-88);
+    # the status is available through the additive lvt_get_last_status
+    vo.check_status = False
     R, t = vo.track(np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))
-    assert not R.any() and not t.any() and vo.get_state() == 1
+    assert not R.any() and not t.any() and vo.get_state() == 1 and vo.last_status() == -1
+    vo.check_status = True
+    with pytest.raises(capi.LvtError):
+        vo.track(np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))
+    # an entry point that does not match the handle's sensor type is refused (not tracked on stale buffers)
+    with pytest.raises(capi.LvtError):
+        vo.track_rgbd(np.zeros((375, 1242), np.uint8), np.ones((375, 1242), np.float32))
+    assert vo.get_state() == 1 and vo.frame_info()["frame_number"] == 0
+    rgbd = cuda.create(configs.make_params("tum_synth"), 2)
+    with pytest.raises(capi.LvtError):
+        rgbd.track(np.zeros((480, 640), np.uint8), np.zeros((480, 640), np.uint8))
+    st = make_stream("kitti_synth", 1)
+    vo.track(*st.frame(0))
+    assert vo.last_status() == 0 and vo.get_state() == 2
 
 
 def test_track_pool_equals_per_frame_calls(cuda, oracle):
