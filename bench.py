@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""Benchmark of the per-frame track() path (BASELINE.json metric: stereo frames/s at 1242x375).
+"""Benchmark of the per-frame track() path (BASELINE.json metric: stereo frames/s at 1242x375; ATE vs reference).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --config euroc --seqs-per-gpu 2 ...      # BASELINE config 5 (16 sequences on 8 GPUs)
+    python bench.py --config tum                             # BASELINE config 3 (640x480 RGB-D)
 
-A "step" is one pass of the hot path over FRAMES_PER_STEP consecutive frames of a synthetic stereo
-stream (1242x375, ~2000 keypoints/frame; the local map is the
-emergent ~2000 points).  N > 1: N independent sequences, one per GPU (weak scaling), the only
-collective is one NCCL broadcast of the calibration block.
+A "step" is one pass of the hot path over `frames_per_step` consecutive frames of a synthetic stream
+(default = config 2: 1242x375, ~2000 keypoints/frame, the local map is the emergent
+~2000 points).  N > 1: independent sequences, `--seqs-per-gpu` per GPU (weak scaling), the only collective
+is one NCCL broadcast of the calibration block.
 
-`value`  : whole-job frames/s with the frames already resident in HBM (lvt_track_pool), timed on the
-           device with CUDA events, max over ranks.
-`e2e`    : the same metric through the reference's own C call, lvt_track(handle, left*, right*, ...),
-           with HOST buffers -- H2D of both images and D2H of the pose inside the timed region.
+`value`  : whole-job frames/s with the frames already resident in HBM (lvt_track_pool), timed on the device
+           with CUDA events, max over ranks.
+`e2e`    : the same metric through the reference's own C call, lvt_track(handle, left*, right*, ...), with
+           HOST buffers -- H2D of both images and D2H of the pose inside the timed region, blocking per frame.
+`ate_vs_reference_m`: RMSE over frames of |t_b200 - t_oracle| (same world frame, no alignment) between
+           the e2e arm's trajectory and the CPU oracle's on the same frames (rank 0, sequence 0).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -29,12 +34,23 @@ sys.path.insert(0, ROOT)
 
 from lvt_b200 import capi, configs, synth  # noqa: E402
 
-CONFIG = "kitti_synth"
-FRAMES_PER_STEP = 50
-REF_FRAMES_PER_STEP = 10
+WORKLOADS = {
+    "kitti": dict(name="kitti_synth", metric="stereo frames/sec at 1242x375", frames_per_step=50,
+                  workload="config 2: 1242x375 synthetic stereo stream (SURVEY 8d), max_keypoints_per_cell=250 "
+                           "(~2000 keypoints/frame), emergent local map"),
+    "euroc": dict(name="euroc_synth", metric="stereo frames/sec at 752x480", frames_per_step=20,
+                  workload="config 5: 752x480 EuRoC-shape synthetic stereo stream (SURVEY 8d), agast_threshold=8, "
+                           "max_keypoints_per_cell=1020 (~5000 keypoints/frame), emergent local map"),
+    "tum": dict(name="tum_synth", metric="RGB-D frames/sec at 640x480", frames_per_step=20,
+                workload="config 3: 640x480 synthetic RGB-D stream (SURVEY 8d, TUM shape), max_keypoints_per_cell=1860 "
+                         "(~1500 keypoints/frame), triangulation policy 2 (emergent map ~17 000 points)"),
+}
 CPU_SAMPLE_FRAMES = 400
-METRIC = "stereo frames/sec at 1242x375"
+PROFILE_STEPS = 4
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liblvt_oracle.so")
+f64p = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
 
 
 def load_traffic():
@@ -108,58 +124,92 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def host_frames(stream, first, n):
-    """n stereo pairs as one contiguous host array [n][2][H][W] (what a caller of lvt_track holds)."""
-    out = np.empty((n, 2, stream.H, stream.W), np.uint8)
+def make_stream(wl, n_frames, seed):
+    cfg = configs.CONFIGS[wl["name"]]
+    cls = synth.StereoStream if cfg["sensor"] == 1 else synth.RgbdStream
+    return cls(n_frames=n_frames, seed=seed, **cfg["stream"])
+
+
+def host_frames(stream, first, n, sensor):
+    """n frames as host arrays (what a caller of lvt_track holds): stereo [n][2][H][W] u8; RGB-D gray [n][H][W] u8 and
+    depth [n][H][W] f32"""
+    if sensor == 1:
+        out = np.empty((n, 2, stream.H, stream.W), np.uint8)
+        for i in range(n):
+            out[i, 0], out[i, 1] = stream.frame(first + i)
+        return out, None
+    gray = np.empty((n, stream.H, stream.W), np.uint8)
+    depth = np.empty((n, stream.H, stream.W), np.float32)
     for i in range(n):
-        out[i, 0], out[i, 1] = stream.frame(first + i)
-    return out
+        gray[i], depth[i] = stream.frame(first + i)
+    return gray, depth
 
 
-def cpu_baseline(params, stream, n_frames):
-    """the oracle (CPU port of the reference path) timed on this box's host cores: wall clock around
-    track() only, as examples/kitti/kitti_example.cpp:129-131 does"""
+def frame_caller(lib, vo, sensor, frames, depth, poses):
+    """bind lvt_track / lvt_track_rgbd on host buffers; pose of frame i lands in poses[i] (R row-major, t)"""
+    fn = lib.lib.lvt_track if sensor == 1 else lib.lib.lvt_track_rgbd
+    H, W = frames.shape[-2:]
+    h = vo.h
+    args = []
+    for i in range(len(frames)):
+        Rp = C.cast(poses[i].ctypes.data, f64p)
+        tp = C.cast(poses[i, 9:].ctypes.data, f64p)
+        if sensor == 1:
+            args.append((h, frames[i, 0].ctypes.data_as(u8p), frames[i, 1].ctypes.data_as(u8p), H, W, Rp, tp))
+        else:
+            args.append((h, frames[i].ctypes.data_as(u8p), depth[i].ctypes.data_as(f32p), H, W, Rp, tp))
+    return fn, args
+
+
+def oracle_run(params, sensor, stream, n_frames, skip):
+    """the oracle (CPU port of the reference path) on the first `n_frames` frames of `stream` (the very frames the
+    b200 arms track): wall clock around track() only, as examples/kitti/kitti_example.cpp:129-131 does; the first
+    `skip` frames are warm-up"""
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
     orc = capi.Library(ORACLE_SO)
-    vo = orc.create(params, 1)
-    frames = host_frames(stream, 0, n_frames)
-    for i in range(min(10, n_frames)):  # warm-up, discarded (BASELINE.md section 3)
-        vo.track(frames[i, 0], frames[i, 1])
-    t0 = time.perf_counter()
-    for i in range(10, n_frames):
-        vo.track(frames[i, 0], frames[i, 1])
-    dt = time.perf_counter() - t0
+    vo = orc.create(params, sensor)
+    frames, depth = host_frames(stream, 0, n_frames, sensor)
+    poses = np.zeros((n_frames, 12))
+    fn, args = frame_caller(orc, vo, sensor, frames, depth, poses)
+    infos, dt = [], 0.0
+    for i in range(n_frames):
+        t0 = time.perf_counter()
+        fn(*args[i])
+        t1 = time.perf_counter()
+        if i >= skip:
+            dt += t1 - t0
+        infos.append(vo.frame_info())
     ok = vo.get_state() == capi.STATE_TRACKING
     vo.destroy()
-    return {"value": (n_frames - 10) / dt, "unit": "frames/s", "cores": 2, "kind": "port",
-            "sample": "%d consecutive frames of the same stream after 10 warm-up frames, 1 sequence, 2 threads "
-                      "(left/right extraction, as lvt_image_features_handler.cpp:204-206), tracking=%s" % (n_frames - 10, ok)}
+    return (n_frames - skip) / dt, poses, infos, ok
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the genuine sources cannot be built
-    here) on all the host threads it can use: N sequences in parallel, 2 threads each."""
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU path (oracle port; the genuine sources cannot be built here,
+    DESIGN.md) on all the host threads it can use: every sequence of the job in parallel, 2 threads each,
+    on the same frames and frames_per_step as the b200 arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.gpus
+    n_seq = args.gpus * args.seqs_per_gpu
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
     orc = capi.Library(ORACLE_SO)
-    params = configs.make_params(CONFIG)
-    fps_step = REF_FRAMES_PER_STEP
+    sensor = configs.CONFIGS[wl["name"]]["sensor"]
+    params = configs.make_params(wl["name"])
+    fps_step = args.frames_per_step
     total = (args.warmup + args.steps) * fps_step
-    streams = [synth.StereoStream(n_frames=total, seed=s, **configs.CONFIGS[CONFIG]["stream"]) for s in range(n)]
-    frames = [host_frames(st, 0, total) for st in streams]
-    vos = [orc.create(params, 1) for _ in range(n)]
+    vos, calls = [], []
+    for s in range(n_seq):
+        # the canvas depends on the stream length: build it as the b200 arm does, so that both arms see the same frames
+        frames, depth = host_frames(make_stream(wl, stream_length(args, args.seqs_per_gpu), s), 0, total, sensor)
+        vo = orc.create(params, sensor)
+        vos.append(vo)
+        calls.append(frame_caller(orc, vo, sensor, frames, depth, np.zeros((total, 12))) + (frames, depth))
     cores = os.cpu_count() or 1
-    workers = max(1, min(n, cores // 2))
-
-    def run_seq(s, lo, hi):
-        for i in range(lo, hi):
-            vos[s].track(frames[s][i, 0], frames[s][i, 1])
+    workers = max(1, min(n_seq, cores // 2))
 
     def run_all(lo, hi):
-        pending = list(range(n))
+        pending = list(range(n_seq))
         lock = threading.Lock()
 
         def worker():
@@ -168,7 +218,9 @@ def run_reference(args):
                     if not pending:
                         return
                     s = pending.pop()
-                run_seq(s, lo, hi)  # ctypes releases the GIL inside lvt_track
+                fn, a = calls[s][0], calls[s][1]
+                for i in range(lo, hi):
+                    fn(*a[i])  # ctypes releases the GIL inside the call
         th = [threading.Thread(target=worker) for _ in range(workers)]
         [t.start() for t in th]
         [t.join() for t in th]
@@ -177,21 +229,55 @@ def run_reference(args):
     t0 = time.perf_counter()
     run_all(args.warmup * fps_step, total)
     dt = time.perf_counter() - t0
-    value = n * args.steps * fps_step / dt
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": n, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1242x375 synthetic stereo stream (SURVEY 8d config 2), %d independent sequence(s); "
-                                   "reference arm: %d frames per step per sequence (bounded sample)" % (n, fps_step),
-                       "frames_per_step": fps_step, "sequences": n},
+    ok = all(v.get_state() == capi.STATE_TRACKING for v in vos)
+    value = n_seq * args.steps * fps_step / dt
+    line = {"impl": "reference", "metric": wl["metric"], "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": bench_config(wl, fps_step, args.gpus, args.seqs_per_gpu),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": min(cores, 2 * workers), "kind": "port",
-                             "sample": "%d sequences x %d frames, %d sequences at a time, 2 threads each, %d host cores"
-                                       % (n, args.steps * fps_step, workers, cores)},
+                             "sample": "%d sequence(s) x %d frames (the b200 arm's timed frames), %d at a time, 2 threads "
+                                       "each (left/right extraction, lvt_image_features_handler.cpp:204-206), %d host "
+                                       "cores, tracking=%s" % (n_seq, args.steps * fps_step, workers, cores, ok)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_b200(args):
+def stream_length(args, K):
+    """frames of the synthetic stream (its canvas depends on it): warm-up + timed + profiled repeat of the b200 arm"""
+    prof_steps = min(args.steps, PROFILE_STEPS) if K == 1 else 0
+    return (args.warmup + args.steps + prof_steps) * args.frames_per_step
+
+
+def bench_config(wl, fps_step, gpus, seqs_per_gpu):
+    """identical in both arms"""
+    return {"workload": wl["workload"], "frames_per_step": fps_step, "sequences": gpus * seqs_per_gpu,
+            "sequences_per_gpu": seqs_per_gpu}
+
+
+def algorithmic_bytes(W, H, sensor, st):
+    """SURVEY 8d / DESIGN.md section 4: algorithmic bytes per launch.  A launch covers the frame's images
+    (2 for stereo).  st: measured workload statistics."""
+    imgs = 2 if sensor == 1 else 1
+    n_l, n_r, m_map, m_trk, staged = st["n_l"], st["n_r"], st["map"], st["tracked"], st["staged"]
+    feats = n_l + n_r
+    return {
+        "score_kernel": imgs * W * H,                                   # detect: every pixel read once
+        "nms_tile_kernel": imgs * 12 * st["n_pre"],                      # NMS: 12 B per pre-NMS corner
+        "tile_kernel": imgs * 12 * st["n_post"] + 12 * feats / st["border_keep"],  # ANMS: survivors in, kept out
+        "brief_kernel": imgs * W * H + 8 * feats / st["border_keep"] + 32 * feats,  # image + keypoints in, descriptors out
+        "index_kernel": 8 * feats + 2 * 4 * feats,
+        "mapcand_kernel": 32 * (m_map + n_l) + 8 * n_l + 24 * m_map + 12 * m_map,
+        "stagedcand_kernel": 32 * (staged + n_l) + 8 * n_l + 24 * staged + 12 * staged,
+        "rowcand_kernel": 2 * (32 + 8) * n_l,
+        "track_a_kernel": 44 * m_map + 32 * m_trk,
+        "pose_kernel": st["lm_evals"] * 32 * m_trk,                     # per evaluation: xyz f64 x3 + uv f32 x2
+        "track_b_kernel": 68 * m_map + 8 * n_l,
+        "depth_gate_kernel": 12 * n_l,
+    }
+
+
+def run_b200(args, wl):
     import torch
     import torch.distributed as dist
     import lvt_b200
@@ -203,19 +289,26 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = lvt_b200.load()
+    name = wl["name"]
+    sensor = configs.CONFIGS[name]["sensor"]
+    K = args.seqs_per_gpu
 
     # the only collective: broadcast of the calibration / parameter block from rank 0 over NCCL
-    p0 = configs.make_params(CONFIG)
+    p0 = configs.make_params(name)
     blob = torch.from_numpy(p0.to_array() if rank == 0 else np.zeros_like(p0.to_array())).cuda()
     if world > 1:
         dist.broadcast(blob, src=0)
     params = capi.Params.from_array(blob.cpu().numpy())
 
     fps_step = args.frames_per_step
-    n_value = (args.warmup + 2 * args.steps) * fps_step  # warm-up, timed, profiled repeat
+    prof_steps = min(args.steps, PROFILE_STEPS) if K == 1 else 0
+    n_value = (args.warmup + args.steps + prof_steps) * fps_step  # warm-up, timed, profiled repeat
     n_e2e = (args.warmup + args.steps) * fps_step
-    stream = synth.StereoStream(n_frames=max(n_value, n_e2e, CPU_SAMPLE_FRAMES), seed=rank, **configs.CONFIGS[CONFIG]["stream"])
-    H, W = stream.H, stream.W
+    n_timed = args.steps * fps_step
+    seeds = [rank * K + k for k in range(K)]
+    assert n_value == stream_length(args, K) and n_e2e <= n_value
+    streams = [make_stream(wl, n_value, s) for s in seeds]
+    H, W = streams[0].H, streams[0].W
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,132 +322,216 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def in_threads(fn):
+        """fn(k) for the K sequences of this rank, one host thread each (ctypes releases the GIL)"""
+        if K == 1:
+            return [fn(0)]
+        out, err = [None] * K, []
+
+        def work(k):
+            try:
+                torch.cuda.set_device(local)
+                out[k] = fn(k)
+            except Exception as e:  # noqa: BLE001
+                err.append(repr(e))
+        th = [threading.Thread(target=work, args=(k,)) for k in range(K)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if err:
+            raise RuntimeError("; ".join(err))
+        return out
+
     # ---------------- value: frames resident in HBM, pipelined, device-timed ----------------------
-    vo = lib.create(params, 1)
-    vo.pool_reserve(n_value)
-    chunk = host_frames(stream, 0, n_value)
-    for i in range(n_value):
-        vo.pool_upload(i, chunk[i, 0], chunk[i, 1])
-    for s in range(args.warmup):
-        vo.track_pool(s * fps_step, fps_step, want_infos=False)
+    resident = sensor == 1  # lvt_track_pool is the stereo path; RGB-D frames go through lvt_track_rgbd
+    vos = [lib.create(params, sensor) for _ in range(K)]
+    value_poses = [np.zeros((0, 12)) for _ in range(K)]
+    value_infos = [[] for _ in range(K)]
+    if resident:
+        def upload(k):
+            vos[k].pool_reserve(n_value)
+            for s0 in range(0, n_value, fps_step):
+                chunk, _ = host_frames(streams[k], s0, fps_step, sensor)
+                for i in range(fps_step):
+                    vos[k].pool_upload(s0 + i, chunk[i, 0], chunk[i, 1])
+        in_threads(upload)
+
+        def steps(k, lo, hi):
+            ms = 0.0
+            for s in range(lo, hi):
+                poses, inf = vos[k].track_pool(s * fps_step, fps_step)
+                ms += vos[k].last_batch_ms()
+                value_poses[k] = np.concatenate([value_poses[k], poses])
+                value_infos[k] += inf
+            return ms
+        in_threads(lambda k: steps(k, 0, args.warmup))
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     launches0 = lib.launch_count()
-    dev_ms, infos = 0.0, []
-    t0 = time.perf_counter()
-    for s in range(args.warmup, args.warmup + args.steps):
-        _, inf = vo.track_pool(s * fps_step, fps_step)
-        dev_ms += vo.last_batch_ms()
-        infos += inf
-    torch.cuda.synchronize()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = wall_ms = 0.0
+    if resident:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        per_seq_ms = in_threads(lambda k: steps(k, args.warmup, args.warmup + args.steps))
+        torch.cuda.synchronize()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        ev1.record()
+        ev1.synchronize()
+        # one sequence: the sum of the per-call device times (CUDA events around each lvt_track_pool call on its own
+        # stream); several concurrent sequences: the device-side span around all of them
+        dev_ms = per_seq_ms[0] if K == 1 else ev0.elapsed_time(ev1)
     launches = lib.launch_count() - launches0
     barrier()
     sampler.pause()
     dev_ms = max_over_ranks(dev_ms)
     wall_ms = max_over_ranks(wall_ms)
-    n_timed = args.steps * fps_step
-    value = world * n_timed / (dev_ms * 1e-3)
-    lost = sum(1 for i in infos if i["state"] != capi.STATE_TRACKING)
 
-    # ---------------- roofline: per-kernel CUDA-event times over an identical repeat --------------
-    lib.reset_kernel_times()
-    lib.set_profiling(True)
-    for s in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
-        vo.track_pool(s * fps_step, fps_step, want_infos=False)
-    lib.set_profiling(False)
-    ktimes = lib.kernel_times()
-    vo.destroy()
-    peak, peak_src = load_peaks()
-    mean = lambda k: float(np.mean([i[k] for i in infos]))  # noqa: E731
-    n_l, n_r, m_map, m_trk = mean("n_features_left"), mean("n_features_right"), mean("map_points_before"), mean("tracked")
-    # algorithmic bytes per launch; a launch covers the stereo pair
-    alg = {
-        "score_kernel": 2 * W * H,
-        "nms_tile_kernel": 2 * W * H,
-        "tile_kernel": 12 * 2 * 3900 + 12 * (n_l + n_r) / 0.8,
-        # descriptors + the feature index its extra CTA builds (positions in, two CSRs out)
-        "brief_kernel": 8 * (n_l + n_r) + 32 * (n_l + n_r) + 57 * 57 * (n_l + n_r) + 2 * 8 * (n_l + n_r) + 2 * 4 * (n_l + n_r),
-        "index_kernel": 2 * 8 * (n_l + n_r) + 2 * 4 * (n_l + n_r),
-        "mapcand_kernel": 32 * (m_map + n_l) + 8 * n_l + 24 * m_map + 12 * m_map,
-        "rowcand_kernel": 2 * (32 + 8) * n_l,
-        "track_a_kernel": 4 * 8 * m_map + 12 * m_map + 32 * m_trk,
-        "pose_kernel": 12 * 32 * m_trk,
-        "track_b_kernel": 68 * m_map + 8 * n_l,
-    }
-    per_kernel = {}
-    for k, (ms, cnt) in ktimes.items():
-        if cnt:
-            per_kernel[k] = {"avg_us": 1e3 * ms / cnt, "launches": cnt, "share": ms}
-    tot = sum(v["share"] for v in per_kernel.values()) or 1.0
-    for v in per_kernel.values():
-        v["share"] = v["share"] / tot
-    dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["share"] * tot, default=None)
-    roofline = None
-    traffic = load_traffic()
-    if dom:
-        achieved = alg[dom] / (per_kernel[dom]["avg_us"] * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic.get(dom), "traffic_source": "profiles/traffic.json (ncu --set full, dram read + write per launch)",
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                    "avg_launch_us": per_kernel[dom]["avg_us"],
-                    "note": "latency/ALU-bound at one stereo pair per launch (1.45 MB of traffic per frame); see DESIGN.md",
-                    "per_kernel": {k: {"avg_us": round(v["avg_us"], 2), "share": round(v["share"], 4),
-                                       "GBps": round(alg[k] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None,
-                                       "traffic": traffic.get(k)}
-                                   for k, v in per_kernel.items()}}
+    # ---------------- roofline: per-kernel CUDA-event times over a short identical repeat ----------
+    ktimes, lm_evals = {}, []
+    if resident and prof_steps:
+        lib.reset_kernel_times()
+        lib.set_profiling(True)
+        for s in range(args.warmup + args.steps, args.warmup + args.steps + prof_steps):
+            vos[0].track_pool(s * fps_step, fps_step, want_infos=False)
+            lm_evals += [vos[0].frame_counters(i)["lm_evaluations"] for i in range(fps_step)]
+        lib.set_profiling(False)
+        ktimes = lib.kernel_times()
+    for vo in vos:
+        vo.destroy()
 
     # ---------------- e2e: lvt_track with host buffers, H2D + D2H inside the timed region -----------
-    vo2 = lib.create(params, 1)
-    frames = host_frames(stream, 0, n_e2e)
-    R = np.zeros((3, 3))
-    t = np.zeros(3)
-    import ctypes as C
-    f64p = C.POINTER(C.c_double)
-    u8p = C.POINTER(C.c_uint8)
-    track = lib.lib.lvt_track
-    Rp, tp = R.ctypes.data_as(f64p), t.ctypes.data_as(f64p)
-    ptrs = [(frames[i, 0].ctypes.data_as(u8p), frames[i, 1].ctypes.data_as(u8p)) for i in range(n_e2e)]
-    for i in range(args.warmup * fps_step):
-        track(vo2.h, ptrs[i][0], ptrs[i][1], H, W, Rp, tp)
+    vos2 = [lib.create(params, sensor) for _ in range(K)]
+    e2e_poses = [np.zeros((n_e2e, 12)) for _ in range(K)]
+    callers = []
+    for k in range(K):
+        frames, depth = host_frames(streams[k], 0, n_e2e, sensor)
+        callers.append(frame_caller(lib, vos2[k], sensor, frames, depth, e2e_poses[k]) + (frames, depth))
+
+    def e2e_range(k, lo, hi):
+        fn, a = callers[k][0], callers[k][1]
+        for i in range(lo, hi):
+            fn(*a[i])
+    if not resident or not prof_steps:
+        lib.reset_kernel_times()
+        lib.set_profiling(K == 1 and not resident)  # RGB-D: per-kernel times come from the blocking calls' warm-up
+    in_threads(lambda k: e2e_range(k, 0, args.warmup * fps_step))
+    if not resident and K == 1:
+        lib.set_profiling(False)
+        ktimes = lib.kernel_times()
     barrier()
     sampler.start()  # second timed region: the samples of both go into one record
+    launches1 = lib.launch_count()
     t0 = time.perf_counter()
-    for i in range(args.warmup * fps_step, n_e2e):
-        track(vo2.h, ptrs[i][0], ptrs[i][1], H, W, Rp, tp)
+    in_threads(lambda k: e2e_range(k, args.warmup * fps_step, n_e2e))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_ok = vo2.get_state() == capi.STATE_TRACKING
+    e2e_launches = lib.launch_count() - launches1
+    e2e_ok = all(v.get_state() == capi.STATE_TRACKING and v.last_status() == 0 for v in vos2)
     barrier()
     clocks = sampler.stop()  # sampled during both timed regions (value and e2e)
     e2e_s = max_over_ranks(e2e_s)
-    e2e_value = world * n_timed / e2e_s
-    gt = stream.ground_truth_t(n_e2e - 1, params.fx, params.baseline)
-    drift = float(np.linalg.norm(t - gt))
-    vo2.destroy()
+    e2e_value = world * K * n_timed / e2e_s
+    if not resident:  # no resident path for RGB-D yet: the device-resident figure is not measured separately
+        dev_ms, launches = 1e3 * e2e_s, e2e_launches
+    value = world * K * n_timed / (dev_ms * 1e-3)
+    drift = None
+    if sensor == 1:
+        gt = streams[0].ground_truth_t(n_e2e - 1, params.fx, params.baseline)
+        drift = float(np.linalg.norm(e2e_poses[0][-1, 9:] - gt))
+    e2e_infos_last = [v.frame_info() for v in vos2]
+    for vo in vos2:
+        vo.destroy()
 
-    cpu = None
+    # ---------------- workload statistics, roofline bookkeeping -----------------------------------
+    infos = value_infos[0][args.warmup * fps_step:] if resident else e2e_infos_last
+    mean = lambda k: float(np.mean([i[k] for i in infos]))  # noqa: E731
+    st = {"n_l": mean("n_features_left"), "n_r": mean("n_features_right"), "map": mean("map_points_before"),
+          "tracked": mean("tracked"), "staged": mean("staged_before"),
+          "lm_evals": float(np.mean(lm_evals)) if lm_evals else None}
+    lost = sum(1 for i in infos if i["state"] != capi.STATE_TRACKING)
+    roofline = None
+    if rank == 0 and ktimes:
+        # corner counts before / after AGAST's NMS on one frame (whole image as one tile, the seam call)
+        ctx = lib.context(params)
+        img = streams[0].frame(n_e2e // 2)[0]
+        st["n_pre"] = float(len(ctx.agast(img, params.agast_threshold, nonmax=False)))
+        st["n_post"] = float(len(ctx.agast(img, params.agast_threshold, nonmax=True)))
+        ctx.destroy()
+        st["border_keep"] = (W - 56.0) * (H - 56.0) / (W * H)
+        if st["lm_evals"] is None:
+            st["lm_evals"] = 22.0
+        alg = algorithmic_bytes(W, H, sensor, st)
+        peak, peak_src = load_peaks()
+        traffic = load_traffic()
+        per_kernel = {k: {"avg_us": 1e3 * ms / cnt, "launches": cnt, "ms": ms} for k, (ms, cnt) in ktimes.items() if cnt}
+        tot = sum(v["ms"] for v in per_kernel.values()) or 1.0
+        frames_prof = max(1, per_kernel.get("pose_kernel", per_kernel.get("track_b_kernel", {"launches": 1}))["launches"])
+        dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["ms"], default=None)
+        if dom:
+            achieved = alg[dom] / (per_kernel[dom]["avg_us"] * 1e-6) / 1e9
+            frame_bytes = sum(alg[k] * v["launches"] for k, v in per_kernel.items() if k in alg) / frames_prof
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic.get(dom),
+                        "traffic_source": "profiles/traffic.json (ncu --set full, dram read + write per launch)",
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                        "avg_launch_us": per_kernel[dom]["avg_us"],
+                        "lm_evaluations_per_frame": st["lm_evals"],
+                        "frame": {"algorithmic_bytes": frame_bytes, "GBps": frame_bytes * value / world / K / 1e9,
+                                  "frac": frame_bytes * value / world / K / 1e9 / peak,
+                                  "note": "all kernels of one frame / time per frame of `value` (one sequence)"},
+                        "note": "latency/ALU-bound at one stereo pair per launch; see DESIGN.md section 4",
+                        "per_kernel": {k: {"avg_us": round(v["avg_us"], 2), "share": round(v["ms"] / tot, 4),
+                                           "launches_per_frame": round(v["launches"] / frames_prof, 2),
+                                           "alg_bytes": round(alg[k]) if k in alg else None,
+                                           "GBps": round(alg[k] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None,
+                                           "traffic": traffic.get(k)}
+                                       for k, v in per_kernel.items()}}
+
+    # ---------------- CPU baseline + ATE vs the reference path (rank 0, sequence 0) ---------------
+    cpu = ate = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(params, stream, CPU_SAMPLE_FRAMES)
+        n_cpu = min(CPU_SAMPLE_FRAMES, n_e2e)
+        cpu_fps, o_poses, o_infos, ok = oracle_run(params, sensor, streams[0], n_cpu, 10)
+        cpu = {"value": cpu_fps, "unit": "frames/s", "cores": 2 if sensor == 1 else 1, "kind": "port",
+               "sample": "the first %d frames of sequence 0 after 10 warm-up frames, 1 sequence, %s, tracking=%s"
+                         % (n_cpu, "2 threads (left/right extraction, as lvt_image_features_handler.cpp:204-206)"
+                            if sensor == 1 else "1 thread", ok)}
+        d = e2e_poses[0][:n_cpu, 9:] - o_poses[:, 9:]
+        ate = {"ate_vs_reference_m": float(np.sqrt(np.mean(np.sum(d * d, axis=1)))),
+               "max_translation_diff_m": float(np.abs(d).max()),
+               "max_rotation_diff": float(np.abs(e2e_poses[0][:n_cpu, :9] - o_poses[:, :9]).max()),
+               "frames_compared": n_cpu, "bound_m": 1e-3,
+               "what": "e2e arm (lvt_track, host buffers) vs the CPU oracle on the same frames; RMSE of |t - t_ref|, no alignment"}
+        if resident:
+            m = min(n_cpu, len(value_infos[0]))
+            ate["frame_info_mismatches"] = sum(1 for a, b in zip(value_infos[0][:m], o_infos[:m]) if a != b)
+            dv = value_poses[0][:m, 9:] - o_poses[:m, 9:]
+            ate["value_arm_ate_vs_reference_m"] = float(np.sqrt(np.mean(np.sum(dv * dv, axis=1))))
+            ate["frame_infos_compared"] = m
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "config 2: 1242x375 synthetic stereo stream (SURVEY 8d), 1 sequence per GPU, "
-                                       "max_keypoints_per_cell=250 (~2000 keypoints/frame), emergent local map",
-                           "frames_per_step": fps_step, "sequences": world,
-                           "mean_keypoints_left": round(n_l, 1), "mean_map_points": round(m_map, 1),
-                           "mean_tracked": round(m_trk, 1), "frames_lost": lost,
-                           "cache": "each frame is read once (inputs: %.0f MB per rank resident in HBM, > 126 MB L2)"
-                                    % (n_value * 2 * W * H / 1e6),
-                           "timing": "CUDA events around each lvt_track_pool call (first extraction launch .. result copy), "
-                                     "summed over steps, max over ranks; wall clock %.1f ms/step" % (wall_ms / args.steps)},
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": fps_step * 2 * W * H,
-                        "d2h_bytes_per_step": fps_step * 176, "call": "lvt_track (reference C ABI), host buffers, blocking per frame",
+        imgs_bytes = (2 * W * H) if sensor == 1 else (W * H * 5)
+        line = {"metric": wl["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": bench_config(wl, fps_step, world, K),
+                "workload_stats": {"mean_keypoints_left": round(st["n_l"], 1), "mean_map_points": round(st["map"], 1),
+                                   "mean_tracked": round(st["tracked"], 1), "frames_lost": lost,
+                                   "cache": "each frame is read once (inputs: %.0f MB per sequence resident in HBM, > 126 MB L2)"
+                                            % (n_value * imgs_bytes / 1e6),
+                                   "timing": ("CUDA events around each lvt_track_pool call (first extraction launch .. result copy), "
+                                              "summed over steps" if K == 1 else
+                                              "CUDA events around the %d concurrent sequences of the rank" % K) +
+                                             ", max over ranks; wall clock %.1f ms/step" % (wall_ms / args.steps)
+                                             if resident else "RGB-D has no resident path yet: value repeats e2e"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": K * fps_step * imgs_bytes,
+                        "d2h_bytes_per_step": K * fps_step * 176,
+                        "call": ("lvt_track" if sensor == 1 else "lvt_track_rgbd") + " (reference C ABI), host buffers, blocking per frame",
                         "tracking_ok": e2e_ok, "drift_vs_ground_truth_m": drift},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        if ate:
+            line.update(ate)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -366,14 +543,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--config", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--seqs-per-gpu", type=int, default=1)
+    ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    wl = WORKLOADS[args.config]
+    if args.frames_per_step <= 0:
+        args.frames_per_step = wl["frames_per_step"]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_b200(args)
+        run_b200(args, wl)
 
 
 if __name__ == "__main__":

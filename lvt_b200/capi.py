@@ -323,6 +323,14 @@ class System:
         _check(self.lib.lvt_track_pool(self.h, first, n, _ptr(poses, c_f64p), infos), "lvt_track_pool")
         return poses, ([infos[i].as_dict() for i in range(n)] if want_infos else None)
 
+    def frame_counters(self, i=-1):
+        """profiling aid: fixed-point rounds (map, retry, staged, row passes) and pose-solver evaluations of pool
+        frame i of the last batch (i < 0: of the last blocking call)"""
+        cyc = (C.c_longlong * 8)()
+        rnd = (C.c_int * 8)()
+        self.lib.lvt_debug_phase_cycles(C.c_void_p(self.h), i, cyc, rnd)
+        return {"rounds": list(rnd)[:4], "lm_evaluations": rnd[4]}
+
     def last_batch_ms(self):
         return float(self.lib.lvt_last_batch_ms(self.h))
 

@@ -1704,8 +1704,8 @@ LVT_API int lvt_track_pool(lvt_handle h, int first_frame, int n_frames, double *
     return rc;
 }
 /* profiling aid: clock64() phase marks and fixed-point round counts of pool frame i of the last batch
- * (or of the last lvt_track call when i < 0) */
-LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int rounds[4])
+ * (or of the last lvt_track call when i < 0); rounds[4] = evaluations of the pose solver in that frame */
+LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int rounds[8])
 {
     System *vo = static_cast<System *>(h);
     if (!vo)

@@ -338,9 +338,15 @@ __device__ inline void pose_evaluate(Cluster &cluster, PoseShared &s, PoseEdge (
 template <class Cluster>
 __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const double *xyz, const float2 *uv, int m,
                                           const PoseD &init, const CamParams &cp, uint8_t *level, double *e2,
-                                          uint8_t *inlier, PoseD *pose_out, int *n_inliers_out, long long *dbg = nullptr)
+                                          uint8_t *inlier, PoseD *pose_out, int *n_inliers_out, long long *dbg = nullptr,
+                                          int *n_evals_out = nullptr)
 {
+    int n_evals = 0; // passes over the correspondences (uniform over the cluster)
+#define LVT_SDBG(k)                                                                                                   \
+    if (dbg && rank == 0 && threadIdx.x == 0 && (k) < 32)                                                             \
+    dbg[k] = clock64()
     const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
+    LVT_SDBG(8);
     if (threadIdx.x == 0)
     {
         CamState &c = s.cam; // the same arithmetic in every CTA: identical copies
@@ -393,6 +399,7 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
     else
         __syncthreads();
 
+    LVT_SDBG(9);
     // LM state of rank 0 / thread 0 (OptimizationAlgorithmLevenberg::solve)
     double lambda = 0, ni = 2, current_chi = 0, rho = 0;
     int qmax = 0, it = 0;
@@ -455,6 +462,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
         // errors + linearisation at the starting state of this optimize()
         pose_evaluate(cluster, s, edge, xyz, uv, level, e2, m, rank, nranks, parity);
         parity ^= 1;
+        n_evals++;
+        LVT_SDBG(9 + n_evals);
         if (boss)
         {
             if (s.sums[28] == 0.0)
@@ -487,6 +496,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
                 break;
             pose_evaluate(cluster, s, edge, xyz, uv, level, e2, m, rank, nranks, parity, dbg); // the trial state
             parity ^= 1;
+            n_evals++;
+            LVT_SDBG(9 + n_evals);
             if (boss)
             {
                 const double temp_chi = s.sums[27];
@@ -586,6 +597,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
             for (int r = 0; r < nranks; r++)
                 v += s.gather[parity][r][0];
             *n_inliers_out = (int)v;
+            if (n_evals_out)
+                *n_evals_out = n_evals;
             pose_out->q = s.cam.r;
             pose_out->t[0] = s.cam.t[0];
             pose_out->t[1] = s.cam.t[1];
@@ -593,6 +606,8 @@ __device__ inline void cluster_solve_pose(Cluster &cluster, PoseShared &s, const
         }
         cluster.sync(); // nobody leaves while another CTA may still read its shared memory
     }
+    LVT_SDBG(31);
+#undef LVT_SDBG
 }
 
 } // namespace lvtb

@@ -41,7 +41,7 @@ struct FrameCtl
     double opt_W[12]; // world->camera of opt, prepared by pose_kernel for the staged-point projection
     lvt_frame_info info;
     long long cyc[8];
-    int rounds[4];
+    int rounds[8]; // as FrameResult::rounds
 };
 
 struct TrackArgs
@@ -196,7 +196,7 @@ __device__ void write_result(const TrackArgs &a, TrackState &S, const PoseD &pos
     c.cyc[7] = clock64();
     for (int k = 0; k < 8; k++)
         a.result->cycles[k] = c.cyc[k];
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 8; k++)
         a.result->rounds[k] = c.rounds[k];
 }
 
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         ctl.info.n_features_right = 0; // track_b: the right image may still be in extraction on another stream
         for (int k = 0; k < 8; k++)
             ctl.cyc[k] = 0;
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < 8; k++)
             ctl.rounds[k] = 0;
         ctl.n_matches = 0;
         ctl.inliers = 0;
@@ -420,7 +420,8 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
         if (cluster.block_rank() == 0 && threadIdx.x == 0)
             a.ctl->cyc[3] = clock64();
     }
-    cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl, a.dbg);
+    cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl, a.dbg,
+                       a.ctl ? &a.ctl->rounds[4] : nullptr);
     if (a.ctl && cluster.block_rank() == 0 && threadIdx.x == 0)
     {
         a.ctl->cyc[4] = clock64();
@@ -907,17 +908,21 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
         static int calls = 0;
         if (++calls == 8)
         {
-            long long h[8];
+            long long h[32];
             cudaMemcpy(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost);
             std::fprintf(stderr, "pose pass: compute %lld | warp+cta reduce %lld | cluster.sync %lld | dsmem reduce %lld | boss LM step %lld cycles\n",
                          h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+            std::fprintf(stderr, "pose solve: setup %lld | evaluations", h[9] - h[8]);
+            for (int k = 10; k < 31 && h[k] > h[k - 1]; k++)
+                std::fprintf(stderr, " %lld", h[k] - h[k - 1]);
+            std::fprintf(stderr, " | total %lld cycles\n", h[31] - h[8]);
         }
     }
     if (a.dbg && std::getenv("LVT_B200_TRACKDBG"))
     {
         static int calls = 0;
         if (calls == 0)
-            cudaMemset(a.dbg, 0, 32 * sizeof(long long));
+            cudaMemset(a.dbg, 0, 32 * sizeof(long long)), cudaMemset(pa.dbg, 0, 32 * sizeof(long long));
         if (++calls == 8)
         {
             long long h[32];

@@ -53,7 +53,8 @@ struct FrameResult
     PoseD pose;
     lvt_frame_info info;
     long long cycles[8]; // clock64() at the phase boundaries of the tracking kernel (profiling aid)
-    int rounds[4];       // fixed-point rounds: map pass, retry pass, staged pass, row matching
+    int rounds[8];       // fixed-point rounds: map pass, retry pass, staged pass, row matching; [4] = evaluations of the
+                         // pose solver (passes over the correspondences: linearisations + LM trials), [5..7] spare
     long long dbg[8];    // clock64() marks inside the map pass (profiling aid)
 };
 

@@ -16,6 +16,8 @@
  */
 #include "lvto.h"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 
 namespace lvto
@@ -214,6 +216,7 @@ Pose solve_pose(const lvt_params_c &prm, const Pose &init, const std::vector<Vec
         }
     };
 
+    static const bool trace = std::getenv("LVTO_LM_TRACE") != nullptr; /* one line per solve: A accept, r reject, | pass */
     for (int pass = 0; pass < 2 /* N_PASSES */; pass++)
     {
         int n_active = 0;
@@ -280,12 +283,16 @@ Pose solve_pose(const lvt_params_c &prm, const Pose &init, const std::vector<Vec
                         lambda *= scale_factor;
                         ni = 2;
                         current_chi = temp_chi;
+                        if (trace)
+                            std::fputc('A', stderr);
                     }
                     else
                     {
                         lambda *= ni;
                         ni *= 2;
                         cam = backup; /* pop(); the edges keep the rejected trial's _error */
+                        if (trace)
+                            std::fputc('r', stderr);
                     }
                     qmax++;
                 } while (rho < 0 && qmax < 10);
@@ -293,6 +300,8 @@ Pose solve_pose(const lvt_params_c &prm, const Pose &init, const std::vector<Vec
                     break; /* Terminate */
             }
         }
+        if (trace)
+            std::fputc(pass == 0 ? '|' : '\n', stderr);
         for (int k = 0; k < M; k++)
         {
             if (ex[k] * ex[k] + ey[k] * ey[k] > TH2)

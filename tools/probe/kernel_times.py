@@ -30,7 +30,7 @@ for t in range(25, n):
     run(*frames[t])
 print("blocking: %.1f us/frame" % (1e6 * (time.perf_counter() - t0) / (n - 25)), vo.frame_info())
 import ctypes as C
-cyc = (C.c_longlong * 8)(); rnd = (C.c_int * 4)()
+cyc = (C.c_longlong * 8)(); rnd = (C.c_int * 8)()
 lib.lib.lvt_debug_phase_cycles(C.c_void_p(vo.h), -1, cyc, rnd)
 c = list(cyc)
 print("rounds (map, retry, staged, row):", list(rnd), "| track_a: match %.1f us, bookkeeping %.1f us | track_b: clean %.1f us, rest %.1f us" % (

@@ -17,7 +17,7 @@ vo.track_pool(0, 10)
 poses, infos = vo.track_pool(10, 30)
 print("batch ms", vo.last_batch_ms(), "per frame", vo.last_batch_ms() / 30)
 cyc = (C.c_longlong * 8)()
-rnd = (C.c_int * 4)()
+rnd = (C.c_int * 8)()
 names = ["A.match", "A.bookkeep", "(gap)", "pose", "(gap)", "B.clean", "B.staged+tri"]
 acc = np.zeros(7)
 for i in range(30):
