@@ -912,6 +912,16 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
             cudaMemcpy(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost);
             std::fprintf(stderr, "pose pass: compute %lld | warp+cta reduce %lld | cluster.sync %lld | dsmem reduce %lld | boss LM step %lld cycles\n",
                          h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+            std::fprintf(stderr, "pose LM block %lld cycles (bracketed) | LM end -> past the CTA barrier %lld\n", h[6], h[7] - h[5]);
+            {
+                int last = 10;
+                while (last + 1 < 31 && h[last + 1] > h[last])
+                    last++;
+                const long long base = h[last - 1]; // end of the evaluation before the last one
+                std::fprintf(stderr, "pose last iteration, cycles since the previous evaluation returned: LM end %lld | past barrier %lld | "
+                                     "eval start %lld | computed %lld | cta sums %lld | cluster sums in %lld | totals %lld | returned %lld\n",
+                             h[5] - base, h[7] - base, h[0] - base, h[1] - base, h[2] - base, h[3] - base, h[4] - base, h[last] - base);
+            }
             std::fprintf(stderr, "pose solve: setup %lld | evaluations", h[9] - h[8]);
             for (int k = 10; k < 31 && h[k] > h[k - 1]; k++)
                 std::fprintf(stderr, " %lld", h[k] - h[k - 1]);
