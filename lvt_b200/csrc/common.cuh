@@ -342,6 +342,79 @@ __device__ inline int block_exclusive_scan(int v, int *scratch, int *total)
     return scratch[warp] + incl - v;
 }
 
+// Four exclusive prefix sums at once: v = four 16-bit counts packed into 64 bits (field j in bits
+// 16j..16j+15; every field's block total must stay below 65536).  Returns the packed exclusive values,
+// *total the packed block totals.  scratch: >= 33 uint64 of shared memory.  All threads must call.
+// Used for 4 x blockDim items handled as item(j, t) = base + j * blockDim + t (coalesced accesses), whose
+// order is j-major: position = sum of the totals of the fields before j + the field's exclusive value.
+__device__ inline unsigned long long block_exclusive_scan4(unsigned long long v, unsigned long long *scratch,
+                                                           unsigned long long *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += n;
+    }
+    __syncthreads(); // scratch may still be read from a previous call
+    if (lane == 31)
+        scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const unsigned long long w = lane < nwarps ? scratch[lane] : 0ull;
+        unsigned long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned long long n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o)
+                wi += n;
+        }
+        scratch[lane] = wi - w; // exclusive per-warp offset
+        if (lane == 31)
+            scratch[32] = wi;
+    }
+    __syncthreads();
+    *total = scratch[32];
+    return scratch[warp] + incl - v;
+}
+// offsets of the four fields of a packed total (j-major order) and the position of item (j, t)
+__device__ __forceinline__ int scan4_position(unsigned long long excl, unsigned long long total, int j)
+{
+    int before = 0;
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++)
+        if (jj < j)
+            before += (int)((total >> (16 * jj)) & 0xFFFFull);
+    return before + (int)((excl >> (16 * j)) & 0xFFFFull);
+}
+__device__ __forceinline__ int scan4_sum(unsigned long long total)
+{
+    return (int)(total & 0xFFFFull) + (int)((total >> 16) & 0xFFFFull) + (int)((total >> 32) & 0xFFFFull) +
+           (int)((total >> 48) & 0xFFFFull);
+}
+
+// asynchronous global -> shared copies of 4 / 8 / 16 bytes (LDGSTS): no register in between, so a thread
+// can have many in flight; cp_async_wait_all() makes the calling thread's copies visible to itself (a
+// barrier publishes them to the CTA)
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
+{
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async copies 4, 8 or 16 bytes");
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) + mbarrier, hand-written PTX
 // ---------------------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ struct TrackShared
     double W[24]; // world->camera of the left [0..11] and right [12..23] camera
     PoseD pose;
     int flag[8];
-    int scan[34];
+    int scan[68]; // block_exclusive_scan (34 ints) / block_exclusive_scan4 (33 uint64)
     int ctrl[4];
 };
 
@@ -314,32 +314,56 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     for (int j = threadIdx.x; j < nl; j += blockDim.x)
         fl.matched[j] = owner_a[j] != kFree;
     LVT_PHASE(1);
-    // bookkeeping (:201-224) + the solver's inputs, in map order
+    // bookkeeping (:201-224) + the solver's inputs, in map order.  Four points per thread, interleaved
+    // (coalesced), their loads in flight together, and one packed block scan per 4 x blockDim points: the
+    // chain through L2 is what this phase costs, not the work.
     int n_matches = 0;
-    for (int i0 = 0; i0 < M; i0 += blockDim.x)
+    for (int base = 0; base < M; base += 4 * (int)blockDim.x)
     {
-        const int i = i0 + threadIdx.x;
-        int c = -3;
-        if (i < M)
+        int idx[4], c[4];
+        unsigned long long packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
         {
-            c = a.sc.ms.vis[i] ? a.sc.ms.choice[i] : -2;
-            a.map.match_idx[i] = c;
-            if (c < 0)
-                a.map.counter[i] += 1;
-            else
-                a.map.age[i] += 1;
+            idx[k] = base + k * (int)blockDim.x + (int)threadIdx.x;
+            c[k] = -3;
+            if (idx[k] < M)
+                c[k] = a.sc.ms.vis[idx[k]] ? a.sc.ms.choice[idx[k]] : -2;
         }
-        int total;
-        const int pos = block_exclusive_scan(c >= 0, sh.scan, &total);
-        if (c >= 0)
+        int cnt[4], age[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (idx[k] < M)
+            {
+                cnt[k] = a.map.counter[idx[k]];
+                age[k] = a.map.age[idx[k]];
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
         {
-            const int d = n_matches + pos;
-            a.sc.sol_xyz[3 * d] = a.map.xyz[3 * i];
-            a.sc.sol_xyz[3 * d + 1] = a.map.xyz[3 * i + 1];
-            a.sc.sol_xyz[3 * d + 2] = a.map.xyz[3 * i + 2];
-            a.sc.sol_uv[d] = fl.xy[c];
+            if (idx[k] < M)
+            {
+                a.map.match_idx[idx[k]] = c[k];
+                if (c[k] < 0)
+                    a.map.counter[idx[k]] = cnt[k] + 1;
+                else
+                    a.map.age[idx[k]] = age[k] + 1;
+            }
+            packed |= (unsigned long long)(c[k] >= 0) << (16 * k);
         }
-        n_matches += total;
+        unsigned long long total;
+        const unsigned long long excl = block_exclusive_scan4(packed, reinterpret_cast<unsigned long long *>(sh.scan), &total);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (c[k] >= 0)
+            {
+                const int d = n_matches + scan4_position(excl, total, k), i = idx[k];
+                a.sc.sol_xyz[3 * d] = a.map.xyz[3 * i];
+                a.sc.sol_xyz[3 * d + 1] = a.map.xyz[3 * i + 1];
+                a.sc.sol_xyz[3 * d + 2] = a.map.xyz[3 * i + 2];
+                a.sc.sol_uv[d] = fl.xy[c[k]];
+            }
+        n_matches += scan4_sum(total);
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -594,12 +618,25 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
     // ---- clean_untracked_points (lvt/src/lvt_local_map.cpp:393-413)
     const int M = map_n;
     const int th = tp.untracked_threshold;
-    for (int i = threadIdx.x; i < M; i += blockDim.x)
-        if (a.map.counter[i] >= th && a.map.match_idx[i] >= 0)
-            fl.matched[a.map.match_idx[i]] = 0;
-    __syncthreads();
-    const int *cnt = a.map.counter;
-    map_n = block_compact_points(a.map, M, [cnt, th](int i) { return cnt[i] < th; }, sh.scan);
+    // a dropped point gives its feature back (:398-404): done where the keep flag is taken (one pass over the counters)
+    long long *cdbg = a.dbg ? a.dbg + 40 : nullptr;
+    if (cdbg && threadIdx.x == 0)
+        cdbg[0] = clock64(), cdbg[6] = ctl.cyc[5];
+    {
+        const int *cnt = a.map.counter, *midx = a.map.match_idx;
+        uint8_t *matched = fl.matched;
+        map_n = block_compact_points(
+            a.map, M,
+            [cnt, midx, matched, th](int i) {
+                if (cnt[i] < th)
+                    return true;
+                const int mi = midx[i];
+                if (mi >= 0)
+                    matched[mi] = 0;
+                return false;
+            },
+            sh.scan, s_owner, cdbg);
+    }
     LVT_PHASE(6);
 
     // ---- update_staged_map_points (lvt/src/lvt_local_map.cpp:355-391); stagedcand projected the
@@ -656,7 +693,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
                 *a.error = S.error = LVTK_ERR_CAPACITY;
             map_n = a.map.cap;
         }
-        staged_n = block_compact_points(a.staged, Sn, [flag](int i) { return flag[i] == 1; }, sh.scan);
+        staged_n = block_compact_points(a.staged, Sn, [flag](int i) { return flag[i] == 1; }, sh.scan, s_owner);
     }
 
     // ---- need_new_triangulation (lvt/src/lvt_system.cpp:308-334)
@@ -931,9 +968,10 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     if (a.dbg && std::getenv("LVT_B200_TRACKDBG"))
     {
         static int calls = 0;
+        static const int at = std::getenv("LVT_B200_DBG_FRAME") ? std::atoi(std::getenv("LVT_B200_DBG_FRAME")) : 8;
         if (calls == 0)
             cudaMemset(a.dbg, 0, 32 * sizeof(long long)), cudaMemset(pa.dbg, 0, 32 * sizeof(long long));
-        if (++calls == 8)
+        if (++calls == at)
         {
             long long h[32];
             cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -941,6 +979,12 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
                          h[24] - h[4], h[25] - h[24], h[26] - h[25], h[27] - h[26], h[28] - h[27], h[5] - h[28]);
             std::fprintf(stderr, "map pass: n_fast %lld n_slow %lld smem keys %lld sum counts %lld max count %lld from global %lld\n", h[16],
                          h[17], h[18], h[19], h[20], h[21]);
+            {
+                long long c[8];
+                cudaMemcpy(c, a.dbg + 40, sizeof(c), cudaMemcpyDeviceToHost);
+                std::fprintf(stderr, "track_b clean: marks reset %lld | keep flags %lld | scan %lld | xyz %lld | desc %lld | ints+sync %lld cycles\n",
+                             c[0] - c[6], c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4]);
+            }
             std::fprintf(stderr, "map pass: lists %lld | cache+reset %lld | rounds", h[1] - h[0], h[2] - h[1]);
             for (int r = 0; r < 12 && h[3 + r] > h[2] && h[3 + r] < h[15]; r++)
                 std::fprintf(stderr, " %lld", h[3 + r] - (r ? h[2 + r] : h[2]));

@@ -289,47 +289,97 @@ __device__ inline void copy_point(const PointStore &dst, int d, const double *xy
     dst.match_idx[d] = match_idx;
 }
 
-// In-place, order-preserving compaction of a PointStore by keep(i).  Chunks are read into
-// registers, synchronised, then written: destinations never run ahead of the sources.
+// In-place, order-preserving compaction of a PointStore by keep(i).  Four points per thread, interleaved
+// (point j * blockDim + t of the chunk: coalesced accesses), one packed block scan per 4 x blockDim points.
+// A chunk is moved field by field through SHARED memory -- every kept element of the chunk is read into the
+// staging buffer (flat, coalesced: the 24-byte positions as a flat array of doubles), a barrier, then
+// written to its place -- so destinations never run ahead of sources and nothing is staged in registers
+// (at 1024 threads a thread has 64 of them: register staging spills to local memory, i.e. goes through L2).
+// Chunks in front of the first dropped point do not move at all.
+// s_scan: >= 33 uint64 of shared memory; smem: >= 4 x blockDim x (4 + 32) bytes of shared memory, 16-byte aligned.
 template <class Keep>
-__device__ inline int block_compact_points(const PointStore &ps, int n, Keep keep, int *s_scan)
+__device__ inline int block_compact_points(const PointStore &ps, int n, Keep keep, int *s_scan, int *smem,
+                                           long long *dbg = nullptr)
 {
+#define LVT_CDBG(k)                                                                                                   \
+    if (dbg && threadIdx.x == 0)                                                                                      \
+    dbg[k] = clock64()
+    constexpr int K = 4;
+    const int T = (int)blockDim.x, t = (int)threadIdx.x;
+    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(s_scan);
+    int *s_map = smem; // source index of the kept points of the chunk, in order
+    double *buf_d = reinterpret_cast<double *>(smem + K * T);
+    uint4 *buf_q = reinterpret_cast<uint4 *>(smem + K * T);
+    int *buf_i = smem + K * T;
     int running = 0;
-    for (int i0 = 0; i0 < n; i0 += blockDim.x)
+    for (int base = 0; base < n; base += K * T)
     {
-        const int i = i0 + threadIdx.x;
-        const bool k = i < n && keep(i);
-        double xyz[3] = {0, 0, 0};
-        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
-        int cnt = 0, age = 0, mi = 0;
-        if (k)
+        int idx[K];
+        bool k[K];
+        unsigned long long packed = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++)
         {
-            xyz[0] = ps.xyz[3 * i];
-            xyz[1] = ps.xyz[3 * i + 1];
-            xyz[2] = ps.xyz[3 * i + 2];
-            d0 = *reinterpret_cast<const uint4 *>(ps.desc + 8 * (size_t)i);
-            d1 = *reinterpret_cast<const uint4 *>(ps.desc + 8 * (size_t)i + 4);
-            cnt = ps.counter[i];
-            age = ps.age[i];
-            mi = ps.match_idx[i];
+            idx[j] = base + j * T + t;
+            k[j] = idx[j] < n && keep(idx[j]);
+            packed |= (unsigned long long)k[j] << (16 * j);
         }
-        int total;
-        const int pos = block_exclusive_scan(k ? 1 : 0, s_scan, &total); // syncs: all reads done
-        if (k)
+        LVT_CDBG(1);
+        unsigned long long total;
+        const unsigned long long excl = block_exclusive_scan4(packed, scratch, &total); // syncs
+        LVT_CDBG(2);
+        const int kept = scan4_sum(total), chunk = min(K * T, n - base);
+        if (running != base || kept != chunk) // uniform: something in or before this chunk was dropped
         {
-            const int d = running + pos;
-            ps.xyz[3 * d] = xyz[0];
-            ps.xyz[3 * d + 1] = xyz[1];
-            ps.xyz[3 * d + 2] = xyz[2];
-            *reinterpret_cast<uint4 *>(ps.desc + 8 * (size_t)d) = d0;
-            *reinterpret_cast<uint4 *>(ps.desc + 8 * (size_t)d + 4) = d1;
-            ps.counter[d] = cnt;
-            ps.age[d] = age;
-            ps.match_idx[d] = mi;
+#pragma unroll
+            for (int j = 0; j < K; j++)
+                if (k[j])
+                    s_map[scan4_position(excl, total, j)] = idx[j];
+            __syncthreads();
+            // positions: 3 x kept doubles.  Asynchronous copies (LDGSTS): every element of the chunk is in
+            // flight at once, no register in between
+            for (int e = t; e < 3 * kept; e += T)
+            {
+                const int p = e / 3;
+                cp_async<8>(buf_d + e, ps.xyz + 3 * (size_t)s_map[p] + (e - 3 * p));
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            for (int e = t; e < 3 * kept; e += T)
+                ps.xyz[3 * (size_t)running + e] = buf_d[e];
+            __syncthreads();
+            LVT_CDBG(3);
+            // descriptors: 2 x kept 16-byte halves
+            for (int e = t; e < 2 * kept; e += T)
+                cp_async<16>(buf_q + e, ps.desc + 8 * (size_t)s_map[e >> 1] + 4 * (e & 1));
+            cp_async_wait_all();
+            __syncthreads();
+            for (int e = t; e < 2 * kept; e += T)
+                *reinterpret_cast<uint4 *>(ps.desc + 8 * (size_t)running + 4 * (size_t)e) = buf_q[e];
+            __syncthreads();
+            LVT_CDBG(4);
+            // counter, age, match_idx
+            for (int e = t; e < kept; e += T)
+            {
+                const int src = s_map[e];
+                cp_async<4>(buf_i + e, ps.counter + src);
+                cp_async<4>(buf_i + kept + e, ps.age + src);
+                cp_async<4>(buf_i + 2 * kept + e, ps.match_idx + src);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            for (int e = t; e < kept; e += T)
+            {
+                ps.counter[running + e] = buf_i[e];
+                ps.age[running + e] = buf_i[kept + e];
+                ps.match_idx[running + e] = buf_i[2 * kept + e];
+            }
         }
-        running += total;
+        running += kept;
         __syncthreads();
+        LVT_CDBG(5);
     }
+#undef LVT_CDBG
     return running;
 }
 
