@@ -342,7 +342,7 @@ def run_b200(args, wl):
         return out
 
     # ---------------- value: frames resident in HBM, pipelined, device-timed ----------------------
-    resident = sensor == 1  # lvt_track_pool is the stereo path; RGB-D frames go through lvt_track_rgbd
+    resident = True
     vos = [lib.create(params, sensor) for _ in range(K)]
     value_poses = [np.zeros((0, 12)) for _ in range(K)]
     value_infos = [[] for _ in range(K)]
@@ -350,9 +350,12 @@ def run_b200(args, wl):
         def upload(k):
             vos[k].pool_reserve(n_value)
             for s0 in range(0, n_value, fps_step):
-                chunk, _ = host_frames(streams[k], s0, fps_step, sensor)
+                chunk, dep = host_frames(streams[k], s0, fps_step, sensor)
                 for i in range(fps_step):
-                    vos[k].pool_upload(s0 + i, chunk[i, 0], chunk[i, 1])
+                    if sensor == 1:
+                        vos[k].pool_upload(s0 + i, chunk[i, 0], chunk[i, 1])
+                    else:
+                        vos[k].pool_upload(s0 + i, chunk[i], dep[i])
         in_threads(upload)
 
         def steps(k, lo, hi):
@@ -388,7 +391,7 @@ def run_b200(args, wl):
     wall_ms = max_over_ranks(wall_ms)
 
     # ---------------- roofline: per-kernel CUDA-event times over a short identical repeat ----------
-    ktimes, lm_evals = {}, []
+    ktimes, ktimes_single, lm_evals = {}, {}, []
     if resident and prof_steps:
         lib.reset_kernel_times()
         lib.set_profiling(True)
@@ -397,6 +400,21 @@ def run_b200(args, wl):
             lm_evals += [vos[0].frame_counters(i)["lm_evaluations"] for i in range(fps_step)]
         lib.set_profiling(False)
         ktimes = lib.kernel_times()
+        # the same kernels at one frame per extraction launch ("report both single-frame and batched")
+        os.environ["LVT_B200_GROUP"] = "1"
+        single = lib.create(params, sensor)
+        single.pool_reserve(2 * fps_step)
+        chunk, dep = host_frames(streams[0], 0, 2 * fps_step, sensor)
+        for i in range(2 * fps_step):
+            single.pool_upload(i, chunk[i, 0] if sensor == 1 else chunk[i], chunk[i, 1] if sensor == 1 else dep[i])
+        single.track_pool(0, fps_step, want_infos=False)
+        del os.environ["LVT_B200_GROUP"]
+        lib.reset_kernel_times()
+        lib.set_profiling(True)
+        single.track_pool(fps_step, fps_step, want_infos=False)
+        lib.set_profiling(False)
+        ktimes_single = lib.kernel_times()
+        single.destroy()
     for vo in vos:
         vo.destroy()
 
@@ -412,13 +430,7 @@ def run_b200(args, wl):
         fn, a = callers[k][0], callers[k][1]
         for i in range(lo, hi):
             fn(*a[i])
-    if not resident or not prof_steps:
-        lib.reset_kernel_times()
-        lib.set_profiling(K == 1 and not resident)  # RGB-D: per-kernel times come from the blocking calls' warm-up
     in_threads(lambda k: e2e_range(k, 0, args.warmup * fps_step))
-    if not resident and K == 1:
-        lib.set_profiling(False)
-        ktimes = lib.kernel_times()
     barrier()
     sampler.start()  # second timed region: the samples of both go into one record
     launches1 = lib.launch_count()
@@ -432,8 +444,7 @@ def run_b200(args, wl):
     clocks = sampler.stop()  # sampled during both timed regions (value and e2e)
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * K * n_timed / e2e_s
-    if not resident:  # no resident path for RGB-D yet: the device-resident figure is not measured separately
-        dev_ms, launches = 1e3 * e2e_s, e2e_launches
+    _ = e2e_launches
     value = world * K * n_timed / (dev_ms * 1e-3)
     drift = None
     if sensor == 1:
@@ -442,6 +453,46 @@ def run_b200(args, wl):
     e2e_infos_last = [v.frame_info() for v in vos2]
     for vo in vos2:
         vo.destroy()
+
+    # ---------------- e2e, look-ahead: lvt_track_batch on the same host buffers, one call per step -----------
+    def batch_arm(pinned):
+        vs = [lib.create(params, sensor) for _ in range(K)]
+        bufs = []
+        for k in range(K):
+            fr, dp = callers[k][2], callers[k][3]
+            if pinned:
+                pf = lib.pinned_empty(fr.shape, fr.dtype)
+                pf[...] = fr
+                pd = None
+                if dp is not None:
+                    pd = lib.pinned_empty(dp.shape, dp.dtype)
+                    pd[...] = dp
+                fr, dp = pf, pd
+            bufs.append((fr, dp))
+        out = [np.zeros((0, 12)) for _ in range(K)]
+
+        def run(k, lo, hi):
+            fr, dp = bufs[k]
+            for s in range(lo, hi):
+                sl = slice(s * fps_step, (s + 1) * fps_step)
+                if sensor == 1:
+                    p, _ = vs[k].track_batch(list(fr[sl, 0]), list(fr[sl, 1]), want_infos=False)
+                else:
+                    p, _ = vs[k].track_batch(list(fr[sl]), list(dp[sl]), want_infos=False)
+                out[k] = np.concatenate([out[k], p])
+        in_threads(lambda k: run(k, 0, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        in_threads(lambda k: run(k, args.warmup, args.warmup + args.steps))
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        ok = all(v.get_state() == capi.STATE_TRACKING for v in vs)
+        same = bool(np.array_equal(out[0], e2e_poses[0]))
+        for v in vs:
+            v.destroy()
+        return world * K * n_timed / dt, ok, same
+    batch_value, batch_ok, batch_same = batch_arm(False)
+    batch_pinned_value, _, batch_pinned_same = batch_arm(True)
 
     # ---------------- workload statistics, roofline bookkeeping -----------------------------------
     infos = value_infos[0][args.warmup * fps_step:] if resident else e2e_infos_last
@@ -464,17 +515,28 @@ def run_b200(args, wl):
         alg = algorithmic_bytes(W, H, sensor, st)
         peak, peak_src = load_peaks()
         traffic = load_traffic()
-        per_kernel = {k: {"avg_us": 1e3 * ms / cnt, "launches": cnt, "ms": ms} for k, (ms, cnt) in ktimes.items() if cnt}
+        def table(kt):
+            pk = {k: {"avg_us": 1e3 * ms / cnt, "launches": cnt, "ms": ms} for k, (ms, cnt) in kt.items() if cnt}
+            fr = max(1, pk.get("pose_kernel", pk.get("track_b_kernel", {"launches": 1}))["launches"])
+            for k, v in pk.items():
+                v["launches_per_frame"] = v["launches"] / fr
+                v["us_per_frame"] = 1e3 * v["ms"] / fr
+                # `alg` is per frame; a launch covers 1 / launches_per_frame frames
+                v["alg_per_launch"] = alg[k] / v["launches_per_frame"] if k in alg else None
+            return pk, fr
+        per_kernel, frames_prof = table(ktimes)
+        per_kernel_single, _ = table(ktimes_single) if ktimes_single else ({}, 1)
         tot = sum(v["ms"] for v in per_kernel.values()) or 1.0
-        frames_prof = max(1, per_kernel.get("pose_kernel", per_kernel.get("track_b_kernel", {"launches": 1}))["launches"])
         dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["ms"], default=None)
         if dom:
-            achieved = alg[dom] / (per_kernel[dom]["avg_us"] * 1e-6) / 1e9
-            frame_bytes = sum(alg[k] * v["launches"] for k, v in per_kernel.items() if k in alg) / frames_prof
+            achieved = per_kernel[dom]["alg_per_launch"] / (per_kernel[dom]["avg_us"] * 1e-6) / 1e9
+            frame_bytes = sum(alg[k] for k in per_kernel if k in alg)
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic.get(dom),
                         "traffic_source": "profiles/traffic.json (ncu --set full, dram read + write per launch)",
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": per_kernel[dom]["alg_per_launch"],
+                        "frames_per_extraction_launch": round(1.0 / per_kernel["score_kernel"]["launches_per_frame"], 2)
+                        if "score_kernel" in per_kernel else None,
                         "avg_launch_us": per_kernel[dom]["avg_us"],
                         "lm_evaluations_per_frame": st["lm_evals"],
                         "frame": {"algorithmic_bytes": frame_bytes, "GBps": frame_bytes * value / world / K / 1e9,
@@ -482,11 +544,15 @@ def run_b200(args, wl):
                                   "note": "all kernels of one frame / time per frame of `value` (one sequence)"},
                         "note": "latency/ALU-bound at one stereo pair per launch; see DESIGN.md section 4",
                         "per_kernel": {k: {"avg_us": round(v["avg_us"], 2), "share": round(v["ms"] / tot, 4),
-                                           "launches_per_frame": round(v["launches"] / frames_prof, 2),
-                                           "alg_bytes": round(alg[k]) if k in alg else None,
-                                           "GBps": round(alg[k] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None,
+                                           "launches_per_frame": round(v["launches_per_frame"], 3),
+                                           "alg_bytes_per_launch": round(v["alg_per_launch"]) if k in alg else None,
+                                           "GBps": round(v["alg_per_launch"] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None,
                                            "traffic": traffic.get(k)}
-                                       for k, v in per_kernel.items()}}
+                                       for k, v in per_kernel.items()},
+                        "per_kernel_one_frame_per_launch": {
+                            k: {"avg_us": round(v["avg_us"], 2), "launches_per_frame": round(v["launches_per_frame"], 3),
+                                "GBps": round(v["alg_per_launch"] / (v["avg_us"] * 1e-6) / 1e9, 2) if k in alg else None}
+                            for k, v in per_kernel_single.items()}}
 
     # ---------------- CPU baseline + ATE vs the reference path (rank 0, sequence 0) ---------------
     cpu = ate = None
@@ -523,12 +589,19 @@ def run_b200(args, wl):
                                    "timing": ("CUDA events around each lvt_track_pool call (first extraction launch .. result copy), "
                                               "summed over steps" if K == 1 else
                                               "CUDA events around the %d concurrent sequences of the rank" % K) +
-                                             ", max over ranks; wall clock %.1f ms/step" % (wall_ms / args.steps)
-                                             if resident else "RGB-D has no resident path yet: value repeats e2e"},
+                                             ", max over ranks; wall clock %.1f ms/step" % (wall_ms / args.steps),
+                                   "frames_per_extraction_launch": "4 (lvt_track_pool / lvt_track_batch group size)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": K * fps_step * imgs_bytes,
                         "d2h_bytes_per_step": K * fps_step * 176,
                         "call": ("lvt_track" if sensor == 1 else "lvt_track_rgbd") + " (reference C ABI), host buffers, blocking per frame",
-                        "tracking_ok": e2e_ok, "drift_vs_ground_truth_m": drift},
+                        "tracking_ok": e2e_ok, "drift_vs_ground_truth_m": drift,
+                        "batch": {"value": batch_value, "unit": "frames/s",
+                                  "call": "lvt_track_batch%s, %d frames per call, the same (pageable) host buffers: staging, H2D and "
+                                          "extraction of later frames run behind the tracking of earlier ones"
+                                          % ("" if sensor == 1 else "_rgbd", fps_step),
+                                  "tracking_ok": batch_ok, "poses_identical_to_blocking_calls": batch_same,
+                                  "page_locked_buffers_value": batch_pinned_value,
+                                  "page_locked_poses_identical": batch_pinned_same}},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         if ate:
             line.update(ate)

@@ -22,6 +22,8 @@
 #define LVT_API
 #endif
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -174,7 +176,7 @@ LVT_API int lvt_set_rectification(lvt_handle vo_system, const lvt_rectify_c *lef
  * frames are already in device memory the same per-frame pipeline can run back to back with the
  * feature extraction of frame t+1 overlapped with the tracking of frame t (compute_features is
  * state-free, lvt/src/lvt_image_features_handler.cpp:196-209).  Results are identical to calling
- * lvt_track on the same frames in the same order.  Stereo only. */
+ * lvt_track (lvt_track_rgbd) on the same frames in the same order. */
 LVT_API int lvt_pool_reserve(lvt_handle vo_system, int n_frames);
 /* copy one stereo pair (tightly packed u8) into pool slot `frame` */
 LVT_API int lvt_pool_upload(lvt_handle vo_system, int frame, const unsigned char *left, const unsigned char *right);
@@ -182,7 +184,27 @@ LVT_API int lvt_pool_upload(lvt_handle vo_system, int frame, const unsigned char
  * (R row-major, then t), infos: n entries; either may be NULL.  Returns 0 on success. */
 LVT_API int lvt_track_pool(lvt_handle vo_system, int first_frame, int n_frames, double *poses, lvt_frame_info *infos);
 
-/* device time (CUDA events, ms) of the last lvt_track_pool call, and kernels launched so far */
+/* RGB-D frame into pool slot `frame` (gray u8 + depth in metres, float32) */
+LVT_API int lvt_pool_upload_rgbd(lvt_handle vo_system, int frame, const unsigned char *gray, const float *depth_m);
+
+/* ---- batches of frames in HOST memory (new; the look-ahead path of SURVEY.md section 8b / 8f-2) -------
+ * n_frames consecutive frames the caller holds in host memory, as lvt_track takes them (8-bit, tightly
+ * packed; left[i] / right[i] point at frame i).  Equivalent to n_frames consecutive lvt_track calls on the
+ * same frames -- same poses, same map, bit for bit -- but the frames go through the device in groups:
+ * staging / H2D of later frames and their feature extraction (one launch per group of frames: the
+ * extraction is state-free, lvt/src/lvt_image_features_handler.cpp:196-209) run behind the tracking of
+ * earlier ones.  Page-locked buffers (lvt_alloc_pinned, cudaHostRegister) are read by the DMA engine
+ * directly; pageable ones are staged.  Blocks until every pose is known.  poses: n x 12 doubles (R
+ * row-major, then t), infos: n entries; either may be NULL.  Returns 0 on success (see lvt_get_last_status). */
+LVT_API int lvt_track_batch(lvt_handle vo_system, int n_frames, const unsigned char *const *left,
+                            const unsigned char *const *right, int n_rows, int n_cols, double *poses, lvt_frame_info *infos);
+LVT_API int lvt_track_batch_rgbd(lvt_handle vo_system, int n_frames, const unsigned char *const *gray,
+                                 const float *const *depth_m, int n_rows, int n_cols, double *poses, lvt_frame_info *infos);
+/* page-locked host memory for frames handed to lvt_track* (optional: any host memory is accepted) */
+LVT_API void *lvt_alloc_pinned(size_t bytes);
+LVT_API void lvt_free_pinned(void *p);
+
+/* device time (CUDA events, ms) of the last lvt_track_pool / lvt_track_batch call, and kernels launched so far */
 LVT_API double lvt_last_batch_ms(lvt_handle vo_system);
 LVT_API long lvt_launch_count(void);
 /* per-kernel device time, measured with CUDA event pairs on the launching stream */

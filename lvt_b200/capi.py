@@ -160,6 +160,14 @@ class Library:
         lib.lvt_pool_reserve.argtypes = [vp, C.c_int]
         lib.lvt_pool_upload.argtypes = [vp, C.c_int, c_u8p, c_u8p]
         lib.lvt_track_pool.argtypes = [vp, C.c_int, C.c_int, c_f64p, C.POINTER(FrameInfo)]
+        lib.lvt_pool_upload_rgbd.argtypes = [vp, C.c_int, c_u8p, c_f32p]
+        lib.lvt_track_batch.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, c_f64p,
+                                        C.POINTER(FrameInfo)]
+        lib.lvt_track_batch_rgbd.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                             c_f64p, C.POINTER(FrameInfo)]
+        lib.lvt_alloc_pinned.restype = C.c_void_p
+        lib.lvt_alloc_pinned.argtypes = [C.c_size_t]
+        lib.lvt_free_pinned.argtypes = [C.c_void_p]
         lib.lvt_set_profiling.argtypes = [C.c_int]
         lib.lvt_get_kernel_times.argtypes = [c_f64p, C.POINTER(C.c_long), C.c_int]
         lib.lvt_kernel_name.argtypes = [C.c_int]
@@ -185,6 +193,22 @@ class Library:
         cnt = (C.c_long * 32)()
         n = self.lib.lvt_get_kernel_times(_ptr(ms, c_f64p), cnt, 32)
         return {self.lib.lvt_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def pinned_empty(self, shape, dtype=np.uint8):
+        """numpy array over page-locked host memory from lvt_alloc_pinned (kept alive by the array's base object)"""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self.lib.lvt_alloc_pinned(n)
+        if not ptr:
+            raise LvtError("lvt_alloc_pinned(%d) failed" % n)
+        lib = self.lib
+
+        class _Owner:
+            def __del__(self_inner):
+                lib.lvt_free_pinned(ptr)
+        buf = (C.c_uint8 * n).from_address(ptr)
+        owner = _Owner()
+        buf._owner = owner
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def last_error(self):
         return self.lib.lvtk_last_error().decode()
@@ -312,9 +336,31 @@ class System:
         _check(self.lib.lvt_pool_reserve(self.h, n_frames), "lvt_pool_reserve")
 
     def pool_upload(self, frame, left, right):
+        """stereo: (left, right) u8 images; RGB-D: (gray u8, depth float32 metres)"""
         left = np.ascontiguousarray(left, np.uint8)
+        if np.asarray(right).dtype == np.float32:
+            depth = np.ascontiguousarray(right, np.float32)
+            _check(self.lib.lvt_pool_upload_rgbd(self.h, frame, _u8(left), _ptr(depth, c_f32p)), "lvt_pool_upload_rgbd")
+            return
         right = np.ascontiguousarray(right, np.uint8)
         _check(self.lib.lvt_pool_upload(self.h, frame, _u8(left), _u8(right)), "lvt_pool_upload")
+
+    def track_batch(self, a, b, want_infos=True):
+        """n frames in host memory through lvt_track_batch / lvt_track_batch_rgbd.  a: n left (gray) images u8,
+        b: n right images u8 or n depth images float32 (lists of arrays, or arrays [n][H][W]).
+        Returns (poses n x 12, infos list or None)."""
+        n = len(a)
+        rgbd = np.asarray(b[0]).dtype == np.float32
+        a = [np.ascontiguousarray(x, np.uint8) for x in a]
+        b = [np.ascontiguousarray(x, np.float32 if rgbd else np.uint8) for x in b]
+        pa = (C.c_void_p * n)(*[x.ctypes.data for x in a])
+        pb = (C.c_void_p * n)(*[x.ctypes.data for x in b])
+        poses = np.zeros((n, 12), np.float64)
+        infos = (FrameInfo * n)() if want_infos else None
+        fn = self.lib.lvt_track_batch_rgbd if rgbd else self.lib.lvt_track_batch
+        _check(fn(self.h, n, pa, pb, a[0].shape[0], a[0].shape[1], _ptr(poses, c_f64p), infos),
+               "lvt_track_batch_rgbd" if rgbd else "lvt_track_batch")
+        return poses, ([infos[i].as_dict() for i in range(n)] if want_infos else None)
 
     def track_pool(self, first, n, want_infos=True):
         """Track resident frames [first, first+n): returns (poses n x 12, infos list or None)."""

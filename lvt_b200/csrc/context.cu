@@ -391,6 +391,7 @@ struct lvtk_ctx
     static constexpr int kSets = 6;     // feature sets (left, right) cycling through them
     FeatDev feats_h[2 * kSets];
     int last_set = 0; // set holding the features of the last tracked frame
+    const FeatDev *last_feats_h = nullptr; // host copies of the (left, right) feature sets of the last tracked frame
     FeatDev *feats_d = nullptr;
     int *d_slots = nullptr;
     uint8_t *h_stage = nullptr; // pinned, one image per pool slot, the pool's pitch
@@ -435,8 +436,33 @@ struct lvtk_ctx
     ImagePool rpool;
     int rpool_frames = 0;
     int *d_slot_table = nullptr;       // [2 * rpool_frames] = 0, 1, 2, ...
-    FrameResult *d_results = nullptr;  // [rpool_frames]
-    FrameResult *h_results = nullptr;  // pinned
+
+    float *rdepth = nullptr;           // resident RGB-D pool: [rpool_frames][rows][cols] metres
+
+    // ---- the batched engine (lvt_track_pool / lvt_track_batch*): frames go through feature extraction in
+    // groups of `G` (one launch of every extraction kernel per group: grid z indexes the images) on one of
+    // three extraction streams while the tracking stream consumes their feature sets in order.  Allocated
+    // at the first batched call (ctx_ensure_engine).
+    struct Engine
+    {
+        static constexpr int kSlots = 3; // groups in flight: being uploaded / extracted / tracked
+        bool ready = false;
+        int G = 4;
+        DeviceArena arena;
+        std::vector<FeatDev> feats_h; // [2 * kSlots * G]
+        FeatDev *feats_d = nullptr;
+        std::vector<CandLists> row_cand; // [kSlots * G]
+        DetectWorkspace ws[kSlots];      // batch = 2 G images
+        cudaEvent_t ev_extracted[kSlots] = {}, ev_tracked[kSlots] = {};
+        // ring of device image slots for frames that arrive in host memory, their pinned staging, slot table
+        ImagePool pool;
+        uint8_t *raw = nullptr, *h_stage = nullptr;
+        int *d_slots = nullptr;
+        float *d_depth = nullptr, *h_depth = nullptr;
+        // per-frame results of a batch
+        FrameResult *d_results = nullptr, *h_results = nullptr;
+        int results_cap = 0;
+    } eng;
 
     PointStore map, staged;
     TrackScratch sc;
@@ -499,6 +525,114 @@ static int ctx_grow_points(lvtk_ctx *c)
     LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->n_grown++;
     return LVTK_OK;
+}
+
+static int ctx_ensure_engine(lvtk_ctx *c)
+{
+    lvtk_ctx::Engine &E = c->eng;
+    if (E.ready)
+        return LVTK_OK;
+    LVT_CUDA_TRY(cudaDeviceSynchronize());
+    E.G = 4;
+    if (const char *e = std::getenv("LVT_B200_GROUP")) // frames per extraction launch (tuning aid)
+        E.G = std::max(1, std::min(8, std::atoi(e)));
+    const int n_sets = lvtk_ctx::Engine::kSlots * E.G, rows = c->params.img_height, cols = c->params.img_width;
+    const int n_cells = c->cam.cells_x * c->cam.cells_y;
+    E.feats_h.resize(2 * (size_t)n_sets);
+    E.row_cand.resize((size_t)n_sets);
+    int rc = LVTK_OK;
+    for (size_t i = 0; i < E.feats_h.size() && !rc; i++)
+        rc = make_feat(&E.feats_h[i], E.arena, c->fcap, n_cells, rows);
+    rc = rc ? rc : E.arena.alloc(&E.feats_d, E.feats_h.size());
+    for (int i = 0; i < n_sets && !rc; i++)
+    {
+        rc = E.arena.alloc(&E.row_cand[i].keys, (size_t)c->fcap * kRowCandCap);
+        rc = rc ? rc : E.arena.alloc(&E.row_cand[i].count, (size_t)c->fcap);
+        E.row_cand[i].cap = kRowCandCap;
+    }
+    for (int k = 0; k < lvtk_ctx::Engine::kSlots && !rc; k++)
+    {
+        rc = make_detect_workspace(&E.ws[k], E.arena, c->dp.grid, rows, c->pool.pitch, 2 * E.G);
+        E.ws[k].error = c->ws.error; // one sticky error flag per context
+    }
+    // the ring for host frames: 2 images per frame (RGB-D uses every other slot's worth: G per group)
+    rc = rc ? rc : make_image_pool(&E.pool, E.arena, rows, cols, 2 * n_sets);
+    rc = rc ? rc : E.arena.alloc(&E.raw, E.pool.slot_bytes() * 2 * (size_t)n_sets);
+    rc = rc ? rc : E.arena.alloc(&E.d_slots, 2 * (size_t)n_sets);
+    rc = rc ? rc : E.arena.alloc(&E.d_depth, (size_t)n_sets * rows * cols);
+    if (rc)
+        return rc;
+    LVT_CUDA_TRY(cudaMemcpy(E.feats_d, E.feats_h.data(), sizeof(FeatDev) * E.feats_h.size(), cudaMemcpyHostToDevice));
+    std::vector<int> table(2 * (size_t)n_sets);
+    for (size_t i = 0; i < table.size(); i++)
+        table[i] = (int)i;
+    LVT_CUDA_TRY(cudaMemcpy(E.d_slots, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice));
+    LVT_CUDA_TRY(cudaMallocHost(&E.h_stage, E.pool.slot_bytes() * 2 * (size_t)n_sets));
+    std::memset(E.h_stage, 0, E.pool.slot_bytes() * 2 * (size_t)n_sets);
+    LVT_CUDA_TRY(cudaMallocHost(&E.h_depth, sizeof(float) * (size_t)n_sets * rows * cols));
+    for (int k = 0; k < lvtk_ctx::Engine::kSlots; k++)
+    {
+        LVT_CUDA_TRY(cudaEventCreateWithFlags(&E.ev_extracted[k], cudaEventDisableTiming));
+        LVT_CUDA_TRY(cudaEventCreateWithFlags(&E.ev_tracked[k], cudaEventDisableTiming));
+    }
+    LVT_CUDA_TRY(cudaDeviceSynchronize()); // the arena's memsets ran on the default stream
+    E.ready = true;
+    return LVTK_OK;
+}
+
+static int ctx_ensure_results(lvtk_ctx *c, int n)
+{
+    lvtk_ctx::Engine &E = c->eng;
+    if (n <= E.results_cap)
+        return LVTK_OK;
+    LVT_CUDA_TRY(cudaDeviceSynchronize());
+    if (E.d_results)
+        cudaFree(E.d_results);
+    if (E.h_results)
+        cudaFreeHost(E.h_results);
+    E.d_results = nullptr, E.h_results = nullptr, E.results_cap = 0;
+    int cap = 64;
+    while (cap < n)
+        cap <<= 1;
+    LVT_CUDA_TRY(cudaMalloc(&E.d_results, sizeof(FrameResult) * (size_t)cap));
+    LVT_CUDA_TRY(cudaMallocHost(&E.h_results, sizeof(FrameResult) * (size_t)cap));
+    E.results_cap = cap;
+    return LVTK_OK;
+}
+
+static void ctx_free_engine(lvtk_ctx *c)
+{
+    lvtk_ctx::Engine &E = c->eng;
+    E.arena.release();
+    for (int k = 0; k < lvtk_ctx::Engine::kSlots; k++)
+    {
+        if (E.ev_extracted[k])
+            cudaEventDestroy(E.ev_extracted[k]);
+        if (E.ev_tracked[k])
+            cudaEventDestroy(E.ev_tracked[k]);
+    }
+    if (E.h_stage)
+        cudaFreeHost(E.h_stage);
+    if (E.h_depth)
+        cudaFreeHost(E.h_depth);
+    if (E.d_results)
+        cudaFree(E.d_results);
+    if (E.h_results)
+        cudaFreeHost(E.h_results);
+    E.ready = false;
+}
+
+// true when `p` is page-locked host memory (cudaMallocHost / cudaHostRegister / lvt_alloc_pinned): the DMA
+// engine reads it directly, the staging copy is skipped
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
 }
 
 // the context's copy of the BRIEF table follows lvt_set_brief_pairs; `stream` = where the next
@@ -741,8 +875,7 @@ static void ctx_free(lvtk_ctx *c)
     if (c->h_early)
         cudaFreeHost(c->h_early);
     c->rarena.release();
-    if (c->h_results)
-        cudaFreeHost(c->h_results);
+    ctx_free_engine(c);
     c->arena.release();
     if (c->h_stage)
         cudaFreeHost(c->h_stage);
@@ -932,6 +1065,7 @@ struct System
     {
         lvtk_ctx *c = ctx;
         c->last_set = 0;
+        c->last_feats_h = c->feats_h;
         if (int rc = launch_index(c->feats_d, sensor == 1 ? 2 : 1, c->cam, c->stream))
             return rc;
         if (sensor == 1)
@@ -1052,6 +1186,7 @@ struct System
         const int *slots = c->d_slots + 2 * s;
         host_mark(0);
         c->last_set = s;
+        c->last_feats_h = c->feats_h + 2 * s;
         static const bool timeline = std::getenv("LVT_B200_TIMELINE") != nullptr;
         if (timeline)
         {
@@ -1205,6 +1340,7 @@ struct System
         float *h_depth = c->h_depth + s * npx, *d_depth = c->d_depth + s * npx;
         host_mark(0);
         c->last_set = s;
+        c->last_feats_h = c->feats_h + 2 * s;
         ctx_stage_image(c, 2 * s, gray, rows, cols, cols);
         if (int rc = ctx_stage_flush(c, xl))
             return rc;
@@ -1251,7 +1387,7 @@ struct System
         return LVTK_OK;
     }
 
-    // ---- resident pool: frames already in HBM, extraction of frame t+1 overlapped with tracking of t
+    // ---- resident pool: frames already in HBM -------------------------------------------------------
     int pool_reserve(int n_frames)
     {
         lvtk_ctx *c = ctx;
@@ -1260,31 +1396,30 @@ struct System
         finish_pending();
         LVT_CUDA_TRY(cudaDeviceSynchronize());
         c->rarena.release();
-        if (c->h_results)
-            cudaFreeHost(c->h_results);
-        c->h_results = nullptr;
         c->rpool_frames = 0;
+        c->rdepth = nullptr;
         const int per = sensor == 1 ? 2 : 1;
         if (int rc = make_image_pool(&c->rpool, c->rarena, c->params.img_height, c->params.img_width, per * n_frames))
             return rc;
         int rc = c->rarena.alloc(&c->d_slot_table, (size_t)per * n_frames);
-        rc = rc ? rc : c->rarena.alloc(&c->d_results, (size_t)n_frames);
+        if (sensor == 2)
+            rc = rc ? rc : c->rarena.alloc(&c->rdepth, (size_t)n_frames * c->params.img_height * c->params.img_width);
         if (rc)
             return rc;
         std::vector<int> table((size_t)per * n_frames);
         for (size_t i = 0; i < table.size(); i++)
             table[i] = (int)i;
         LVT_CUDA_TRY(cudaMemcpy(c->d_slot_table, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice));
-        LVT_CUDA_TRY(cudaMallocHost(&c->h_results, sizeof(FrameResult) * (size_t)n_frames));
         LVT_CUDA_TRY(cudaDeviceSynchronize());
         c->rpool_frames = n_frames;
         return LVTK_OK;
     }
 
-    int pool_upload(int frame, const uint8_t *left, const uint8_t *right)
+    // stereo: (left, right); RGB-D: (gray, nullptr, depth)
+    int pool_upload(int frame, const uint8_t *left, const uint8_t *right, const float *depth)
     {
         lvtk_ctx *c = ctx;
-        if (frame < 0 || frame >= c->rpool_frames || !left || (sensor == 1 && !right))
+        if (frame < 0 || frame >= c->rpool_frames || !left || (sensor == 1 && !right) || (sensor == 2 && !depth))
             return LVTK_ERR_ARG;
         const int per = sensor == 1 ? 2 : 1, rows = c->params.img_height, cols = c->params.img_width;
         const uint8_t *src[2] = {left, right};
@@ -1296,6 +1431,9 @@ struct System
             uint8_t *dst = c->rectify && sensor == 1 ? c->raw + c->pool.slot_bytes() * k : slot;
             LVT_CUDA_TRY(cudaMemcpy2DAsync(dst, c->rpool.pitch, src[k], cols, cols, rows, cudaMemcpyHostToDevice, c->stream));
         }
+        if (sensor == 2)
+            LVT_CUDA_TRY(cudaMemcpyAsync(c->rdepth + (size_t)frame * rows * cols, depth, sizeof(float) * (size_t)rows * cols,
+                                         cudaMemcpyHostToDevice, c->stream));
         if (c->rectify && sensor == 1)
         {
             // raw frames are rectified once, on their way into the resident pool
@@ -1310,49 +1448,138 @@ struct System
         return LVTK_OK;
     }
 
-    // frames [start, n) of the batch that begins at pool frame `first`: enqueue, wait, fetch the results
-    int run_pool_range(int first, int start, int n)
+    // ---- the batched engine ---------------------------------------------------------------------------
+    // Where the frames of a batch come from: the resident pool (first + i) or the caller's host memory.
+    struct FrameSource
+    {
+        int first = 0;                       // resident: pool frame of batch frame 0
+        const uint8_t *const *a = nullptr;   // host: left / gray images, tightly packed
+        const uint8_t *const *b = nullptr;   // host: right images (stereo)
+        const float *const *depth = nullptr; // host: depth images in metres (RGB-D)
+        bool host() const { return a != nullptr; }
+    };
+
+    // one host image -> ring slot `slot` on stream sx: page-locked memory is read by the DMA engine directly,
+    // pageable memory goes through the pinned staging slot (row bands copied by the staging lanes)
+    int upload_ring_image(const uint8_t *img, int slot, cudaStream_t sx, bool to_raw)
     {
         lvtk_ctx *c = ctx;
-        // timed on the device: first extraction launch .. last result copy
-        LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
-        for (int x = 0; x < lvtk_ctx::kXStreams; x++)
-            LVT_CUDA_TRY(cudaStreamWaitEvent(c->xs[x], c->ev_batch[0], 0));
-        for (int i = start; i < n; i++)
+        lvtk_ctx::Engine &E = c->eng;
+        const int rows = c->params.img_height, cols = c->params.img_width;
+        uint8_t *dst = (to_raw ? E.raw : E.pool.data) + E.pool.slot_bytes() * (size_t)slot;
+        if (is_pinned_host(img))
         {
-            // frame i: extraction pipeline k % kXStreams, feature set k % kSets.  Extraction is
-            // state-free, so up to kXStreams frames are extracted concurrently while the tracking
-            // stream consumes them in order; a set is reused only after its frame has been tracked.
-            const int k = i - start;
-            const int set = k % lvtk_ctx::kSets, x = k % lvtk_ctx::kXStreams;
-            cudaStream_t sx = c->xs[x];
-            if (k >= lvtk_ctx::kSets)
-                LVT_CUDA_TRY(cudaStreamWaitEvent(sx, c->ev_tracked[set], 0));
-            const int *slots = c->d_slot_table + 2 * (size_t)(first + i);
-            FeatDev *feats = c->feats_d + 2 * set;
-            if (int rc = launch_detect(c->rpool, c->wsx[x], c->dp, slots, 2, feats, kBriefBorder, 1, sx))
-                return rc;
-            const bool fused_index = brief_can_index(c->cam);
-            if (int rc = launch_brief(c->rpool, slots, 2, feats, c->d_brief_offsets, sx, fused_index ? &c->cam : nullptr))
-                return rc;
-            if (!fused_index)
-                if (int rc = launch_index(feats, 2, c->cam, sx))
-                    return rc;
-            if (int rc = launch_rowcand(feats, c->cam, c->row_cand[set], sx))
-                return rc;
-            LVT_CUDA_TRY(cudaEventRecord(c->ev_extracted[set], sx));
-            LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_extracted[set], 0));
-            if (int rc = ctx_launch_track(c, c->d_results + i, feats, c->row_cand[set], c->stream))
-                return rc;
-            LVT_CUDA_TRY(cudaEventRecord(c->ev_tracked[set], c->stream));
-            c->last_set = set;
+            LVT_CUDA_TRY(cudaMemcpy2DAsync(dst, E.pool.pitch, img, cols, cols, rows, cudaMemcpyHostToDevice, sx));
+            return LVTK_OK;
         }
-        LVT_CUDA_TRY(cudaMemcpyAsync(c->h_results + start, c->d_results + start, sizeof(FrameResult) * (size_t)(n - start),
+        c->lanes.add_image(img, (size_t)cols, E.h_stage + E.pool.slot_bytes() * (size_t)slot, dst, E.pool.pitch, (size_t)cols,
+                           rows, c->upload_bands, c->upload_dmas);
+        LVT_CUDA_TRY(c->lanes.run(sx));
+        return LVTK_OK;
+    }
+
+    // frames [start, n) of a batch: enqueue everything, wait, fetch the results into eng.h_results[start..n)
+    int run_frames(const FrameSource &src, int start, int n)
+    {
+        lvtk_ctx *c = ctx;
+        lvtk_ctx::Engine &E = c->eng;
+        constexpr int kSlots = lvtk_ctx::Engine::kSlots;
+        const int G = E.G, per = sensor == 1 ? 2 : 1;
+        const int rows = c->params.img_height, cols = c->params.img_width;
+        const size_t npx = (size_t)rows * cols;
+        const bool fused_index = sensor == 1 && brief_can_index(c->cam);
+        // timed on the device: first upload / extraction launch .. last result copy
+        LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
+        for (int k = 0; k < kSlots; k++)
+            LVT_CUDA_TRY(cudaStreamWaitEvent(c->xs[k], c->ev_batch[0], 0));
+        int gi = 0;
+        for (int g0 = start; g0 < n; g0 += G, gi++)
+        {
+            // group gi: frames g0 .. g0 + gn - 1, extraction stream / workspace / feature sets of slot gi % 3.
+            // Extraction is state-free (lvt_image_features_handler.cpp:196-209): up to three groups are in
+            // flight (uploading, extracting, being tracked); a slot is reused once its frames have been tracked.
+            const int gn = std::min(G, n - g0), slot = gi % kSlots, set0 = slot * G;
+            cudaStream_t sx = c->xs[slot];
+            if (gi >= kSlots)
+            {
+                if (src.host()) // the slot's staging buffers and ring images were last read by that extraction
+                    LVT_CUDA_TRY(cudaEventSynchronize(E.ev_extracted[slot]));
+                LVT_CUDA_TRY(cudaStreamWaitEvent(sx, E.ev_tracked[slot], 0));
+            }
+            const ImagePool *pool = &c->rpool;
+            const int *slots = c->d_slot_table + (size_t)per * (src.first + g0);
+            const float *depth = sensor == 2 ? c->rdepth + npx * (size_t)(src.first + g0) : nullptr;
+            if (src.host())
+            {
+                pool = &E.pool;
+                slots = E.d_slots + per * set0;
+                for (int k = 0; k < gn; k++)
+                {
+                    const bool raw = c->rectify && sensor == 1;
+                    if (int rc = upload_ring_image(src.a[g0 + k], per * (set0 + k), sx, raw))
+                        return rc;
+                    if (sensor == 1)
+                    {
+                        if (int rc = upload_ring_image(src.b[g0 + k], per * (set0 + k) + 1, sx, raw))
+                            return rc;
+                        if (raw)
+                        {
+                            const size_t sb = E.pool.slot_bytes();
+                            const uint8_t *rw[2] = {E.raw + sb * (size_t)(2 * (set0 + k)), E.raw + sb * (size_t)(2 * (set0 + k) + 1)};
+                            uint8_t *dst[2] = {E.pool.data + sb * (size_t)(2 * (set0 + k)), E.pool.data + sb * (size_t)(2 * (set0 + k) + 1)};
+                            const RectifyDev *cams[2] = {&c->rect[0], &c->rect[1]};
+                            if (int rc = launch_rectify(rw, dst, 2, cams, E.pool, sx))
+                                return rc;
+                        }
+                    }
+                    else
+                    {
+                        float *dd = E.d_depth + npx * (size_t)(set0 + k);
+                        if (is_pinned_host(src.depth[g0 + k]))
+                            LVT_CUDA_TRY(cudaMemcpyAsync(dd, src.depth[g0 + k], sizeof(float) * npx, cudaMemcpyHostToDevice, sx));
+                        else
+                        {
+                            c->lanes.add_image(src.depth[g0 + k], sizeof(float) * (size_t)cols, E.h_depth + npx * (size_t)(set0 + k), dd,
+                                               sizeof(float) * (size_t)cols, sizeof(float) * (size_t)cols, rows, 2 * c->upload_bands, 2);
+                            LVT_CUDA_TRY(c->lanes.run(sx));
+                        }
+                    }
+                }
+                depth = sensor == 2 ? E.d_depth + npx * (size_t)set0 : nullptr;
+            }
+            // extraction: ONE launch of every kernel for the per * gn images of the group
+            FeatDev *feats = E.feats_d + per * set0;
+            const FeatDev *feats_h = E.feats_h.data() + per * set0;
+            if (int rc = launch_detect(*pool, E.ws[slot], c->dp, slots, per * gn, feats, kBriefBorder, 1, sx))
+                return rc;
+            if (int rc = launch_brief(*pool, slots, per * gn, feats, c->d_brief_offsets, sx, fused_index ? &c->cam : nullptr))
+                return rc;
+            if (sensor == 2)
+                for (int k = 0; k < gn; k++)
+                    if (int rc = launch_depth_gate(feats_h[k], depth + npx * (size_t)k, c->params, sx))
+                        return rc;
+            if (!fused_index)
+                if (int rc = launch_index(feats, per * gn, c->cam, sx))
+                    return rc;
+            if (sensor == 1)
+                for (int k = 0; k < gn; k++)
+                    if (int rc = launch_rowcand(feats + 2 * k, c->cam, E.row_cand[set0 + k], sx))
+                        return rc;
+            LVT_CUDA_TRY(cudaEventRecord(E.ev_extracted[slot], sx));
+            // tracking: strictly in order on the tracking stream
+            LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, E.ev_extracted[slot], 0));
+            for (int k = 0; k < gn; k++)
+                if (int rc = ctx_launch_track(c, E.d_results + (g0 + k), feats + per * k, E.row_cand[set0 + k], c->stream))
+                    return rc;
+            LVT_CUDA_TRY(cudaEventRecord(E.ev_tracked[slot], c->stream));
+            c->last_feats_h = feats_h + per * (gn - 1);
+        }
+        LVT_CUDA_TRY(cudaMemcpyAsync(E.h_results + start, E.d_results + start, sizeof(FrameResult) * (size_t)(n - start),
                                      cudaMemcpyDeviceToHost, c->stream));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[1], c->stream));
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        for (int x = 0; x < lvtk_ctx::kXStreams; x++)
-            LVT_CUDA_TRY(cudaStreamSynchronize(c->xs[x]));
+        for (int k = 0; k < kSlots; k++)
+            LVT_CUDA_TRY(cudaStreamSynchronize(c->xs[k]));
         float ms = 0.f;
         LVT_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_batch[0], c->ev_batch[1]));
         c->last_batch_ms += ms;
@@ -1361,25 +1588,29 @@ struct System
         return LVTK_OK;
     }
 
-    int track_pool(int first, int n, double *poses /* n x 12: R row-major, t */, lvt_frame_info *infos)
+    // n frames of `src`, in order: exactly what n blocking calls would return
+    int track_frames(const FrameSource &src, int n, double *poses /* n x 12: R row-major, t */, lvt_frame_info *infos)
     {
         lvtk_ctx *c = ctx;
-        if (sensor != 1 || first < 0 || n <= 0 || first + n > c->rpool_frames)
-            return LVTK_ERR_ARG;
         if (int rc = finish_pending())
+            return rc;
+        if (int rc = ctx_ensure_engine(c))
+            return rc;
+        if (int rc = ctx_ensure_results(c, n))
             return rc;
         if (int rc = ctx_sync_pairs(c, c->stream))
             return rc;
         // A frame that could overflow the point stores is refused on the device, and so is every frame
         // behind it (TrackState::halt): grow the stores and run the rest of the batch again.
         c->last_batch_ms = 0.f;
+        const FrameResult *res = c->eng.h_results;
         for (int start = 0; start < n;)
         {
-            if (int rc = run_pool_range(first, start, n))
+            if (int rc = run_frames(src, start, n))
                 return rc;
             int refused = n;
             for (int i = start; i < n && refused == n; i++)
-                if (c->h_results[i].info.state == 0)
+                if (res[i].info.state == 0)
                     refused = i;
             if (refused == n)
                 break;
@@ -1389,7 +1620,7 @@ struct System
         }
         for (int i = 0; i < n; i++)
         {
-            const FrameResult &r = c->h_results[i];
+            const FrameResult &r = res[i];
             const bool first_frame = state == 1;
             frame_number++;
             info = r.info;
@@ -1408,6 +1639,32 @@ struct System
                 infos[i] = info;
         }
         return LVTK_OK;
+    }
+
+    int track_pool(int first, int n, double *poses, lvt_frame_info *infos)
+    {
+        if (first < 0 || n <= 0 || first + n > ctx->rpool_frames)
+            return LVTK_ERR_ARG;
+        FrameSource src;
+        src.first = first;
+        return track_frames(src, n, poses, infos);
+    }
+
+    int track_batch(int n, const uint8_t *const *a, const uint8_t *const *b, const float *const *depth, int rows, int cols,
+                    double *poses, lvt_frame_info *infos)
+    {
+        lvtk_ctx *c = ctx;
+        if (n <= 0 || !a || (sensor == 1 && !b) || (sensor == 2 && !depth) || rows != c->params.img_height ||
+            cols != c->params.img_width)
+            return LVTK_ERR_ARG;
+        for (int i = 0; i < n; i++)
+            if (!a[i] || (sensor == 1 && !b[i]) || (sensor == 2 && !depth[i]))
+                return LVTK_ERR_ARG;
+        FrameSource src;
+        src.a = a;
+        src.b = b;
+        src.depth = depth;
+        return track_frames(src, n, poses, infos);
     }
 
     int finish(PoseD *out)
@@ -1584,7 +1841,7 @@ LVT_API int lvt_debug_get_features(lvt_handle h, int which, float *kps_xy, unsig
     lvtk_ctx *c = vo->ctx;
     cudaSetDevice(c->device);
     vo->finish_pending();
-    const FeatDev &f = c->feats_h[2 * c->last_set + which];
+    const FeatDev &f = (c->last_feats_h ? c->last_feats_h : c->feats_h)[which];
     int n = 0;
     if (cudaMemcpy(&n, f.n, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
         return -1;
@@ -1690,7 +1947,56 @@ LVT_API int lvt_pool_upload(lvt_handle h, int frame, const unsigned char *left, 
     if (!vo)
         return LVTK_ERR_ARG;
     cudaSetDevice(vo->ctx->device);
-    return vo->pool_upload(frame, left, right);
+    if (vo->sensor != 1)
+        return LVTK_ERR_ARG;
+    return vo->pool_upload(frame, left, right, nullptr);
+}
+LVT_API int lvt_pool_upload_rgbd(lvt_handle h, int frame, const unsigned char *gray, const float *depth_m)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || vo->sensor != 2)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    return vo->pool_upload(frame, gray, nullptr, depth_m);
+}
+LVT_API int lvt_track_batch(lvt_handle h, int n_frames, const unsigned char *const *left, const unsigned char *const *right,
+                            int n_rows, int n_cols, double *poses, lvt_frame_info *infos)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || vo->sensor != 1)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    const int rc = vo->last_status = vo->track_batch(n_frames, left, right, nullptr, n_rows, n_cols, poses, infos);
+    if (prof_enabled())
+        prof_collect();
+    return rc;
+}
+LVT_API int lvt_track_batch_rgbd(lvt_handle h, int n_frames, const unsigned char *const *gray, const float *const *depth_m,
+                                 int n_rows, int n_cols, double *poses, lvt_frame_info *infos)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || vo->sensor != 2)
+        return LVTK_ERR_ARG;
+    cudaSetDevice(vo->ctx->device);
+    const int rc = vo->last_status = vo->track_batch(n_frames, gray, nullptr, depth_m, n_rows, n_cols, poses, infos);
+    if (prof_enabled())
+        prof_collect();
+    return rc;
+}
+LVT_API void *lvt_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+LVT_API void lvt_free_pinned(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
 }
 LVT_API int lvt_track_pool(lvt_handle h, int first_frame, int n_frames, double *poses, lvt_frame_info *infos)
 {
@@ -1711,7 +2017,7 @@ LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int
     if (!vo)
         return -1;
     vo->finish_pending();
-    const FrameResult &r = i < 0 ? *vo->ctx->h_result : vo->ctx->h_results[i];
+    const FrameResult &r = i < 0 ? *vo->ctx->h_result : vo->ctx->eng.h_results[i];
     std::memcpy(cycles, r.cycles, sizeof(r.cycles));
     std::memcpy(rounds, r.rounds, sizeof(r.rounds));
     return 0;

@@ -257,6 +257,7 @@ namespace
 struct HostPool
 {
     std::vector<std::vector<uint8_t>> left, right;
+    std::vector<std::vector<float>> depth;
 };
 std::map<void *, HostPool> g_pools;
 } // namespace
@@ -513,8 +514,63 @@ LVT_API int lvt_pool_reserve(lvt_handle h, int n_frames)
     HostPool &p = g_pools[h];
     p.left.assign(n_frames, {});
     p.right.assign(n_frames, {});
+    p.depth.assign(n_frames, {});
     return 0;
 }
+LVT_API int lvt_pool_upload_rgbd(lvt_handle h, int frame, const unsigned char *gray, const float *depth_m)
+{
+    auto it = g_pools.find(h);
+    if (it == g_pools.end() || frame < 0 || frame >= (int)it->second.left.size())
+        return -1;
+    const lvt_params_c &prm = static_cast<System *>(h)->params;
+    const size_t n = (size_t)prm.img_width * prm.img_height;
+    it->second.left[frame].assign(gray, gray + n);
+    it->second.depth[frame].assign(depth_m, depth_m + n);
+    return 0;
+}
+/* host batches: the oracle simply runs the blocking call frame by frame */
+LVT_API int lvt_track_batch(lvt_handle h, int n_frames, const unsigned char *const *left, const unsigned char *const *right,
+                            int n_rows, int n_cols, double *poses, lvt_frame_info *infos)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || n_frames <= 0 || !left || !right || vo->sensor != 1)
+        return -1;
+    for (int i = 0; i < n_frames; i++)
+    {
+        double R[3][3], t[3];
+        lvt_track(h, const_cast<unsigned char *>(left[i]), const_cast<unsigned char *>(right[i]), n_rows, n_cols, R, t);
+        if (poses)
+        {
+            std::memcpy(poses + 12 * (size_t)i, R, sizeof(R));
+            std::memcpy(poses + 12 * (size_t)i + 9, t, sizeof(t));
+        }
+        if (infos)
+            infos[i] = vo->info;
+    }
+    return 0;
+}
+LVT_API int lvt_track_batch_rgbd(lvt_handle h, int n_frames, const unsigned char *const *gray, const float *const *depth_m,
+                                 int n_rows, int n_cols, double *poses, lvt_frame_info *infos)
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo || n_frames <= 0 || !gray || !depth_m || vo->sensor != 2)
+        return -1;
+    for (int i = 0; i < n_frames; i++)
+    {
+        double R[3][3], t[3];
+        lvt_track_rgbd(h, gray[i], depth_m[i], n_rows, n_cols, R, t);
+        if (poses)
+        {
+            std::memcpy(poses + 12 * (size_t)i, R, sizeof(R));
+            std::memcpy(poses + 12 * (size_t)i + 9, t, sizeof(t));
+        }
+        if (infos)
+            infos[i] = vo->info;
+    }
+    return 0;
+}
+LVT_API void *lvt_alloc_pinned(size_t bytes) { return std::malloc(bytes ? bytes : 1); } /* no device: plain host memory */
+LVT_API void lvt_free_pinned(void *p) { std::free(p); }
 LVT_API int lvt_pool_upload(lvt_handle h, int frame, const unsigned char *left, const unsigned char *right)
 {
     auto it = g_pools.find(h);
@@ -535,8 +591,12 @@ LVT_API int lvt_track_pool(lvt_handle h, int first, int n, double *poses, lvt_fr
     for (int i = 0; i < n; i++)
     {
         double R[3][3], t[3];
-        lvt_track(h, it->second.left[first + i].data(), it->second.right[first + i].data(), vo->params.img_height,
-                  vo->params.img_width, R, t); /* rectifies first when lvt_set_rectification is on */
+        if (vo->sensor == 2)
+            lvt_track_rgbd(h, it->second.left[first + i].data(), it->second.depth[first + i].data(), vo->params.img_height,
+                           vo->params.img_width, R, t);
+        else
+            lvt_track(h, it->second.left[first + i].data(), it->second.right[first + i].data(), vo->params.img_height,
+                      vo->params.img_width, R, t); /* rectifies first when lvt_set_rectification is on */
         if (poses)
         {
             std::memcpy(poses + 12 * (size_t)i, R, sizeof(R));
