@@ -204,7 +204,8 @@ def run_reference(args, wl):
         frames, depth = host_frames(make_stream(wl, stream_length(args, args.seqs_per_gpu), s), 0, total, sensor)
         vo = orc.create(params, sensor)
         vos.append(vo)
-        calls.append(frame_caller(orc, vo, sensor, frames, depth, np.zeros((total, 12))) + (frames, depth))
+        poses = np.zeros((total, 12))  # kept alive with the call arguments: the C side writes R, t into it
+        calls.append(frame_caller(orc, vo, sensor, frames, depth, poses) + (frames, depth, poses))
     cores = os.cpu_count() or 1
     workers = max(1, min(n_seq, cores // 2))
 
@@ -424,7 +425,15 @@ def run_b200(args, wl):
     callers = []
     for k in range(K):
         frames, depth = host_frames(streams[k], 0, n_e2e, sensor)
-        callers.append(frame_caller(lib, vos2[k], sensor, frames, depth, e2e_poses[k]) + (frames, depth))
+        # the caller's frames live in page-locked host memory (lvt_alloc_pinned): the H2D copy inside the call is
+        # one DMA per image straight from these buffers; the pageable variant (staged) is reported next to it
+        pf = lib.pinned_empty(frames.shape, frames.dtype)
+        pf[...] = frames
+        pd = None
+        if depth is not None:
+            pd = lib.pinned_empty(depth.shape, depth.dtype)
+            pd[...] = depth
+        callers.append(frame_caller(lib, vos2[k], sensor, pf, pd, e2e_poses[k]) + (frames, depth, pf, pd))
 
     def e2e_range(k, lo, hi):
         fn, a = callers[k][0], callers[k][1]
@@ -453,6 +462,19 @@ def run_b200(args, wl):
     e2e_infos_last = [v.frame_info() for v in vos2]
     for vo in vos2:
         vo.destroy()
+    # the same blocking calls on PAGEABLE buffers (staged through pinned memory inside the call), sequence 0 only
+    vp = lib.create(params, sensor)
+    pg_poses = np.zeros((n_e2e, 12))
+    fn_pg, a_pg = frame_caller(lib, vp, sensor, callers[0][2], callers[0][3], pg_poses)
+    for i in range(args.warmup * fps_step):
+        fn_pg(*a_pg[i])
+    t0 = time.perf_counter()
+    for i in range(args.warmup * fps_step, n_e2e):
+        fn_pg(*a_pg[i])
+    torch.cuda.synchronize()
+    e2e_pageable = n_timed / (time.perf_counter() - t0)
+    e2e_pageable_same = bool(np.array_equal(pg_poses, e2e_poses[0]))
+    vp.destroy()
 
     # ---------------- e2e, look-ahead: lvt_track_batch on the same host buffers, one call per step -----------
     def batch_arm(pinned):
@@ -593,10 +615,11 @@ def run_b200(args, wl):
                                    "frames_per_extraction_launch": "4 (lvt_track_pool / lvt_track_batch group size)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": K * fps_step * imgs_bytes,
                         "d2h_bytes_per_step": K * fps_step * 176,
-                        "call": ("lvt_track" if sensor == 1 else "lvt_track_rgbd") + " (reference C ABI), host buffers, blocking per frame",
+                        "call": ("lvt_track" if sensor == 1 else "lvt_track_rgbd") + " (reference C ABI), page-locked host buffers, blocking per frame",
+                        "pageable_buffers_value_one_sequence": e2e_pageable, "pageable_poses_identical": e2e_pageable_same,
                         "tracking_ok": e2e_ok, "drift_vs_ground_truth_m": drift,
                         "batch": {"value": batch_value, "unit": "frames/s",
-                                  "call": "lvt_track_batch%s, %d frames per call, the same (pageable) host buffers: staging, H2D and "
+                                  "call": "lvt_track_batch%s, %d frames per call, pageable host buffers: staging, H2D and "
                                           "extraction of later frames run behind the tracking of earlier ones"
                                           % ("" if sensor == 1 else "_rgbd", fps_step),
                                   "tracking_ok": batch_ok, "poses_identical_to_blocking_calls": batch_same,

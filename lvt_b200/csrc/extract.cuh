@@ -30,6 +30,8 @@ int make_rectify_dev(const lvt_rectify_c &r, RectifyDev *out);
 int launch_rectify(const uint8_t *const raw[2], uint8_t *const dst[2], int n_images, const RectifyDev *const cam[2],
                    const ImagePool &pool, cudaStream_t stream);
 int launch_rectify_maps(const RectifyDev &r, int rows, int cols, float *d_map_x, float *d_map_y, cudaStream_t stream);
+// tightly packed rows (cols bytes each) -> rows of `pitch` bytes (pitch a multiple of 16, >= cols)
+int launch_repitch(const uint8_t *d_packed, uint8_t *d_dst, int rows, int cols, int pitch, cudaStream_t stream);
 
 constexpr int kScoreTileW = 64, kScoreTileH = 32;
 constexpr int kScoreBoxW = 96, kScoreBoxH = kScoreTileH + 6, kScoreBoxX = 16;

@@ -162,6 +162,51 @@ int launch_rectify(const uint8_t *const raw[2], uint8_t *const dst[2], int n_ima
     return LVTK_OK;
 }
 
+// ---- tightly packed image (as the caller holds it, lvt/src/lvt_c.cpp:69-70) -> pitched pool slot ----------
+// A page-locked caller buffer is fetched with ONE contiguous DMA (15 us for 1242x375; the pitched 2-D copy of
+// the same image takes 55 us: measured, tools/probe/h2d_probe.cu) and re-pitched here: every thread writes one
+// aligned 16-byte piece of a destination row from (unaligned) source bytes.
+struct RepitchArgs
+{
+    const uint8_t *src;
+    uint8_t *dst;
+    int rows, cols, pitch;
+};
+
+__global__ void __launch_bounds__(128) repitch_kernel(RepitchArgs a)
+{
+    LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
+    const int y = blockIdx.y, x0 = 16 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (x0 >= a.cols)
+        return;
+    const uint8_t *s = a.src + (size_t)y * a.cols + x0;
+    uint32_t w[4] = {0, 0, 0, 0};
+    const int n = min(16, a.cols - x0);
+    // the source row starts at an arbitrary byte: 2-byte loads when the row offset is even, bytes otherwise
+    if ((((size_t)s) & 1) == 0 && n == 16)
+    {
+        const uint16_t *s2 = reinterpret_cast<const uint16_t *>(s);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            w[k] = (uint32_t)s2[2 * k] | ((uint32_t)s2[2 * k + 1] << 16);
+    }
+    else
+        for (int k = 0; k < n; k++)
+            w[k >> 2] |= (uint32_t)s[k] << (8 * (k & 3));
+    *reinterpret_cast<uint4 *>(a.dst + (size_t)y * a.pitch + x0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_repitch(const uint8_t *d_packed, uint8_t *d_dst, int rows, int cols, int pitch, cudaStream_t stream)
+{
+    RepitchArgs a{d_packed, d_dst, rows, cols, pitch};
+    const dim3 grid(((cols + 15) / 16 + 127) / 128, rows);
+    count_launch();
+    if (launch_chained(repitch_kernel, grid, dim3(128), 0, stream, a) != cudaSuccess)
+        return LVTK_ERR_CUDA;
+    LVT_LAUNCH_CHECK(stream, "repitch_kernel");
+    return LVTK_OK;
+}
+
 int launch_rectify_maps(const RectifyDev &r, int rows, int cols, float *d_map_x, float *d_map_y, cudaStream_t stream)
 {
     RectifyMapArgs a{r, rows, cols, d_map_x, d_map_y};
