@@ -299,11 +299,26 @@ __device__ __forceinline__ void dsmem_red_or(int *local, unsigned rank, int v)
 // from the home slices (coalesced remote loads).  Three generations of home slices rotate, so the
 // slices of the next round are cleared while the current round runs and one barrier per round
 // suffices.  The "changed" flag / match count of a round are collected in rank 0's shared memory.
+//
+// Replica mode (rep != nullptr, the default of track_a_kernel): instead of home slices every CTA keeps a
+// replica of ALL queries' current choices (rep[q], shared memory).  A query that changes its choice
+// stores the new one into every CTA's replica (one coalesced distributed-shared-memory store per warp and
+// CTA; after the first round only a handful change), one cluster barrier ends the round, and every CTA
+// rebuilds its own owner array from its replica with local shared-memory atomics -- no refresh of remote
+// slices, no flags relayed through rank 0.  Stores of the next round that arrive early only make a replica
+// fresher; a round that changes no choice anywhere has seen exactly the final choices in every CTA, and
+// query k is final after round k as before, so the fixed point and the termination test are unchanged.
 struct RoundsTeam
 {
     int rank = 0, nranks = 1;
     int *team_flags = nullptr; // [3][2] in shared memory (every CTA has the array; rank 0's copy is used)
+    int *rep = nullptr;        // [rep_cap] shared memory, same offset in every CTA: choice of every query (replica mode)
+    int rep_cap = 0;
 };
+__device__ __forceinline__ void dsmem_store(int *local, unsigned rank, int v)
+{
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(dsmem_addr(local, rank)), "r"(v) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // phase 2: the rounds.  All threads of the CTA (of every CTA of the team) call.
@@ -346,13 +361,18 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             for (int k = 0; k < 6; k++)
                 team.team_flags[k] = 0;
     }
+    const bool replica = nranks > 1 && team.rep != nullptr && n_q <= team.rep_cap;
+    int *rep = team.rep;
     for (int j = threadIdx.x; j < n_f; j += blockDim.x)
     {
         const int v = (marks && marks[j]) ? kTaken : kFree;
         cur[j] = v;
-        if (nranks > 1 && j >= home0 && j < home0 + slice)
+        if (nranks > 1 && !replica && j >= home0 && j < home0 + slice)
             home(0)[j - home0] = v; // the first round finds its home slices clean (later ones: cleared a round ahead)
     }
+    if (replica)
+        for (int q = threadIdx.x; q < n_q; q += blockDim.x)
+            rep[q] = -1;
     if (nranks > 1)
         cgr::this_cluster().sync(); // every replica initialised (and every CTA running) before the first remote store
     else
@@ -406,6 +426,12 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
     };
     // `prev` = the query's choice of the previous round (a register copy for the cached queries)
+    // replica mode: a changed choice goes into every CTA's replica (consecutive lanes hold consecutive queries:
+    // one 128-byte store per warp and CTA)
+    auto broadcast_choice = [&](int q, int c) {
+        for (int r = 0; r < nranks; r++)
+            dsmem_store(rep + q, (unsigned)r, c);
+    };
     auto publish_cached = [&](int q, uint32_t b1, uint32_t b2, int &my_count, int &prev) {
         const int c = accept_match(b1, b2, ratio_th, dist_th);
         if (c != prev)
@@ -413,10 +439,13 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             prev = c;
             choice[q] = c;
             s_flag[0] = 1;
+            if (replica)
+                broadcast_choice(q, c);
         }
         if (c >= 0)
         {
-            claim(c, q);
+            if (!replica)
+                claim(c, q);
             my_count++;
             if (out_d1)
             {
@@ -431,10 +460,13 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         {
             choice[q] = c;
             s_flag[0] = 1;
+            if (replica)
+                broadcast_choice(q, c);
         }
         if (c >= 0)
         {
-            claim(c, q);
+            if (!replica)
+                claim(c, q);
             my_count++;
             if (out_d1)
             {
@@ -551,7 +583,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         if (nranks == 1)
             for (int j = threadIdx.x; j < n_f; j += blockDim.x)
                 nxt[j] = cur[j] == kTaken ? kTaken : kFree;
-        else
+        else if (!replica)
         {
             home_now = home(rounds);
             int *next_gen = home(rounds + 1);
@@ -577,7 +609,17 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
                 best2(rk4[u], skeys + roff[u], rcnt[u], cur, rq[u], b1, b2);
             else
                 best2(rk4[u], L.keys + (size_t)rq[u] * L.cap, rcnt[u], cur, rq[u], b1, b2);
+            if (rounds == 2 && u == 0)
+            {
+                asm volatile("" ::"r"(b1), "r"(b2));
+                LVT_RDBG(29);
+            }
             publish_cached(rq[u], b1, b2, my_count, rprev[u]);
+            if (rounds == 2 && u == 0)
+            {
+                asm volatile("" ::: "memory");
+                LVT_RDBG(30);
+            }
         }
         // queries beyond the register-resident ones (maps of more than 4 x blockDim points): entries, first
         // chunks and previous choices of four queries are fetched together, so a round pays the L2
@@ -641,6 +683,40 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             nxt = t;
             __syncthreads();
         }
+        else if (replica)
+        {
+            // "somebody changed a choice in this round": slot rounds % 3 of EVERY CTA's flags (a plain store of 1);
+            // slot (rounds + 2) % 3 is cleared locally after the barrier (its last readers: two rounds ago, its next
+            // writers: past the next barrier, which needs this CTA's arrival)
+            cgr::cluster_group cl = cgr::this_cluster();
+            int *flags = team.team_flags;
+            if (threadIdx.x == 0 && s_flag[0])
+                for (int r = 0; r < nranks; r++)
+                    dsmem_store(flags + (rounds % 3), (unsigned)r, 1);
+            if (rounds == 2)
+                LVT_RDBG(27);
+            cl.sync(); // every changed choice of the round is in every replica
+            if (rounds == 2)
+                LVT_RDBG(28);
+            changed = flags[rounds % 3];
+            if (changed)
+            {
+                // the owners of the next round, rebuilt from the replica with local atomics
+                for (int j = threadIdx.x; j < n_f; j += blockDim.x)
+                    if (cur[j] != kTaken)
+                        cur[j] = kFree;
+                if (threadIdx.x == 0)
+                    flags[(rounds + 2) % 3] = 0;
+                __syncthreads();
+                for (int q = threadIdx.x; q < n_q; q += blockDim.x)
+                {
+                    const int c = rep[q];
+                    if (c >= 0)
+                        atomicMin(&cur[c], q);
+                }
+                __syncthreads();
+            }
+        }
         else
         {
             // this CTA's share of the round goes to slot rounds % 3 of rank 0's team_flags.  Rank 0 clears
@@ -679,6 +755,21 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             LVT_RDBG(3 + rounds);
         if (!changed)
             break;
+    }
+    if (replica)
+    {
+        // matches of the pass: the replica holds every query's final choice
+        int mine = 0;
+        for (int q = threadIdx.x; q < n_q; q += blockDim.x)
+            mine += rep[q] >= 0;
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (threadIdx.x == 0)
+            s_flag[1] = 0;
+        __syncthreads();
+        if (lane == 0 && mine)
+            atomicAdd(&s_flag[1], mine);
+        __syncthreads();
+        count = s_flag[1];
     }
     if (nranks > 1)
         cgr::this_cluster().sync(); // rank 0's flags have been read by everybody; no remote access after this

@@ -36,7 +36,7 @@ struct FrameCtl
               // 4 refused: the point stores could overflow in this frame (TrackState::halt), nothing was touched
     int n_matches;
     int inliers;
-    int pad;
+    int map_n_clean; // map points left by clean_untracked_points, which runs next to the pose solver (pose_kernel's second cluster)
     PoseD pred, opt;
     double opt_W[12]; // world->camera of opt, prepared by pose_kernel for the staged-point projection
     lvt_frame_info info;
@@ -223,9 +223,21 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     team.rank = rank;
     team.nranks = nranks;
     team.team_flags = s_team_flags;
-    const int n_owner = 2;
-    uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + n_owner * a.owner_cap);
-    const int key_cap = a.key_cap - (n_owner - 2) * a.owner_cap;
+    uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap);
+    int key_cap = a.key_cap;
+    {
+        // replica of all queries' choices (match.cuh, RoundsTeam): in the second owner array when the map fits there,
+        // else at the end of the key cache; maps beyond that fall back to the home-slice exchange
+        const int need = (a.st->map_n + 3) & ~3;
+        if (need <= a.owner_cap)
+            team.rep = owner_b;
+        else if (need <= key_cap)
+        {
+            key_cap -= need;
+            team.rep = reinterpret_cast<int *>(skeys) + key_cap;
+        }
+        team.rep_cap = team.rep ? need : 0;
+    }
 
     TrackState &S = *a.st;
     FrameCtl &ctl = *a.ctl;
@@ -268,6 +280,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
             ctl.rounds[k] = 0;
         ctl.n_matches = 0;
         ctl.inliers = 0;
+        ctl.map_n_clean = -1;
         ctl.cyc[0] = clock64();
     }
     if (state0 == 3)
@@ -407,7 +420,17 @@ struct PoseArgs
     const TrackState *st; // with ctl: where a frame that skips the solver takes its pose from
     EarlyResult *early;   // pose + state for a blocking caller, in mapped host memory (nullptr: not wanted)
     int early_seq;
+    // the launch's second cluster (blockIdx.x >= kPoseCluster, frames only): clean_untracked_points
+    // (lvt/src/lvt_local_map.cpp:393-413) needs the matches of the frame, not its pose, so the map is culled and
+    // compacted on another SM WHILE the solver runs instead of behind it
+    PointStore map;
+    const FeatDev *feats;
+    int untracked_threshold;
 };
+
+// dynamic shared memory of pose_kernel: the solver's exchange buffers / the culling CTA's staging (4 x 256 points)
+constexpr int kCleanSmemBytes = 4 * kPoseThreads * (4 + 32);
+constexpr int kPoseSmemBytes = (int)sizeof(PoseShared) > kCleanSmemBytes ? (int)sizeof(PoseShared) : kCleanSmemBytes;
 
 __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1) pose_kernel(PoseArgs a)
 {
@@ -415,6 +438,36 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
     extern __shared__ __align__(16) unsigned char pose_smem[];
     PoseShared &s = *reinterpret_cast<PoseShared *>(pose_smem);
     cg::cluster_group cluster = cg::this_cluster();
+    if (blockIdx.x >= kPoseCluster)
+    {
+        // ---- the culling cluster: one CTA works, and only on frames that go on tracking
+        if (cluster.block_rank() != 0 || !a.ctl || a.ctl->mode != 1)
+            return;
+        __shared__ unsigned long long clean_scan[34];
+        const long long t0 = clock64();
+        const FeatDev fl = a.feats[0];
+        const int *cnt = a.map.counter, *midx = a.map.match_idx;
+        uint8_t *matched = fl.matched;
+        const int th = a.untracked_threshold;
+        // a dropped point gives its feature back (:398-404): done where the keep flag is taken
+        const int left = block_compact_points(
+            a.map, a.st->map_n,
+            [cnt, midx, matched, th](int i) {
+                if (cnt[i] < th)
+                    return true;
+                const int mi = midx[i];
+                if (mi >= 0)
+                    matched[mi] = 0;
+                return false;
+            },
+            reinterpret_cast<int *>(clean_scan), reinterpret_cast<int *>(pose_smem));
+        if (threadIdx.x == 0)
+        {
+            a.ctl->map_n_clean = left;
+            a.ctl->rounds[5] = (int)(clock64() - t0);
+        }
+        return;
+    }
     int m = a.m;
     PoseD init = a.init;
     PoseD *out = a.out;
@@ -615,28 +668,9 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         ctl.info.inliers = ctl.inliers;
     }
     __syncthreads();
-    // ---- clean_untracked_points (lvt/src/lvt_local_map.cpp:393-413)
-    const int M = map_n;
-    const int th = tp.untracked_threshold;
-    // a dropped point gives its feature back (:398-404): done where the keep flag is taken (one pass over the counters)
-    long long *cdbg = a.dbg ? a.dbg + 40 : nullptr;
-    if (cdbg && threadIdx.x == 0)
-        cdbg[0] = clock64(), cdbg[6] = ctl.cyc[5];
-    {
-        const int *cnt = a.map.counter, *midx = a.map.match_idx;
-        uint8_t *matched = fl.matched;
-        map_n = block_compact_points(
-            a.map, M,
-            [cnt, midx, matched, th](int i) {
-                if (cnt[i] < th)
-                    return true;
-                const int mi = midx[i];
-                if (mi >= 0)
-                    matched[mi] = 0;
-                return false;
-            },
-            sh.scan, s_owner, cdbg);
-    }
+    // clean_untracked_points (lvt/src/lvt_local_map.cpp:393-413) has run next to the pose solver (pose_kernel's
+    // second cluster): the map is compacted already
+    map_n = ctl.map_n_clean;
     LVT_PHASE(6);
 
     // ---- update_staged_map_points (lvt/src/lvt_local_map.cpp:355-391); stagedcand projected the
@@ -883,7 +917,7 @@ static int ensure_smem()
         LVT_CUDA_TRY(cudaFuncSetAttribute(track_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(match_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         LVT_CUDA_TRY(cudaFuncSetAttribute(row_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        LVT_CUDA_TRY(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoseShared)));
+        LVT_CUDA_TRY(cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseSmemBytes));
         return (int)LVTK_OK;
     });
 }
@@ -937,8 +971,10 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     LVT_TIMED(stream, K_TRACK_A, launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
-                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early, early_seq};
-    LVT_TIMED(stream, K_POSE, launch_chained(pose_kernel, dim3(kPoseCluster), dim3(kPoseThreads), sizeof(PoseShared), stream, pa));
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early, early_seq,
+                map, d_feats, tp.untracked_threshold};
+    // two clusters: the solver and, next to it, the culling of the map
+    LVT_TIMED(stream, K_POSE, launch_chained(pose_kernel, dim3(2 * kPoseCluster), dim3(kPoseThreads), kPoseSmemBytes, stream, pa));
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     if (pa.dbg && std::getenv("LVT_B200_POSEDBG"))
     {
@@ -977,14 +1013,10 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
             cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
             std::fprintf(stderr, "map pass round 2: wipe+sync %lld | evaluate %lld | count+sync %lld | forward flags %lld | cluster barrier %lld | read+rotate %lld\n",
                          h[24] - h[4], h[25] - h[24], h[26] - h[25], h[27] - h[26], h[28] - h[27], h[5] - h[28]);
+            std::fprintf(stderr, "map pass round 2, thread 0: best2 of its first query %lld | publish %lld | rest of evaluate %lld\n", h[29] - h[24],
+                         h[30] - h[29], h[25] - h[30]);
             std::fprintf(stderr, "map pass: n_fast %lld n_slow %lld smem keys %lld sum counts %lld max count %lld from global %lld\n", h[16],
                          h[17], h[18], h[19], h[20], h[21]);
-            {
-                long long c[8];
-                cudaMemcpy(c, a.dbg + 40, sizeof(c), cudaMemcpyDeviceToHost);
-                std::fprintf(stderr, "track_b clean: marks reset %lld | keep flags %lld | scan %lld | xyz %lld | desc %lld | ints+sync %lld cycles\n",
-                             c[0] - c[6], c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4]);
-            }
             std::fprintf(stderr, "map pass: lists %lld | cache+reset %lld | rounds", h[1] - h[0], h[2] - h[1]);
             for (int r = 0; r < 12 && h[3 + r] > h[2] && h[3 + r] < h[15]; r++)
                 std::fprintf(stderr, " %lld", h[3 + r] - (r ? h[2 + r] : h[2]));
@@ -1050,8 +1082,9 @@ int launch_pose_seam(const double *d_xyz, const float2 *d_uv, int m, const PoseD
 {
     if (int rc = ensure_smem())
         return rc;
-    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr, nullptr, nullptr, 0};
-    pose_kernel<<<kPoseCluster, kPoseThreads, sizeof(PoseShared), stream>>>(a);
+    PoseArgs a{nullptr, d_xyz, d_uv, m, init, cam, d_level, d_inlier, d_e2, d_out, d_n_inliers, nullptr, nullptr, nullptr, 0,
+               PointStore{}, nullptr, 0};
+    pose_kernel<<<kPoseCluster, kPoseThreads, kPoseSmemBytes, stream>>>(a);
     LVT_LAUNCH_CHECK(stream, "pose_kernel");
     return LVTK_OK;
 }

@@ -20,13 +20,16 @@ cyc = (C.c_longlong * 8)()
 rnd = (C.c_int * 8)()
 names = ["A.match", "A.bookkeep", "(gap)", "pose", "(gap)", "B.clean", "B.staged+tri"]
 acc = np.zeros(7)
+clean = 0.0
 for i in range(30):
     lib.lib.lvt_debug_phase_cycles(C.c_void_p(vo.h), i, cyc, rnd)
     c = np.array(list(cyc), dtype=np.float64)
     d = np.diff(c[:8])
     acc += d
+    clean += list(rnd)[5]
     if i < 12:
         print(i, "rounds", list(rnd), "tri", infos[i]["triangulated"], "staged", infos[i]["staged_before"], " ".join("%s=%.0fus" % (nm, v / 1965.0) for nm, v in zip(names, d)))
+print("map culling next to the pose solver: %.1f us" % (clean / 30 / 1965.0))
 print("mean us:", " ".join("%s=%.1f" % (nm, v / 30 / 1965.0) for nm, v in zip(names, acc)), "total=%.1f" % (acc.sum() / 30 / 1965.0))
 lib.reset_kernel_times(); lib.set_profiling(True)
 vo.track_pool(20, 20, want_infos=False)
