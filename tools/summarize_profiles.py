@@ -45,7 +45,7 @@ def launches(tag):
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     out = ["# ncu launch list summary (%s)" % tag, "",
-           "`ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 420 python bench.py --steps 2 --warmup 1`",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c <n> python bench.py --steps 2 --warmup 1` (r1: -s 1200 -c 420; r2: -s 400 -c 800, inside the value arm)",
            "(cold-cache, serialised launches: compare SHARES, not absolutes)", "",
            "| kernel | launches | avg us | total us | share |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
