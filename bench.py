@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 from lvt_b200 import capi, configs, synth  # noqa: E402
 
 WORKLOADS = {
-    "kitti": dict(name="kitti_synth", metric="stereo frames/sec at 1242x375", frames_per_step=50,
+    "kitti": dict(name="kitti_synth", metric="stereo frames/sec at 1242x375", frames_per_step=100,
                   workload="config 2: 1242x375 synthetic stereo stream (SURVEY 8d), max_keypoints_per_cell=250 "
                            "(~2000 keypoints/frame), emergent local map"),
     "euroc": dict(name="euroc_synth", metric="stereo frames/sec at 752x480", frames_per_step=20,

@@ -699,9 +699,17 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     c->tp.untracked_threshold = p.untracked_threshold;
     c->tp.staged_threshold = p.staged_threshold;
     c->tp.triangulation_policy = p.triangulation_policy;
-    LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // the tracking chain is the serial part of a frame: its kernels go in front of the (state-free)
+    // extraction of later frames / of the right image whenever an SM frees up
+    int prio_lo = 0, prio_hi = 0;
+    LVT_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (std::getenv("LVT_B200_NO_PRIORITY"))
+        prio_hi = prio_lo;
+    LVT_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+    // xs[0..2]: extraction of the batched engine / of the right image; xs[3]: the left (gray) image of a blocking
+    // call, which is on the way to the pose
     for (int i = 0; i < lvtk_ctx::kXStreams; i++)
-        LVT_CUDA_TRY(cudaStreamCreateWithFlags(&c->xs[i], cudaStreamNonBlocking));
+        LVT_CUDA_TRY(cudaStreamCreateWithPriority(&c->xs[i], cudaStreamNonBlocking, i == 3 ? prio_hi : prio_lo));
     for (int i = 0; i < lvtk_ctx::kSets; i++)
     {
         LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_extracted[i], cudaEventDisableTiming));
@@ -1198,7 +1206,7 @@ struct System
         // the previous frame, which this thread has waited for.
         const int s = c->parity;
         c->parity ^= 1;
-        cudaStream_t xl = c->xs[0], xr = c->xs[1], st = c->stream;
+        cudaStream_t xl = c->xs[3], xr = c->xs[1], st = c->stream;
         FeatDev *feats = c->feats_d + 2 * s;
         const int *slots = c->d_slots + 2 * s;
         host_mark(0);
@@ -1370,7 +1378,7 @@ struct System
         const bool first_frame = state == 1;
         const int s = c->parity;
         c->parity ^= 1;
-        cudaStream_t xl = c->xs[0], xr = c->xs[1], st = c->stream;
+        cudaStream_t xl = c->xs[3], xr = c->xs[1], st = c->stream;
         FeatDev *feats = c->feats_d + 2 * s;
         const int *slots = c->d_slots + 2 * s;
         const size_t npx = (size_t)rows * cols;
@@ -1546,6 +1554,8 @@ struct System
         const int rows = c->params.img_height, cols = c->params.img_width;
         const size_t npx = (size_t)rows * cols;
         const bool fused_index = sensor == 1 && brief_can_index(c->cam);
+        host_mark(0);
+        host_mark(1);
         // timed on the device: first upload / extraction launch .. last result copy
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
         for (int k = 0; k < kSlots; k++)
@@ -1635,9 +1645,11 @@ struct System
         LVT_CUDA_TRY(cudaMemcpyAsync(E.h_results + start, E.d_results + start, sizeof(FrameResult) * (size_t)(n - start),
                                      cudaMemcpyDeviceToHost, c->stream));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[1], c->stream));
+        host_mark(2); // everything is enqueued ([1]: host time of the enqueue loop); from here the host only waits
         LVT_CUDA_TRY(cudaStreamSynchronize(c->stream));
         for (int k = 0; k < kSlots; k++)
             LVT_CUDA_TRY(cudaStreamSynchronize(c->xs[k]));
+        host_mark(3);
         float ms = 0.f;
         LVT_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_batch[0], c->ev_batch[1]));
         c->last_batch_ms += ms;
