@@ -100,6 +100,34 @@ class lvt_system
                                         reinterpret_cast<double(*)[2]>(cr.data()), (int)corners_right.size(), p.R, p.t);
         return p;
     }
+    // a run of consecutive stereo frames the caller already holds (a recorded sequence, a look-ahead buffer):
+    // the same poses as calling track() on each pair in turn, with the upload and feature extraction of later
+    // frames running behind the tracking of earlier ones (lvt_track_batch).  Empty on failure (last_status()).
+    std::vector<lvt_pose_view> track_batch(const std::vector<lvt_image_view> &left, const std::vector<lvt_image_view> &right)
+    {
+        std::vector<lvt_pose_view> out;
+        const size_t n = left.size();
+        if (n == 0 || right.size() != n)
+            return out;
+        std::vector<const unsigned char *> l(n), r(n);
+        for (size_t i = 0; i < n; i++)
+            l[i] = left[i].data, r[i] = right[i].data;
+        std::vector<double> poses(12 * n);
+        if (lvt_track_batch(m_handle, (int)n, l.data(), r.data(), left[0].rows, left[0].cols, poses.data(), nullptr) != 0)
+            return out;
+        out.resize(n);
+        for (size_t i = 0; i < n; i++)
+        {
+            for (int k = 0; k < 9; k++)
+                out[i].R[k / 3][k % 3] = poses[12 * i + k];
+            for (int k = 0; k < 3; k++)
+                out[i].t[k] = poses[12 * i + 9 + k];
+        }
+        return out;
+    }
+    // 0 = the last tracking call succeeded; < 0: LVTK_ERR_* (the reference swallows failures, lvt_c.cpp:63-134)
+    int last_status() const { return lvt_get_last_status(m_handle); }
+
     // examples/euroc/euroc_example.cpp:96-107,142-143 moved behind track()
     bool set_rectification(const lvt_rectify_c *left, const lvt_rectify_c *right)
     {

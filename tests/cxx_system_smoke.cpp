@@ -49,6 +49,11 @@ int main(int argc, char **argv)
                     pose.t[0] * pose.t[0] + pose.t[1] * pose.t[1] + pose.t[2] * pose.t[2] < 1e-6;
     vo->reset();
     const bool reset_ok = vo->get_state() == lvt_system::eState_NOT_INITIALIZED;
+    // the same two frames as a batch: same answer
+    const std::vector<lvt_pose_view> batch = vo->track_batch(std::vector<lvt_image_view>(2, l), std::vector<lvt_image_view>(2, r));
+    if (batch.size() != 2 || vo->last_status() != 0 || batch[0].R[0][0] != 1.0 || batch[1].t[0] != pose.t[0] ||
+        vo->get_state() != lvt_system::eState_TRACKING)
+        return 7;
     lvt_system::destroy(vo);
     return ok && reset_ok ? 0 : 6;
 }
