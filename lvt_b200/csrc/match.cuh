@@ -590,9 +590,12 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             for (int j = threadIdx.x; j < slice && home0 + j < n_f; j += blockDim.x)
                 next_gen[j] = cur[home0 + j] == kTaken ? kTaken : kFree;
         }
-        if (threadIdx.x == 0)
-            s_flag[0] = 0, s_flag[1] = 0;
-        __syncthreads();
+        if (!replica || rounds == 0)
+        {
+            if (threadIdx.x == 0)
+                s_flag[0] = 0, s_flag[1] = 0;
+            __syncthreads();
+        } // replica mode, later rounds: reset behind the rebuild of the owners, whose barrier ends the previous round
         if (rounds == 0)
             LVT_RDBG(2);
         if (rounds == 2)
@@ -664,6 +667,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
         }
         if (rounds == 2)
             LVT_RDBG(25);
+        if (!replica) // (replica mode counts the matches once, at the end)
         {
             // one shared-memory atomic per warp: a thousand threads adding to one address serialise
             const int warp_count = __reduce_add_sync(0xffffffffu, my_count);
@@ -690,9 +694,8 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             // writers: past the next barrier, which needs this CTA's arrival)
             cgr::cluster_group cl = cgr::this_cluster();
             int *flags = team.team_flags;
-            if (threadIdx.x == 0 && s_flag[0])
-                for (int r = 0; r < nranks; r++)
-                    dsmem_store(flags + (rounds % 3), (unsigned)r, 1);
+            if ((int)threadIdx.x < nranks && s_flag[0])
+                dsmem_store(flags + (rounds % 3), threadIdx.x, 1);
             if (rounds == 2)
                 LVT_RDBG(27);
             cl.sync(); // every changed choice of the round is in every replica
@@ -702,11 +705,17 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
             if (changed)
             {
                 // the owners of the next round, rebuilt from the replica with local atomics
-                for (int j = threadIdx.x; j < n_f; j += blockDim.x)
-                    if (cur[j] != kTaken)
-                        cur[j] = kFree;
+                if (marks)
+                {
+                    for (int j = threadIdx.x; j < n_f; j += blockDim.x)
+                        if (cur[j] != kTaken)
+                            cur[j] = kFree;
+                }
+                else // nothing was marked before the pass: a plain fill, 16 bytes per store (cur is 16-byte aligned)
+                    for (int j = 4 * threadIdx.x; j < n_f; j += 4 * blockDim.x)
+                        *reinterpret_cast<int4 *>(cur + j) = make_int4(kFree, kFree, kFree, kFree);
                 if (threadIdx.x == 0)
-                    flags[(rounds + 2) % 3] = 0;
+                    flags[(rounds + 2) % 3] = 0, s_flag[0] = 0, s_flag[1] = 0;
                 __syncthreads();
                 for (int q = threadIdx.x; q < n_q; q += blockDim.x)
                 {
