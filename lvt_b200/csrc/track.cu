@@ -69,9 +69,16 @@ struct TrackShared
     int ctrl[4];
 };
 
+// phase marks: the GPU-wide nanosecond timer (clock64 is per SM: the kernels of a frame run on different SMs)
+__device__ __forceinline__ long long phase_clock()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #define LVT_PHASE(k)                                                                                                  \
     if (threadIdx.x == 0)                                                                                             \
-    a.ctl->cyc[k] = clock64()
+    a.ctl->cyc[k] = phase_clock()
 
 // ---------------------------------------------------------------------------------------------
 // phase 1 of the matchers: candidate keys, one warp per query, the whole GPU
@@ -193,7 +200,7 @@ __device__ void write_result(const TrackArgs &a, TrackState &S, const PoseD &pos
     c.info.staged_after = staged_n;
     a.result->pose = pose;
     a.result->info = c.info;
-    c.cyc[7] = clock64();
+    c.cyc[7] = phase_clock();
     for (int k = 0; k < 8; k++)
         a.result->cycles[k] = c.cyc[k];
     for (int k = 0; k < 8; k++)
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         ctl.n_matches = 0;
         ctl.inliers = 0;
         ctl.map_n_clean = -1;
-        ctl.cyc[0] = clock64();
+        ctl.cyc[0] = phase_clock();
     }
     if (state0 == 3)
     {
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         ctl.info.tracked = n_matches;
         ctl.info.retried_matching = retried;
         ctl.n_matches = n_matches;
-        ctl.cyc[2] = clock64();
+        ctl.cyc[2] = phase_clock();
         if (n_matches < tp.min_matches)
         {
             // lost: return the last pose (lvt/src/lvt_system.cpp:267-272,199-204)
@@ -495,13 +502,13 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
         out = &a.ctl->opt;
         n_inl = &a.ctl->inliers;
         if (cluster.block_rank() == 0 && threadIdx.x == 0)
-            a.ctl->cyc[3] = clock64();
+            a.ctl->cyc[3] = phase_clock();
     }
     cluster_solve_pose(cluster, s, a.xyz, a.uv, m, init, a.cam, a.level, a.e2, a.inlier, out, n_inl, a.dbg,
                        a.ctl ? &a.ctl->rounds[4] : nullptr);
     if (a.ctl && cluster.block_rank() == 0 && threadIdx.x == 0)
     {
-        a.ctl->cyc[4] = clock64();
+        a.ctl->cyc[4] = phase_clock();
         world_to_camera(a.ctl->opt, a.ctl->opt_W);
         if (a.early)
         {

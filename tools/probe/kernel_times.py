@@ -34,4 +34,4 @@ cyc = (C.c_longlong * 8)(); rnd = (C.c_int * 8)()
 lib.lib.lvt_debug_phase_cycles(C.c_void_p(vo.h), -1, cyc, rnd)
 c = list(cyc)
 print("rounds (map, retry, staged, row):", list(rnd), "| track_a: match %.1f us, bookkeeping %.1f us | track_b: clean %.1f us, rest %.1f us" % (
-    (c[1] - c[0]) / 1965.0, (c[2] - c[1]) / 1965.0, (c[6] - c[5]) / 1965.0, (c[7] - c[6]) / 1965.0))
+    (c[1] - c[0]) / 1e3, (c[2] - c[1]) / 1e3, (c[6] - c[5]) / 1e3, (c[7] - c[6]) / 1e3))
