@@ -72,16 +72,63 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of this rank's GPU during the timed regions (B200_PROFILING.md recipe).  Sampled
+    in-process through NVML (two queries every 50 ms); a `nvidia-smi -lms 50` child per rank, as in round 1, costs the
+    ranks of an 8-GPU job 4 % of `value` (measured: the host's enqueue time per frame goes from 22 to 39 us while eight
+    of them poll the driver).  Falls back to nvidia-smi when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.sm, self.smax, self.reasons = [], [], set()
+        self.nvml = self.handle = None
+        self.run = threading.Event()
+        self.quit = False
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = "NVML, 50 ms"
+            threading.Thread(target=self._poll, daemon=True).start()
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        try:
+            self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        while not self.quit:
+            self.run.wait()
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for name, bit in bits:
+                    if r & int(bit):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def start(self):
         self.paused = False
+        if os.environ.get("LVT_BENCH_NO_CLOCKS"):  # A/B aid: does the sampler itself disturb the ranks?
+            return
+        if self.nvml:
+            self.run.set()
+            return
         try:
+            self.source = "nvidia-smi -lms 50"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
@@ -94,7 +141,10 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def pause(self):
-        """end of one timed region: stop sampling, keep the lines"""
+        """end of one timed region: stop sampling, keep the samples"""
+        if self.nvml:
+            self.run.clear()
+            return
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -102,6 +152,12 @@ class ClockSampler:
             self.paused = True
 
     def stop(self):
+        if self.nvml:
+            self.run.clear()
+            self.quit = True
+            self.run.set()
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.smax) if self.smax else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         if not getattr(self, "paused", False):
@@ -121,7 +177,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def make_stream(wl, n_frames, seed):
@@ -371,6 +427,9 @@ def run_b200(args, wl):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    host_t = (C.c_double * 4)()
+    for vo in vos:
+        lib.lib.lvt_debug_host_times(C.c_void_p(vo.h), host_t, 1)  # reset: host time of the timed calls only
     launches0 = lib.launch_count()
     dev_ms = wall_ms = 0.0
     if resident:
@@ -386,6 +445,9 @@ def run_b200(args, wl):
         # stream); several concurrent sequences: the device-side span around all of them
         dev_ms = per_seq_ms[0] if K == 1 else ev0.elapsed_time(ev1)
     launches = lib.launch_count() - launches0
+    lib.lib.lvt_debug_host_times(C.c_void_p(vos[0].h), host_t, 0)
+    host_enqueue_us = max_over_ranks(host_t[1] / max(1, args.steps * fps_step))
+    host_wait_us = max_over_ranks(host_t[2] / max(1, args.steps * fps_step))
     barrier()
     sampler.pause()
     dev_ms = max_over_ranks(dev_ms)
@@ -612,7 +674,9 @@ def run_b200(args, wl):
                                               "summed over steps" if K == 1 else
                                               "CUDA events around the %d concurrent sequences of the rank" % K) +
                                              ", max over ranks; wall clock %.1f ms/step" % (wall_ms / args.steps),
-                                   "frames_per_extraction_launch": "4 (lvt_track_pool / lvt_track_batch group size)"},
+                                   "frames_per_extraction_launch": "4 (lvt_track_pool / lvt_track_batch group size)",
+                                   "host_us_per_frame": {"enqueue": round(host_enqueue_us, 1), "waiting": round(host_wait_us, 1),
+                                                         "note": "host thread of one sequence inside lvt_track_pool, max over ranks"}},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": K * fps_step * imgs_bytes,
                         "d2h_bytes_per_step": K * fps_step * 176,
                         "call": ("lvt_track" if sensor == 1 else "lvt_track_rgbd") + " (reference C ABI), page-locked host buffers, blocking per frame",

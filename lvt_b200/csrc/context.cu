@@ -1560,12 +1560,12 @@ struct System
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
         for (int k = 0; k < kSlots; k++)
             LVT_CUDA_TRY(cudaStreamWaitEvent(c->xs[k], c->ev_batch[0], 0));
-        int gi = 0;
-        for (int g0 = start; g0 < n; g0 += G, gi++)
-        {
-            // group gi: frames g0 .. g0 + gn - 1, extraction stream / workspace / feature sets of slot gi % 3.
-            // Extraction is state-free (lvt_image_features_handler.cpp:196-209): up to three groups are in
-            // flight (uploading, extracting, being tracked); a slot is reused once its frames have been tracked.
+        // group gi: frames g0 .. g0 + gn - 1, extraction stream / workspace / feature sets of slot gi % 3.
+        // Extraction is state-free (lvt_image_features_handler.cpp:196-209): up to three groups are in
+        // flight (uploading, extracting, being tracked); a slot is reused once its frames have been tracked.
+        const int n_groups = (n - start + G - 1) / G;
+        auto enqueue_extraction = [&](int gi) -> int {
+            const int g0 = start + gi * G;
             const int gn = std::min(G, n - g0), slot = gi % kSlots, set0 = slot * G;
             cudaStream_t sx = c->xs[slot];
             if (gi >= kSlots)
@@ -1634,6 +1634,29 @@ struct System
                     if (int rc = launch_rowcand(feats + 2 * k, c->cam, E.row_cand[set0 + k], sx))
                         return rc;
             LVT_CUDA_TRY(cudaEventRecord(E.ev_extracted[slot], sx));
+            return LVTK_OK;
+        };
+        // LVT_B200_EXTRACT_FIRST (measurement aid, batches of at most three groups): all extraction runs to completion
+        // before the first tracking kernel is launched, so the tracking chain is timed with the GPU to itself
+        static const bool extract_first = std::getenv("LVT_B200_EXTRACT_FIRST") != nullptr;
+        const bool alone = extract_first && n_groups <= kSlots;
+        if (alone)
+        {
+            for (int gi = 0; gi < n_groups; gi++)
+                if (int rc = enqueue_extraction(gi))
+                    return rc;
+            LVT_CUDA_TRY(cudaDeviceSynchronize());
+            LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
+        }
+        for (int gi = 0; gi < n_groups; gi++)
+        {
+            const int g0 = start + gi * G;
+            const int gn = std::min(G, n - g0), slot = gi % kSlots, set0 = slot * G;
+            if (!alone)
+                if (int rc = enqueue_extraction(gi))
+                    return rc;
+            FeatDev *feats = E.feats_d + per * set0;
+            const FeatDev *feats_h = E.feats_h.data() + per * set0;
             // tracking: strictly in order on the tracking stream
             LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, E.ev_extracted[slot], 0));
             for (int k = 0; k < gn; k++)

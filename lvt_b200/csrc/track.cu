@@ -540,6 +540,8 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
     {
         const int np = block_row_match(a.row_cand, fl, nl, fr, nr, tp.cam, a.sc.row_choice, a.sc.ms.items, owner_a,
                                        owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3], skeys, a.key_cap);
+        if (threadIdx.x == 0)
+            a.ctl->rounds[7] = (int)(phase_clock() - a.ctl->cyc[5]); // ns into track_b: row matching done
         if (np == 0)
             return 0;
         if (threadIdx.x == 0)
@@ -740,6 +742,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
     // ---- need_new_triangulation (lvt/src/lvt_system.cpp:308-334)
     if (threadIdx.x == 0)
     {
+        ctl.rounds[6] = (int)(phase_clock() - ctl.cyc[5]); // ns into track_b: staged points done
         int need;
         if (tp.triangulation_policy == 2)
             need = 1;

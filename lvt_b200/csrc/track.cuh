@@ -54,7 +54,9 @@ struct FrameResult
     lvt_frame_info info;
     long long cycles[8]; // clock64() at the phase boundaries of the tracking kernel (profiling aid)
     int rounds[8];       // fixed-point rounds: map pass, retry pass, staged pass, row matching; [4] = evaluations of the
-                         // pose solver (passes over the correspondences: linearisations + LM trials), [5..7] spare
+                         // pose solver (passes over the correspondences: linearisations + LM trials), [5] = clock cycles of
+                         // the map culling next to the solver, [6] / [7] = ns into track_b when the staged points / the
+                         // row matching were done (profiling aids)
     long long dbg[8];    // clock64() marks inside the map pass (profiling aid)
 };
 

@@ -14,8 +14,9 @@ vo.pool_reserve(n)
 for t in range(n):
     vo.pool_upload(t, *st.frame(t))
 vo.track_pool(0, 10)
-poses, infos = vo.track_pool(10, 30)
-print("batch ms", vo.last_batch_ms(), "per frame", vo.last_batch_ms() / 30)
+NN = int(os.environ.get("PROBE_N", "30"))
+poses, infos = vo.track_pool(10, NN)
+print("batch ms", vo.last_batch_ms(), "per frame", vo.last_batch_ms() / NN)
 cyc = (C.c_longlong * 8)()
 rnd = (C.c_int * 8)()
 names = ["A.match", "A.bookkeep", "(gap)", "pose", "(gap)", "B.clean", "B.staged+tri"]  # phase marks: GPU-wide ns timer
@@ -23,7 +24,7 @@ prev_end = None
 gaps = []
 acc = np.zeros(7)
 clean = 0.0
-for i in range(30):
+for i in range(NN):
     lib.lib.lvt_debug_phase_cycles(C.c_void_p(vo.h), i, cyc, rnd)
     c = np.array(list(cyc), dtype=np.float64)
     d = np.diff(c[:8])
@@ -34,9 +35,9 @@ for i in range(30):
     clean += list(rnd)[5]
     if i < 12:
         print(i, "rounds", list(rnd), "tri", infos[i]["triangulated"], "staged", infos[i]["staged_before"], " ".join("%s=%.0fus" % (nm, v / 1e3) for nm, v in zip(names, d)))
-print("map culling next to the pose solver: %.1f us (cycles / 1965)" % (clean / 30 / 1965.0))
+print("map culling next to the pose solver: %.1f us (cycles / 1965)" % (clean / NN / 1965.0))
 print("frame end -> next frame's track_a start: mean %.1f us" % (np.mean(gaps) if gaps else 0.0))
-print("mean us:", " ".join("%s=%.1f" % (nm, v / 30 / 1e3) for nm, v in zip(names, acc)), "total=%.1f" % (acc.sum() / 30 / 1e3))
+print("mean us:", " ".join("%s=%.1f" % (nm, v / NN / 1e3) for nm, v in zip(names, acc)), "total=%.1f" % (acc.sum() / NN / 1e3))
 lib.reset_kernel_times(); lib.set_profiling(True)
 vo.track_pool(20, 20, want_infos=False)
 lib.set_profiling(False)
