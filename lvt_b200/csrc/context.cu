@@ -2115,6 +2115,19 @@ LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int
     std::memcpy(rounds, r.rounds, sizeof(r.rounds));
     return 0;
 }
+/* profiling aid: nanosecond marks inside track_b of pool frame i of the last batch (i < 0: the last blocking call):
+ * [0] start, [1] staged rounds, [2] promotion, [3] staged compaction, [4] row matching, [5] triangulation,
+ * [6] new points appended, [7] state + prediction written; 0 = phase not run */
+LVT_API int lvt_debug_frame_marks(lvt_handle h, int i, long long marks[8])
+{
+    System *vo = static_cast<System *>(h);
+    if (!vo)
+        return -1;
+    vo->finish_pending();
+    const FrameResult &r = i < 0 ? *vo->ctx->h_result : vo->ctx->eng.h_results[i];
+    std::memcpy(marks, r.dbg, sizeof(r.dbg));
+    return 0;
+}
 /* profiling aid: host time of the blocking calls since the last reset, microseconds:
  * out[0] staging + H2D enqueue, out[1] kernel enqueue, out[2] waiting for the device, out[3] calls */
 LVT_API int lvt_debug_host_times(lvt_handle h, double out[4], int reset)

@@ -406,7 +406,7 @@ __device__ bool nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
 //   * component reaches the window's outer ring     -> labels may be incomplete: nms_resolve
 // The propagation is a few dozen shared-memory sweeps over the corner list; the sequential flood
 // of nms_resolve is left for ties and for components that leave the window.
-constexpr int kNmsTile = 32, kNmsHalo = 16, kNmsWin = kNmsTile + 2 * kNmsHalo;
+constexpr int kNmsTile = 48, kNmsHalo = 8, kNmsWin = kNmsTile + 2 * kNmsHalo;
 constexpr uint32_t kNmsOpen = 0xFFFFFFFFu; // label of a corner on the window's ring
 constexpr int kNmsSlowCap = 256;           // per CTA: components with a shared maximum / open-label candidates;
                                            // beyond that the detection tile is redone sequentially

@@ -79,6 +79,10 @@ __device__ __forceinline__ long long phase_clock()
 #define LVT_PHASE(k)                                                                                                  \
     if (threadIdx.x == 0)                                                                                             \
     a.ctl->cyc[k] = phase_clock()
+// finer marks inside track_b (FrameResult::dbg, read back by lvt_debug_frame_marks)
+#define LVT_BMARK(k)                                                                                                  \
+    if (threadIdx.x == 0)                                                                                             \
+    a.result->dbg[k] = phase_clock()
 
 // ---------------------------------------------------------------------------------------------
 // phase 1 of the matchers: candidate keys, one warp per query, the whole GPU
@@ -542,6 +546,7 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
                                        owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3], skeys, a.key_cap);
         if (threadIdx.x == 0)
             a.ctl->rounds[7] = (int)(phase_clock() - a.ctl->cyc[5]); // ns into track_b: row matching done
+        LVT_BMARK(4);
         if (np == 0)
             return 0;
         if (threadIdx.x == 0)
@@ -562,6 +567,7 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
             a.sc.tri_ok[k] = ok;
         }
         __syncthreads();
+        LVT_BMARK(5);
         for (int k0 = 0; k0 < np; k0 += blockDim.x)
         {
             const int k = k0 + threadIdx.x;
@@ -639,6 +645,12 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
     __syncthreads();
     LVT_PHASE(5);
     if (threadIdx.x == 0)
+    {
+        for (int k = 0; k < 8; k++)
+            a.result->dbg[k] = 0;
+        a.result->dbg[0] = phase_clock();
+    }
+    if (threadIdx.x == 0)
         ctl.info.n_features_right = nr;
     if (mode == 3)
     {
@@ -691,6 +703,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         block_match_projected(a.sc.map_cand, a.staged.desc, a.sc.ms, Sn, fl, nl, tp.cam, (float)(R * R), true, owner_a,
                               owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[2], nullptr,
                               reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap), a.key_cap);
+        LVT_BMARK(1);
         for (int j = threadIdx.x; j < nl; j += blockDim.x)
             if (owner_a[j] != kFree)
                 fl.matched[j] = 1;
@@ -736,8 +749,10 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
                 *a.error = S.error = LVTK_ERR_CAPACITY;
             map_n = a.map.cap;
         }
+        LVT_BMARK(2);
         staged_n = block_compact_points(a.staged, Sn, [flag](int i) { return flag[i] == 1; }, sh.scan, s_owner);
     }
+    LVT_BMARK(3);
 
     // ---- need_new_triangulation (lvt/src/lvt_system.cpp:308-334)
     if (threadIdx.x == 0)
@@ -769,12 +784,14 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         }
     }
     __syncthreads();
+    LVT_BMARK(6);
     if (threadIdx.x == 0)
     {
         S.map_n = map_n;
         S.staged_n = staged_n;
         S.last_pose = sh.pose;
         prepare_prediction(S);
+        a.result->dbg[7] = phase_clock();
         write_result(a, S, sh.pose, 2, map_n, staged_n);
     }
 }

@@ -21,7 +21,7 @@ if stats_lib:
         vo.track(*frames[t])
     tr = np.zeros((4096, 12), dtype=np.int64)
     lib.lib.lvt_debug_nms_trace(tr.ctypes.data_as(C.c_void_p))
-    nx, ny = (p.img_width + 31) // 32, (p.img_height + 31) // 32
+    nx, ny = (p.img_width + 47) // 48, (p.img_height + 47) // 48  # kNmsTile
     tr = tr[: nx * ny * 2]
     mhz = 1965.0
     t0 = tr[:, 0].min()

@@ -35,6 +35,17 @@ for i in range(NN):
     clean += list(rnd)[5]
     if i < 12:
         print(i, "rounds", list(rnd), "tri", infos[i]["triangulated"], "staged", infos[i]["staged_before"], " ".join("%s=%.0fus" % (nm, v / 1e3) for nm, v in zip(names, d)))
+bm = (C.c_longlong * 8)()
+bn = ["staged rounds", "promotion", "staged compaction", "row matching", "triangulation", "append", "state+prediction"]
+print("track_b phases (us since the previous mark; - = not run):")
+for i in range(12):
+    lib.lib.lvt_debug_frame_marks(C.c_void_p(vo.h), i, bm)
+    m = list(bm)
+    prev, parts = m[0], []
+    for k in range(1, 8):
+        if m[k] > 0:
+            parts.append("%s=%.1f" % (bn[k - 1], (m[k] - prev) / 1e3)); prev = m[k]
+    print("  ", i, " ".join(parts))
 print("map culling next to the pose solver: %.1f us (cycles / 1965)" % (clean / NN / 1965.0))
 print("frame end -> next frame's track_a start: mean %.1f us" % (np.mean(gaps) if gaps else 0.0))
 print("mean us:", " ".join("%s=%.1f" % (nm, v / NN / 1e3) for nm, v in zip(names, acc)), "total=%.1f" % (acc.sum() / NN / 1e3))
