@@ -373,10 +373,12 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
     if (replica)
         for (int q = threadIdx.x; q < n_q; q += blockDim.x)
             rep[q] = -1;
+    LVT_RDBG(22);
     if (nranks > 1)
         cgr::this_cluster().sync(); // every replica initialised (and every CTA running) before the first remote store
     else
         __syncthreads();
+    LVT_RDBG(23);
     // work lists, built once: queries served from their key list / by a warp re-scan (order is irrelevant)
     // (warp-aggregated appends: one shared-memory atomic per warp and list)
     for (int j0 = 0; j0 < n_loc; j0 += blockDim.x)
@@ -530,6 +532,7 @@ __device__ inline int block_rounds(const CandLists &L, int n_q, int n_f, Active 
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * k), "l"(src + k) : "memory");
         }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    LVT_RDBG(31);
     if (dbg)
     {
         int sum = 0, mx = max_cnt, nglob = 0;
@@ -824,7 +827,7 @@ __device__ inline int block_match_projected(const CandLists &L, const uint32_t *
 __device__ inline int block_row_match(const CandLists &L, const FeatDev &fl, int nl, const FeatDev &fr, int nr,
                                       const CamParams &cam, int *choice, int *items, int *owner_a, int *owner_b,
                                       int *s_flag, int *s_scan, int *out_query, int *out_train, int *rounds_out,
-                                      uint32_t *skeys = nullptr, int skey_cap = 0)
+                                      uint32_t *skeys = nullptr, int skey_cap = 0, long long *dbg = nullptr)
 {
     const int lane = threadIdx.x & 31;
     auto active = [&](int q) { return fl.matched[q] == 0; }; // tracked from the map this frame: skipped (handler.cpp:307-310)
@@ -839,7 +842,7 @@ __device__ inline int block_row_match(const CandLists &L, const FeatDev &fl, int
         warp_top2(k1, k2, b1, b2);
     };
     block_rounds(L, nl, nr, active, slow, cam.triangulation_ratio_th, cam.desc_dist_th, fr.matched, choice, items,
-                 owner_a, owner_b, s_flag, nullptr, nullptr, rounds_out, nullptr, skeys, skey_cap);
+                 owner_a, owner_b, s_flag, nullptr, nullptr, rounds_out, dbg, skeys, skey_cap);
     for (int j = threadIdx.x; j < nr; j += blockDim.x)
         if (owner_a[j] != kFree)
             fr.matched[j] = 1;

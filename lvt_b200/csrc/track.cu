@@ -543,7 +543,8 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
     if (tp.sensor == 1)
     {
         const int np = block_row_match(a.row_cand, fl, nl, fr, nr, tp.cam, a.sc.row_choice, a.sc.ms.items, owner_a,
-                                       owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3], skeys, a.key_cap);
+                                       owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3], skeys, a.key_cap,
+                                       a.dbg ? a.dbg + 60000 : nullptr); // (debug builds of the launch: far behind the triangulated points)
         if (threadIdx.x == 0)
             a.ctl->rounds[7] = (int)(phase_clock() - a.ctl->cyc[5]); // ns into track_b: row matching done
         LVT_BMARK(4);
@@ -1044,10 +1045,23 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
                          h[30] - h[29], h[25] - h[30]);
             std::fprintf(stderr, "map pass: n_fast %lld n_slow %lld smem keys %lld sum counts %lld max count %lld from global %lld\n", h[16],
                          h[17], h[18], h[19], h[20], h[21]);
+            std::fprintf(stderr, "map pass set-up: owners+replica %lld | first cluster barrier %lld | work lists %lld | lists into shared memory %lld | "
+                                 "(trace) + flags + barrier %lld\n", h[22] - h[0], h[23] - h[22], h[1] - h[23], h[31] - h[1], h[2] - h[31]);
             std::fprintf(stderr, "map pass: lists %lld | cache+reset %lld | rounds", h[1] - h[0], h[2] - h[1]);
             for (int r = 0; r < 12 && h[3 + r] > h[2] && h[3 + r] < h[15]; r++)
                 std::fprintf(stderr, " %lld", h[3 + r] - (r ? h[2 + r] : h[2]));
             std::fprintf(stderr, " | total %lld cycles\n", h[15] - h[0]);
+            // the row-matching pass of the frame before (track_b, single CTA): same marks, second half of the buffer
+            cudaMemcpy(h, a.dbg + 60000, sizeof(h), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "row pass (previous frame that triangulated): n_fast %lld n_slow %lld smem keys %lld sum counts %lld max count %lld | lists %lld | cache+reset %lld | rounds",
+                         h[16], h[17], h[18], h[19], h[20], h[1] - h[0], h[2] - h[1]);
+            for (int r = 0; r < 12 && h[3 + r] > h[2] && h[3 + r] < h[15]; r++)
+                std::fprintf(stderr, " %lld", h[3 + r] - (r ? h[2 + r] : h[2]));
+            std::fprintf(stderr, " | total %lld cycles\n", h[15] - h[0]);
+            std::fprintf(stderr, "row pass set-up: owners %lld | barrier %lld | work lists %lld | lists into shared memory %lld | (trace) + flags + barrier %lld\n",
+                         h[22] - h[0], h[23] - h[22], h[1] - h[23], h[31] - h[1], h[2] - h[31]);
+            std::fprintf(stderr, "row pass round 2: wipe+sync %lld | evaluate %lld | count+sync %lld | swap+sync %lld\n", h[24] - h[4], h[25] - h[24],
+                         h[26] - h[25], h[5] - h[26]);
         }
     }
     }
