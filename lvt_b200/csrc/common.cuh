@@ -44,6 +44,9 @@ enum KernelId
     K_STAGEDCAND,
     K_TRACK_B,
     K_RECTIFY,
+    K_TRACK_A_EARLY, // track_a_kernel, early part of the map pass (batched engine)
+    K_MAPCAND_EARLY, // mapcand_kernel for the coming frame, behind the pose
+    K_TAILCAND,      // mapcand_kernel over the points track_b appended
     K_COUNT
 };
 // Function attributes (opt-in shared memory) are per device and per process: every launcher sets

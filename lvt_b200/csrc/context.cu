@@ -410,7 +410,11 @@ struct lvtk_ctx
     PoseD *d_pose_out = nullptr;
     // tracking
     TrackState *d_state = nullptr;
-    uint8_t *d_ctl = nullptr; // FrameCtl: hand-over between the kernels of the tracking chain
+    uint8_t *d_ctl = nullptr; // 2 x FrameCtl: hand-over between the kernels of the tracking chain; frames alternate, so
+                              // that a frame's early parts read the previous frame's block while that frame's map
+                              // maintenance is still using it (ctl_idx: the block of the frame launched last)
+    int ctl_idx = 0;
+    cudaEvent_t ev_pose_done[2] = {}, ev_rest_done[2] = {}; // batched engine: TrackOverlap events, by frame parity
     FrameResult *d_result = nullptr, *h_result = nullptr;
     int *h_error = nullptr; // pinned copy of ws.error, fetched together with the result
     EarlyResult *h_early = nullptr, *d_early = nullptr; // pose + state in mapped pinned memory (d_early: its device
@@ -476,10 +480,18 @@ struct lvtk_ctx
 
 // one frame's tracking kernels (parts: 1 up to the pose, 2 the rest, 3 both) on `st`
 static int ctx_launch_track(lvtk_ctx *c, FrameResult *result, const FeatDev *feats, const CandLists &row_cand, cudaStream_t st,
-                            cudaEvent_t right_ready = nullptr, int parts = 3, EarlyResult *early = nullptr, int early_seq = 0)
+                            cudaEvent_t right_ready = nullptr, int parts = 3, EarlyResult *early = nullptr, int early_seq = 0,
+                            int overlap = 0 /* 0 none, 1 the rest on the side stream, 2 + early map pass */,
+                            const FeatDev *next_feats = nullptr /* overlap: the next frame's left features (device), if extracted */)
 {
-    return launch_track_frame(c->d_state, c->d_ctl, result, c->map, c->staged, feats, c->tp, c->sc, row_cand, c->tcfg,
-                              c->ws.error, st, right_ready, parts, early, early_seq);
+    if (parts & 1)
+        c->ctl_idx ^= 1; // a new frame (parts == 2 finishes the frame launched with parts == 1)
+    const size_t cb = (frame_ctl_bytes() + 255) & ~(size_t)255;
+    uint8_t *ctl = c->d_ctl + cb * (size_t)c->ctl_idx, *ctl_prev = c->d_ctl + cb * (size_t)(c->ctl_idx ^ 1);
+    TrackOverlap ov{c->xs[3], c->ev_pose_done[c->ctl_idx], c->ev_rest_done[c->ctl_idx], c->ev_rest_done[c->ctl_idx ^ 1], overlap == 2,
+                    next_feats};
+    return launch_track_frame(c->d_state, ctl, result, c->map, c->staged, feats, c->tp, c->sc, row_cand, c->tcfg, c->ws.error, st,
+                              right_ready, parts, early, early_seq, overlap ? &ov : nullptr, ctl_prev);
 }
 
 // The reference's map and staged-point vectors grow without bound (lvt/src/lvt_local_map.cpp:331-353).
@@ -518,6 +530,12 @@ static int ctx_grow_points(lvtk_ctx *c)
     rc = rc ? rc : A.regrow(&c->sc.e2, 0, n);
     rc = rc ? rc : A.regrow(&c->sc.map_cand.keys, 0, n * kMapCandCap);
     rc = rc ? rc : A.regrow(&c->sc.map_cand.count, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.bs.proj, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.bs.vis, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.bs.choice, 0, n);
+    rc = rc ? rc : A.regrow(&c->sc.bs.items, 0, 2 * n + 1024);
+    rc = rc ? rc : A.regrow(&c->sc.staged_cand.keys, 0, n * kMapCandCap);
+    rc = rc ? rc : A.regrow(&c->sc.staged_cand.count, 0, n);
     if (rc)
         return rc;
     c->pcap = (int)n;
@@ -720,6 +738,11 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming));
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_right, cudaEventDisableTiming));
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pose, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++)
+    {
+        LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pose_done[k], cudaEventDisableTiming));
+        LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_rest_done[k], cudaEventDisableTiming));
+    }
     LVT_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_frame, cudaEventDisableTiming));
 
     if (int rc = make_image_pool(&c->pool, c->arena, p.img_height, p.img_width, n_slots))
@@ -779,7 +802,7 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->d_f_b, (size_t)c->in_cap);
     rc = rc ? rc : c->arena.alloc(&c->d_pose_out, 1);
     rc = rc ? rc : c->arena.alloc(&c->d_state, 1);
-    rc = rc ? rc : c->arena.alloc(&c->d_ctl, frame_ctl_bytes());
+    rc = rc ? rc : c->arena.alloc(&c->d_ctl, 2 * ((frame_ctl_bytes() + 255) & ~(size_t)255));
     rc = rc ? rc : c->arena.alloc(&c->d_result, 1);
     rc = rc ? rc : make_points(&c->map, c->arena, c->pcap);
     rc = rc ? rc : make_points(&c->staged, c->arena, c->pcap);
@@ -795,6 +818,13 @@ static int ctx_build(lvtk_ctx *c, const lvt_params_c &p, int device, int n_slots
     rc = rc ? rc : c->arena.alloc(&c->sc.map_cand.keys, (size_t)c->pcap * kMapCandCap);
     rc = rc ? rc : c->arena.alloc(&c->sc.map_cand.count, (size_t)c->pcap);
     c->sc.map_cand.cap = kMapCandCap;
+    rc = rc ? rc : c->arena.alloc(&c->sc.bs.proj, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.bs.vis, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.bs.choice, (size_t)c->pcap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.bs.items, (size_t)2 * c->pcap + 1024);
+    rc = rc ? rc : c->arena.alloc(&c->sc.staged_cand.keys, (size_t)c->pcap * kMapCandCap);
+    rc = rc ? rc : c->arena.alloc(&c->sc.staged_cand.count, (size_t)c->pcap);
+    c->sc.staged_cand.cap = kMapCandCap;
     for (int i = 0; i < lvtk_ctx::kSets; i++)
     {
         rc = rc ? rc : c->arena.alloc(&c->row_cand[i].keys, (size_t)c->fcap * kRowCandCap);
@@ -884,6 +914,13 @@ static void ctx_free(lvtk_ctx *c)
         cudaEventDestroy(c->ev_right);
     if (c->ev_pose)
         cudaEventDestroy(c->ev_pose);
+    for (int k = 0; k < 2; k++)
+    {
+        if (c->ev_pose_done[k])
+            cudaEventDestroy(c->ev_pose_done[k]);
+        if (c->ev_rest_done[k])
+            cudaEventDestroy(c->ev_rest_done[k]);
+    }
     if (c->ev_frame)
         cudaEventDestroy(c->ev_frame);
     if (c->ev_caller_read)
@@ -1638,6 +1675,7 @@ struct System
         };
         // LVT_B200_EXTRACT_FIRST (measurement aid, batches of at most three groups): all extraction runs to completion
         // before the first tracking kernel is launched, so the tracking chain is timed with the GPU to itself
+        static const bool overlap_on = !std::getenv("LVT_B200_NO_OVERLAP"); // A/B aid: the whole chain on one stream
         static const bool extract_first = std::getenv("LVT_B200_EXTRACT_FIRST") != nullptr;
         const bool alone = extract_first && n_groups <= kSlots;
         if (alone)
@@ -1648,23 +1686,46 @@ struct System
             LVT_CUDA_TRY(cudaDeviceSynchronize());
             LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[0], c->stream));
         }
+        else if (int rc = enqueue_extraction(0))
+            return rc;
         for (int gi = 0; gi < n_groups; gi++)
         {
             const int g0 = start + gi * G;
             const int gn = std::min(G, n - g0), slot = gi % kSlots, set0 = slot * G;
-            if (!alone)
-                if (int rc = enqueue_extraction(gi))
+            // one group ahead: the last frame of this group lists the points it appends for the next group's first
+            // frame, so that group's extraction is enqueued before this group's tracking
+            const bool more = gi + 1 < n_groups;
+            if (!alone && more)
+                if (int rc = enqueue_extraction(gi + 1))
                     return rc;
             FeatDev *feats = E.feats_d + per * set0;
             const FeatDev *feats_h = E.feats_h.data() + per * set0;
-            // tracking: strictly in order on the tracking stream
+            // tracking: strictly in order on the tracking stream; a frame's map maintenance (stagedcand + track_b) goes
+            // to the side stream, and from the second frame of the call on the map pass starts early, next to the
+            // previous frame's map maintenance (TrackOverlap, track_a_kernel)
             LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, E.ev_extracted[slot], 0));
             for (int k = 0; k < gn; k++)
-                if (int rc = ctx_launch_track(c, E.d_results + (g0 + k), feats + per * k, E.row_cand[set0 + k], c->stream))
+            {
+                const int overlap = !overlap_on ? 0 : (g0 + k > start ? 2 : 1);
+                const FeatDev *next = nullptr;
+                if (overlap && k + 1 < gn)
+                    next = feats + per * (k + 1);
+                else if (overlap && more)
+                {
+                    const int nslot = (gi + 1) % kSlots;
+                    LVT_CUDA_TRY(cudaStreamWaitEvent(c->xs[3], E.ev_extracted[nslot], 0));
+                    next = E.feats_d + per * (nslot * G);
+                }
+                if (int rc = ctx_launch_track(c, E.d_results + (g0 + k), feats + per * k, E.row_cand[set0 + k], c->stream, nullptr, 3,
+                                              nullptr, 0, overlap, next))
                     return rc;
-            LVT_CUDA_TRY(cudaEventRecord(E.ev_tracked[slot], c->stream));
+            }
+            // the group's feature sets are free once the map maintenance of its last frame is through
+            LVT_CUDA_TRY(cudaEventRecord(E.ev_tracked[slot], overlap_on ? c->xs[3] : c->stream));
             c->last_feats_h = feats_h + per * (gn - 1);
         }
+        if (overlap_on) // the results are complete behind the last frame's track_b
+            LVT_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_rest_done[c->ctl_idx], 0));
         LVT_CUDA_TRY(cudaMemcpyAsync(E.h_results + start, E.d_results + start, sizeof(FrameResult) * (size_t)(n - start),
                                      cudaMemcpyDeviceToHost, c->stream));
         LVT_CUDA_TRY(cudaEventRecord(c->ev_batch[1], c->stream));
@@ -2180,7 +2241,8 @@ LVT_API const char *lvt_kernel_name(int id)
     static const char *names[K_COUNT] = {"score_kernel",   "nms_tile_kernel", "tile_kernel",    "gather_kernel",
                                          "brief_kernel",   "index_kernel",    "track_a_kernel", "mapcand_kernel",
                                          "rowcand_kernel", "pose_kernel",     "stagedcand_kernel", "track_b_kernel",
-                                         "rectify_kernel"};
+                                         "rectify_kernel", "track_a_kernel[early part]", "mapcand_kernel[early]",
+                                         "mapcand_kernel[appended points]"};
     return id >= 0 && id < K_COUNT ? names[id] : "";
 }
 

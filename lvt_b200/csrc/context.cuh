@@ -13,7 +13,8 @@ int track_configure(int owner_cap, TrackLaunchCfg *cfg);
 int launch_track_frame(TrackState *st, void *ctl, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
                        const TrackLaunchCfg &cfg, int *d_error, cudaStream_t stream, cudaEvent_t right_ready = nullptr,
-                       int parts = 3, EarlyResult *early = nullptr, int early_seq = 0);
+                       int parts = 3, EarlyResult *early = nullptr, int early_seq = 0, const TrackOverlap *ov = nullptr,
+                       const void *ctl_prev = nullptr /* FrameCtl of the frame launched before this one */);
 int launch_clear_halt(TrackState *st, cudaStream_t stream);
 size_t frame_ctl_bytes();
 int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists &L, cudaStream_t stream);

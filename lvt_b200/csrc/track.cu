@@ -42,6 +42,15 @@ struct FrameCtl
     lvt_frame_info info;
     long long cyc[8];
     int rounds[8]; // as FrameResult::rounds
+    // the early part of the map pass (track_a_kernel part 1, batched engine): map points it matched (0: it did not
+    // run), their matches, its rounds
+    int a1_m, a1_count, a1_rounds;
+    // what the motion model predicts for the NEXT frame from this frame's pose (pose_kernel, once per frame, as soon as
+    // the pose is known): the next frame's candidate listing and track_a take it from here instead of each running
+    // the same slerp again -- lvt_motion_model::predict_next_pose on the state track_a left
+    PoseD next_pred;
+    MotionState next_motion;
+    double next_W[12];
 };
 
 struct TrackArgs
@@ -58,6 +67,8 @@ struct TrackArgs
     int key_cap;        // candidate keys that fit behind the two owner arrays
     long long *dbg;     // clock64() trace of the map pass (LVT_B200_SYNC builds of the launch only)
     int *error;         // the context's sticky error flag (the one the host fetches with every result)
+    const FrameCtl *ctl_prev; // the previous frame's hand-over block (the early parts read its mode / pose / culled map size)
+    int part;                 // track_a_kernel: 0 the whole map pass, 1 its early part, 2 the rest (see there)
 };
 
 struct TrackShared
@@ -89,9 +100,11 @@ __device__ __forceinline__ long long phase_clock()
 // ---------------------------------------------------------------------------------------------
 struct MapCandArgs
 {
-    const TrackState *st; // nullptr: explicit pose / m (seam)
+    TrackState *st; // nullptr: explicit pose / m (seam)
     const FrameCtl *ctl;
-    int which;            // 0: map points under the predicted pose, 1: staged points under ctl->opt
+    int which;            // 0: map points under the predicted pose, 1: staged points under ctl->opt,
+                          // 2: map points for the coming frame, EARLY (see below), 3: the points track_b appended,
+                          //    for the coming frame
     int staged_threshold;
     PoseD pose;
     int m;
@@ -99,23 +112,84 @@ struct MapCandArgs
     const uint32_t *desc;
     const FeatDev *feat;
     CamParams cam;
-    MatchScratch ms;
+    float2 *proj;
+    uint8_t *vis;
     CandLists L;
+    const FrameCtl *ctl_prev; // which == 2
 };
 
+// one warp (all lanes call): is_point_visible + the sorted candidate keys of map / staged point q
+__device__ __forceinline__ void warp_list_candidates(int q, const double *W /* smem, 12 */, const CamParams &cam, float r2,
+                                                     const double *xyz, const uint32_t *desc, const FeatDev &f, float2 *proj,
+                                                     uint8_t *vis, const CandLists &L, uint32_t *buf /* smem, kMapCandCap */,
+                                                     int lane, int slot = -1 /* row of L; default: q */)
+{
+    if (slot < 0)
+        slot = q;
+    double u, v;
+    const bool ok = point_visible(W, cam, xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2], &u, &v);
+    const float2 p = ok ? make_float2((float)u, (float)v) : make_float2(0.f, 0.f);
+    if (lane == 0)
+    {
+        vis[q] = ok;
+        proj[q] = p;
+    }
+    int n = 0;
+    if (ok)
+    {
+        const uint4 q0 = *reinterpret_cast<const uint4 *>(desc + 8 * (size_t)q);
+        const uint4 q1 = *reinterpret_cast<const uint4 *>(desc + 8 * (size_t)q + 4);
+        WarpCollector col{buf, kMapCandCap, 0, lane};
+        scan_projected_window(f, cam, p, r2, q0, q1, lane, col);
+        n = col.n;
+        if (n <= kMapCandCap)
+            warp_sort_store<kMapCandCap / 32>(buf, n, L.keys + (size_t)slot * kMapCandCap, lane);
+    }
+    if (lane == 0)
+        L.count[slot] = n;
+}
+
+// which == 2, the batched engine: the map pass of the COMING frame is listed as soon as the previous frame's pose
+// is known -- its features are extracted, the pose it is predicted from (ctl_prev->opt) and the culled map
+// (ctl_prev->map_n_clean points; pose_kernel's second cluster) are final -- while that frame's map maintenance
+// (track_b_kernel, another stream) is still running.  Nothing that track_b writes is read here; what it appends
+// to the map is listed by track_a_kernel (TrackState::cand_done).  Only behind a frame that goes on tracking.
 __global__ void __launch_bounds__(kCandWarps * 32) mapcand_kernel(MapCandArgs a)
 {
     LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
     __shared__ double W[12];
     __shared__ uint32_t buf[kCandWarps][kMapCandCap];
-    int m = a.m;
+    int m = a.m, q_first = 0;
     if (a.st)
     {
         if (a.which == 0)
         {
-            if (a.st->state != 2)
+            const bool on = a.st->state == 2;
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                a.st->cand_done = on ? a.st->map_n : 0;
+            if (!on)
                 return; // first frame / lost: no projection matching
             m = a.st->map_n;
+        }
+        else if (a.which == 2)
+        {
+            const bool on = a.ctl_prev->mode == 1;
+            m = on ? a.ctl_prev->map_n_clean : 0;
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                a.st->cand_done = m;
+            if (!on)
+                return;
+        }
+        else if (a.which == 3)
+        {
+            // behind track_b, on its stream: the points it appended, listed for the coming frame
+            const bool on = a.ctl->mode == 1;
+            m = on ? a.st->map_n : 0;
+            q_first = on ? a.ctl->map_n_clean : 0;
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                a.st->tail_done = m;
+            if (!on || q_first >= m)
+                return;
         }
         else
         {
@@ -123,11 +197,9 @@ __global__ void __launch_bounds__(kCandWarps * 32) mapcand_kernel(MapCandArgs a)
                 return;
             m = a.st->staged_n;
         }
-    }
-    if (a.st)
-    {
-        // prepared by the kernel in front: track_b / reset (prediction for the map pass), pose_kernel (staged pass)
-        const double *src = a.which == 0 ? a.st->pred_W : a.ctl->opt_W;
+        // prepared by a kernel in front: track_b / reset (prediction for the map pass), pose_kernel (the staged pass; the
+        // prediction for the early listing of the coming frame)
+        const double *src = a.which == 1 ? a.ctl->opt_W : (a.which == 2 ? a.ctl_prev->next_W : a.st->pred_W);
         if (threadIdx.x < 12)
             W[threadIdx.x] = src[threadIdx.x];
     }
@@ -138,30 +210,8 @@ __global__ void __launch_bounds__(kCandWarps * 32) mapcand_kernel(MapCandArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int R = a.cam.tracking_radius;
     const float r2 = (float)(R * R);
-    for (int q = blockIdx.x * kCandWarps + warp; q < m; q += gridDim.x * kCandWarps)
-    {
-        double u, v;
-        const bool vis = point_visible(W, a.cam, a.xyz[3 * q], a.xyz[3 * q + 1], a.xyz[3 * q + 2], &u, &v);
-        const float2 p = vis ? make_float2((float)u, (float)v) : make_float2(0.f, 0.f);
-        if (lane == 0)
-        {
-            a.ms.vis[q] = vis;
-            a.ms.proj[q] = p;
-        }
-        int n = 0;
-        if (vis)
-        {
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(a.desc + 8 * (size_t)q);
-            const uint4 q1 = *reinterpret_cast<const uint4 *>(a.desc + 8 * (size_t)q + 4);
-            WarpCollector col{buf[warp], kMapCandCap, 0, lane};
-            scan_projected_window(f, a.cam, p, r2, q0, q1, lane, col);
-            n = col.n;
-            if (n <= kMapCandCap)
-                warp_sort_store<kMapCandCap / 32>(buf[warp], n, a.L.keys + (size_t)q * kMapCandCap, lane);
-        }
-        if (lane == 0)
-            a.L.count[q] = n;
-    }
+    for (int q = q_first + blockIdx.x * kCandWarps + warp; q < m; q += gridDim.x * kCandWarps)
+        warp_list_candidates(q, W, a.cam, r2, a.xyz, a.desc, f, a.proj, a.vis, a.L, buf[warp], lane);
 }
 
 struct RowCandArgs
@@ -219,6 +269,16 @@ __device__ void prepare_prediction(TrackState &S)
     world_to_camera(pose, S.pred_W);
 }
 
+// The map pass in the batched engine is cut in two (TrackArgs::part), because the points a frame appends to the map
+// come LAST in the greedy order: the choices of the points that were there before cannot depend on them.
+//   part 1 (early): the rounds over the points the previous frame's culling left, launched behind the early
+//           candidate listing, i.e. while track_b_kernel of the previous frame is still running on another stream.
+//           Reads nothing track_b writes (no TrackState::map_n / last_pose; sizes and pose come from the previous
+//           frame's FrameCtl), writes only scratch, the marks of the COMING frame's features and ctl->a1_*.
+//   part 2: after track_b -- everything else: refusal / lost / first frame, the motion-model update, the candidate
+//           lists and rounds of the appended points (the early part's matches are marks for them), the radius x2
+//           retry, book-keeping, the solver's inputs.
+//   part 0: both in one go (the blocking calls, the first frame of a batch).
 __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
 {
     LVT_GRID_DEP_SYNC(); // nothing of the previous kernel's output is touched before this
@@ -230,16 +290,15 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
     int *owner_a = s_owner, *owner_b = s_owner + a.owner_cap;
-    RoundsTeam team;
-    team.rank = rank;
-    team.nranks = nranks;
-    team.team_flags = s_team_flags;
     uint32_t *skeys = reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap);
-    int key_cap = a.key_cap;
-    {
-        // replica of all queries' choices (match.cuh, RoundsTeam): in the second owner array when the map fits there,
-        // else at the end of the key cache; maps beyond that fall back to the home-slice exchange
-        const int need = (a.st->map_n + 3) & ~3;
+    // replica of all queries' choices (match.cuh, RoundsTeam): in the second owner array when the queries fit there,
+    // else at the end of the key cache; passes beyond that fall back to the home-slice exchange
+    auto make_team = [&](int n_queries, int &key_cap) {
+        RoundsTeam team;
+        team.rank = rank;
+        team.nranks = nranks;
+        team.team_flags = s_team_flags;
+        const int need = (n_queries + 3) & ~3;
         if (need <= a.owner_cap)
             team.rep = owner_b;
         else if (need <= key_cap)
@@ -248,12 +307,42 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
             team.rep = reinterpret_cast<int *>(skeys) + key_cap;
         }
         team.rep_cap = team.rep ? need : 0;
-    }
+        return team;
+    };
 
     TrackState &S = *a.st;
     FrameCtl &ctl = *a.ctl;
     const TrackParams &tp = a.tp;
     const FeatDev fl = a.feats[0];
+    const int R = tp.cam.tracking_radius;
+    if (a.part == 1)
+    {
+        // ---- the early part (see above); uniform over the cluster
+        const bool on = a.ctl_prev->mode == 1;
+        const int M1 = on ? S.cand_done : 0; // = the previous frame's map_n_clean, set by the early candidate listing
+        if (M1 <= 0)
+        {
+            if (threadIdx.x == 0 && rank == 0)
+                ctl.a1_m = ctl.a1_count = ctl.a1_rounds = 0;
+            return;
+        }
+        const int nl1 = min(*fl.n, a.owner_cap);
+        int key_cap = a.key_cap;
+        const RoundsTeam team = make_team(M1, key_cap);
+        const int count = block_match_projected(a.sc.map_cand, a.map.desc, a.sc.ms, M1, fl, nl1, tp.cam, (float)(R * R), false, owner_a,
+                                                owner_b, sh.flag, nullptr, nullptr, &ctl.a1_rounds, rank == 0 ? a.dbg : nullptr, skeys,
+                                                key_cap, team);
+        if (rank != 0)
+            return;
+        for (int j = threadIdx.x; j < nl1; j += blockDim.x)
+            fl.matched[j] = owner_a[j] != kFree;
+        if (threadIdx.x == 0)
+        {
+            ctl.a1_m = M1;
+            ctl.a1_count = count;
+        }
+        return;
+    }
     const int state0 = S.state;
     const int nl = state0 == 3 ? 0 : min(*fl.n, a.owner_cap);
     const int map_n = S.map_n, staged_n = S.staged_n;
@@ -311,32 +400,92 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         return;
     }
 
-    // ---- predict (lvt/src/lvt_system.cpp:196); mapcand_kernel projected with the same prediction
+    // ---- predict (lvt/src/lvt_system.cpp:196); the candidate listings projected with the same prediction
     if (threadIdx.x == 0 && rank == 0)
     {
-        sh.pose = motion_predict(S.motion, last_pose);
+        if (a.ctl_prev && a.ctl_prev->mode == 1)
+        {
+            // pose_kernel of the previous frame ran the motion model already (same state, same pose)
+            S.motion = a.ctl_prev->next_motion;
+            sh.pose = a.ctl_prev->next_pred;
+        }
+        else
+            sh.pose = motion_predict(S.motion, last_pose);
         ctl.pred = sh.pose;
         ctl.info.map_points_before = map_n;
         ctl.info.staged_before = staged_n;
     }
     __syncthreads();
     const int M = map_n;
-    const int R = tp.cam.tracking_radius;
     const CandLists no_lists{nullptr, nullptr, 0};
-    int count = block_match_projected(a.sc.map_cand, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)(R * R), false, owner_a,
-                                      owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0], rank == 0 ? a.dbg : nullptr, skeys,
-                                      key_cap, team);
+    // Candidate lists exist for the points [0, cand_done): all of them behind mapcand_kernel; behind the early
+    // listing, the points the previous frame's culling left -- what track_b appended since (promoted and
+    // triangulated points, a few hundred at most; a whole seeded map behind a first frame) is listed here,
+    // a warp per point over the cluster, under the same prediction (TrackState::pred_W, written by track_b).
+    const int cand_done = min(max(S.cand_done, 0), M);
+    // the early part's points keep their choices; their features are marks for the points behind them
+    const int M1 = a.part == 2 ? min(max(ctl.a1_m, 0), M) : 0;
+    // ... and behind the early part also [cand_done, tail_done): listed behind track_b on its stream
+    const int listed = (a.part == 2 && S.tail_done > cand_done) ? min(S.tail_done, M) : cand_done;
+    if (listed < M) // uniform over the cluster
+    {
+        if (threadIdx.x < 12)
+            sh.W[threadIdx.x] = S.pred_W[threadIdx.x];
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        uint32_t *buf = reinterpret_cast<uint32_t *>(s_owner) + warp * kMapCandCap; // owner arrays / key cache: not in use yet
+        for (int q = listed + rank * nwarps + warp; q < M; q += nranks * nwarps)
+            warp_list_candidates(q, sh.W, tp.cam, (float)(R * R), a.map.xyz, a.map.desc, fl, a.sc.ms.proj, a.sc.ms.vis, a.sc.map_cand, buf,
+                                 lane);
+        __threadfence();
+        cluster.sync(); // the lists are read by whichever CTA the rounds deal the point to
+    }
+    bool owners_current = true; // owner_a describes the marks of the frame's features (else: fl.matched does already)
+    int count, key_cap = a.key_cap;
+    if (M1 == 0)
+    {
+        const RoundsTeam team = make_team(M, key_cap);
+        count = block_match_projected(a.sc.map_cand, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)(R * R), false, owner_a, owner_b,
+                                      sh.flag, nullptr, nullptr, &ctl.rounds[0], rank == 0 ? a.dbg : nullptr, skeys, key_cap, team);
+    }
+    else if (M1 < M)
+    {
+        const MatchScratch tms{a.sc.ms.proj + M1, a.sc.ms.vis + M1, a.sc.ms.choice + M1, a.sc.ms.items};
+        const CandLists tl{a.sc.map_cand.keys + (size_t)M1 * a.sc.map_cand.cap, a.sc.map_cand.count + M1, a.sc.map_cand.cap};
+        // A few hundred appended points at most, and when the early part alone has enough matches the retry cannot
+        // fire whatever they do: rank 0 settles them on its own, without the cluster's barriers.
+        const bool alone = M - M1 <= kTrackThreads && ctl.a1_count >= kNMatchesTh;
+        if (alone && rank != 0)
+            return;
+        const RoundsTeam team = alone ? RoundsTeam() : make_team(M - M1, key_cap);
+        count = ctl.a1_count + block_match_projected(tl, a.map.desc + 8 * (size_t)M1, tms, M - M1, fl, nl, tp.cam, (float)(R * R), true,
+                                                     owner_a, owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[0], nullptr, skeys, key_cap,
+                                                     team);
+        if (threadIdx.x == 0 && rank == 0)
+            ctl.rounds[0] += ctl.a1_rounds;
+    }
+    else
+    {
+        count = ctl.a1_count; // nothing was appended: the early part was the whole pass
+        owners_current = false;
+        if (threadIdx.x == 0 && rank == 0)
+            ctl.rounds[0] = ctl.a1_rounds;
+    }
     int retried = 0;
     if (count < kNMatchesTh)
     {
         retried = 1; // marks reset, radius doubled, cell window unchanged (lvt_local_map.cpp:173-199)
+        key_cap = a.key_cap;
+        const RoundsTeam team = make_team(M, key_cap);
         count = block_match_projected(no_lists, a.map.desc, a.sc.ms, M, fl, nl, tp.cam, (float)((2 * R) * (2 * R)), false,
                                       owner_a, owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[1], nullptr, nullptr, 0, team);
+        owners_current = true;
     }
     if (rank != 0)
         return; // the rounds are over (their last cluster barrier made every choice visible): the rest is rank 0's
-    for (int j = threadIdx.x; j < nl; j += blockDim.x)
-        fl.matched[j] = owner_a[j] != kFree;
+    if (owners_current)
+        for (int j = threadIdx.x; j < nl; j += blockDim.x)
+            fl.matched[j] = owner_a[j] != kFree;
     LVT_PHASE(1);
     // bookkeeping (:201-224) + the solver's inputs, in map order.  Four points per thread, interleaved
     // (coalesced), their loads in flight together, and one packed block scan per 4 x blockDim points: the
@@ -395,6 +544,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         ctl.info.tracked = n_matches;
         ctl.info.retried_matching = retried;
         ctl.n_matches = n_matches;
+        S.cand_done = S.tail_done = 0; // consumed
         ctl.cyc[2] = phase_clock();
         if (n_matches < tp.min_matches)
         {
@@ -521,6 +671,11 @@ __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThre
             __threadfence_system();
             *reinterpret_cast<volatile int *>(&a.early->seq) = a.early_seq;
         }
+        // the prediction for the next frame (behind the blocking caller's pose): see FrameCtl::next_pred
+        MotionState mm = a.st->motion;
+        a.ctl->next_pred = motion_predict(mm, a.ctl->opt);
+        a.ctl->next_motion = mm;
+        world_to_camera(a.ctl->next_pred, a.ctl->next_W);
     }
 }
 
@@ -542,7 +697,7 @@ __device__ int block_new_triangulation(const TrackArgs &a, TrackShared &sh, cons
 
     if (tp.sensor == 1)
     {
-        const int np = block_row_match(a.row_cand, fl, nl, fr, nr, tp.cam, a.sc.row_choice, a.sc.ms.items, owner_a,
+        const int np = block_row_match(a.row_cand, fl, nl, fr, nr, tp.cam, a.sc.row_choice, a.sc.bs.items, owner_a,
                                        owner_b, sh.flag, sh.scan, a.sc.pair_query, a.sc.pair_train, &a.ctl->rounds[3], skeys, a.key_cap,
                                        a.dbg ? a.dbg + 60000 : nullptr); // (debug builds of the launch: far behind the triangulated points)
         if (threadIdx.x == 0)
@@ -701,7 +856,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
     {
         const int Sn = staged_n;
         const int R = tp.cam.tracking_radius;
-        block_match_projected(a.sc.map_cand, a.staged.desc, a.sc.ms, Sn, fl, nl, tp.cam, (float)(R * R), true, owner_a,
+        block_match_projected(a.sc.staged_cand, a.staged.desc, a.sc.bs, Sn, fl, nl, tp.cam, (float)(R * R), true, owner_a,
                               owner_b, sh.flag, nullptr, nullptr, &ctl.rounds[2], nullptr,
                               reinterpret_cast<uint32_t *>(s_owner + 2 * a.owner_cap), a.key_cap);
         LVT_BMARK(1);
@@ -717,7 +872,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         for (int i0 = 0; i0 < Sn; i0 += blockDim.x)
         {
             const int i = i0 + threadIdx.x;
-            const bool hit = i < Sn && a.sc.ms.vis[i] && a.sc.ms.choice[i] >= 0;
+            const bool hit = i < Sn && a.sc.bs.vis[i] && a.sc.bs.choice[i] >= 0;
             int tot_h;
             const int h = block_exclusive_scan(hit, sh.scan, &tot_h);
             bool prom = false;
@@ -791,7 +946,8 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_b_kernel(TrackArgs a)
         S.map_n = map_n;
         S.staged_n = staged_n;
         S.last_pose = sh.pose;
-        prepare_prediction(S);
+        for (int k = 0; k < 12; k++) // the prediction for the next frame: pose_kernel has it
+            S.pred_W[k] = ctl.next_W[k];
         a.result->dbg[7] = phase_clock();
         write_result(a, S, sh.pose, 2, map_n, staged_n);
     }
@@ -807,6 +963,7 @@ __global__ void reset_state_kernel(TrackState *st)
     S.last_matches[0] = S.last_matches[1] = S.last_matches[2] = 0x7FFFFFFF;
     S.error = 0;
     S.halt = 0;
+    S.cand_done = S.tail_done = 0;
     S.last_pose.q = Quat{1, 0, 0, 0};
     S.last_pose.t[0] = S.last_pose.t[1] = S.last_pose.t[2] = 0;
     motion_reset(S.motion);
@@ -984,18 +1141,35 @@ int launch_rowcand(const FeatDev *d_feats, const CamParams &cam, const CandLists
 int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const PointStore &map, const PointStore &staged,
                        const FeatDev *d_feats, const TrackParams &tp, const TrackScratch &sc, const CandLists &row_cand,
                        const TrackLaunchCfg &cfg, int *d_error, cudaStream_t stream, cudaEvent_t right_ready, int parts,
-                       EarlyResult *early, int early_seq)
+                       EarlyResult *early, int early_seq, const TrackOverlap *ov, const void *ctl_prev_v)
 {
     // parts: 1 = up to the pose (mapcand, track_a, pose), 2 = the rest (stagedcand, track_b), 3 = the whole frame
+    // ov (the batched engine, parts == 3): the rest runs on ov->side behind the pose; with ov->early the map pass is
+    // cut in two around the previous frame's rest (track_a_kernel) and starts from that frame's FrameCtl
     FrameCtl *ctl = static_cast<FrameCtl *>(ctl_v);
+    const FrameCtl *ctl_prev = static_cast<const FrameCtl *>(ctl_prev_v); // the frame launched before this one
+    const bool early_pass = ov && ov->early;
     const size_t smem = track_smem_bytes(cfg);
     TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, cfg.owner_cap, cfg.key_cap,
-                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr, d_error};
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr, d_error, ctl_prev, 0};
     if (parts & 1)
     {
-    MapCandArgs mc{st, ctl, 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
-    LVT_TIMED(stream, K_MAPCAND, launch_chained(mapcand_kernel, dim3(148 * 2), dim3(kCandWarps * 32), 0, stream, mc));
+    MapCandArgs mc{st, ctl, early_pass ? 2 : 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms.proj, sc.ms.vis,
+                   sc.map_cand, ctl_prev};
+    LVT_TIMED(stream, early_pass ? K_MAPCAND_EARLY : K_MAPCAND,
+              launch_chained(mapcand_kernel, dim3(148 * 2), dim3(kCandWarps * 32), 0, stream, mc));
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
+    if (early_pass)
+    {
+        TrackArgs a1 = a;
+        a1.part = 1;
+        LVT_TIMED(stream, K_TRACK_A_EARLY,
+                  launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a1));
+        LVT_LAUNCH_CHECK(stream, "track_a_kernel (early part)");
+        // the previous frame's map maintenance (other stream) has to be through before anything else of this frame
+        LVT_CUDA_TRY(cudaStreamWaitEvent(stream, ov->prev_rest_done, 0));
+        a.part = 2;
+    }
     LVT_TIMED(stream, K_TRACK_A, launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
@@ -1067,7 +1241,16 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     }
     if (!(parts & 2))
         return LVTK_OK;
-    MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.ms, sc.map_cand};
+    if (ov)
+    {
+        // the rest of the frame on the side stream: the next frame's candidate listing and early map pass follow the
+        // pose on `stream` at once
+        LVT_CUDA_TRY(cudaEventRecord(ov->pose_done, stream));
+        LVT_CUDA_TRY(cudaStreamWaitEvent(ov->side, ov->pose_done, 0));
+        stream = ov->side;
+    }
+    MapCandArgs sc2{st, ctl, 1, tp.staged_threshold, PoseD{}, 0, staged.xyz, staged.desc, d_feats, tp.cam, sc.bs.proj, sc.bs.vis,
+                    sc.staged_cand, nullptr};
     LVT_TIMED(stream, K_STAGEDCAND, launch_chained(mapcand_kernel, dim3(148), dim3(kCandWarps * 32), 0, stream, sc2));
     LVT_LAUNCH_CHECK(stream, "stagedcand_kernel");
     // everything up to here needs the left image only; the right image's features and the row-matching
@@ -1076,6 +1259,16 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
         LVT_CUDA_TRY(cudaStreamWaitEvent(stream, right_ready, 0));
     LVT_TIMED(stream, K_TRACK_B, launch_chained(track_b_kernel, dim3(1), dim3(kTrackThreads), smem, stream, a));
     LVT_LAUNCH_CHECK(stream, "track_b_kernel");
+    if (ov && ov->next_feats)
+    {
+        // the points this frame appended to the map, listed for the next frame while its early map pass is running
+        MapCandArgs tc{st, ctl, 3, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, ov->next_feats, tp.cam, sc.ms.proj, sc.ms.vis,
+                       sc.map_cand, nullptr};
+        LVT_TIMED(stream, K_TAILCAND, launch_chained(mapcand_kernel, dim3(148), dim3(kCandWarps * 32), 0, stream, tc));
+        LVT_LAUNCH_CHECK(stream, "mapcand_kernel (appended points)");
+    }
+    if (ov)
+        LVT_CUDA_TRY(cudaEventRecord(ov->rest_done, stream));
     return LVTK_OK;
 }
 
@@ -1098,7 +1291,7 @@ int launch_match_seam(const double *d_xyz, const uint32_t *d_pdesc, int m, const
                       int *d_match_idx, float *d_d1, float *d_d2, int *d_count_retried, const TrackLaunchCfg &cfg,
                       cudaStream_t stream)
 {
-    MapCandArgs mc{nullptr, nullptr, 0, 0, pose, m, d_xyz, d_pdesc, d_feat, cam, ms, lists};
+    MapCandArgs mc{nullptr, nullptr, 0, 0, pose, m, d_xyz, d_pdesc, d_feat, cam, ms.proj, ms.vis, lists, nullptr};
     mapcand_kernel<<<148 * 2, kCandWarps * 32, 0, stream>>>(mc);
     LVT_LAUNCH_CHECK(stream, "mapcand_kernel");
     MatchSeamArgs a{d_pdesc, m, d_feat, cam, retry_below, ms, lists, d_match_idx, d_d1, d_d2, d_count_retried, cfg.owner_cap, cfg.key_cap};

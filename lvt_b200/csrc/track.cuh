@@ -46,6 +46,14 @@ struct TrackState
     // that finishes a frame so that mapcand_kernel starts projecting at once (same arithmetic as
     // track_a's own prediction: motion_predict on a copy of the motion state, world_to_camera)
     double pred_W[12];
+    // candidate lists of the map pass exist for the map points [0, cand_done): all of them behind the regular
+    // mapcand_kernel; behind the EARLY one (launched as soon as the previous frame's pose is known, while that
+    // frame's map maintenance is still running) the points its culling left.  track_a_kernel lists the rest
+    // -- what track_b has appended since -- itself and clears this.
+    int cand_done;
+    // ... and for [cand_done, tail_done): the points track_b appended, listed behind it on its own stream for the
+    // coming frame (mapcand_kernel, which == 3) while that frame's early map pass is running
+    int tail_done;
 };
 
 struct FrameResult
@@ -88,6 +96,18 @@ struct TrackLaunchCfg
     int cluster = 1;   // CTAs of track_a_kernel's cluster
 };
 
+// The batched engine overlaps a frame's map maintenance (stagedcand + track_b, on `side`) with the next frame's
+// candidate listing and early map pass (track.cu, track_a_kernel): the events tie the two streams together.
+struct TrackOverlap
+{
+    cudaStream_t side;          // where stagedcand + track_b of this frame run
+    cudaEvent_t pose_done;      // recorded behind this frame's pose_kernel (the side stream waits for it)
+    cudaEvent_t rest_done;      // recorded behind this frame's track_b_kernel
+    cudaEvent_t prev_rest_done; // the previous frame's rest_done (early only)
+    bool early;                 // the previous frame was launched with an overlap too: list / match early
+    const FeatDev *next_feats;  // device: the left features of the frame behind this one when they are extracted (the
+                                // points track_b appends are listed for it right behind track_b), else nullptr
+};
 // scratch for one tracking CTA (global memory, sized for the point / feature capacities)
 struct TrackScratch
 {
@@ -98,6 +118,10 @@ struct TrackScratch
     uint8_t *inlier;   // [pcap]
     double *e2;        // [pcap]
     CandLists map_cand; // [pcap][kMapCandCap] candidate keys of the map pass (mapcand_kernel)
+    // track_b (staged points, row matching) has its own copies of everything the map pass of the NEXT frame
+    // writes: in the batched engine the two run at the same time (context.cu, run_frames)
+    MatchScratch bs;       // [pcap] / items [2 * pcap + 1024]
+    CandLists staged_cand; // [pcap][kMapCandCap]
     int *row_choice;   // [fcap]
     int *pair_query;   // [fcap]
     int *pair_train;   // [fcap]
