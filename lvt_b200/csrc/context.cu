@@ -414,6 +414,7 @@ struct lvtk_ctx
                               // that a frame's early parts read the previous frame's block while that frame's map
                               // maintenance is still using it (ctl_idx: the block of the frame launched last)
     int ctl_idx = 0;
+    int frame_seq = 0; // frames launched with an overlap so far (TrackState::rest_seq)
     cudaEvent_t ev_pose_done[2] = {}, ev_rest_done[2] = {}; // batched engine: TrackOverlap events, by frame parity
     FrameResult *d_result = nullptr, *h_result = nullptr;
     int *h_error = nullptr; // pinned copy of ws.error, fetched together with the result
@@ -488,8 +489,10 @@ static int ctx_launch_track(lvtk_ctx *c, FrameResult *result, const FeatDev *fea
         c->ctl_idx ^= 1; // a new frame (parts == 2 finishes the frame launched with parts == 1)
     const size_t cb = (frame_ctl_bytes() + 255) & ~(size_t)255;
     uint8_t *ctl = c->d_ctl + cb * (size_t)c->ctl_idx, *ctl_prev = c->d_ctl + cb * (size_t)(c->ctl_idx ^ 1);
+    if (overlap)
+        c->frame_seq++;
     TrackOverlap ov{c->xs[3], c->ev_pose_done[c->ctl_idx], c->ev_rest_done[c->ctl_idx], c->ev_rest_done[c->ctl_idx ^ 1], overlap == 2,
-                    next_feats};
+                    c->frame_seq, next_feats};
     return launch_track_frame(c->d_state, ctl, result, c->map, c->staged, feats, c->tp, c->sc, row_cand, c->tcfg, c->ws.error, st,
                               right_ready, parts, early, early_seq, overlap ? &ov : nullptr, ctl_prev);
 }
@@ -2178,8 +2181,9 @@ LVT_API int lvt_debug_phase_cycles(lvt_handle h, int i, long long cycles[8], int
 }
 /* profiling aid: nanosecond marks inside track_b of pool frame i of the last batch (i < 0: the last blocking call):
  * [0] start, [1] staged rounds, [2] promotion, [3] staged compaction, [4] row matching, [5] triangulation,
- * [6] new points appended, [7] state + prediction written; 0 = phase not run */
-LVT_API int lvt_debug_frame_marks(lvt_handle h, int i, long long marks[8])
+ * [6] new points appended, [7] state + prediction written; [8], [9] start / end of the frame's early map pass
+ * (track_a_kernel part 1, batched engine); 0 = phase not run */
+LVT_API int lvt_debug_frame_marks(lvt_handle h, int i, long long marks[12])
 {
     System *vo = static_cast<System *>(h);
     if (!vo)
@@ -2187,6 +2191,7 @@ LVT_API int lvt_debug_frame_marks(lvt_handle h, int i, long long marks[8])
     vo->finish_pending();
     const FrameResult &r = i < 0 ? *vo->ctx->h_result : vo->ctx->eng.h_results[i];
     std::memcpy(marks, r.dbg, sizeof(r.dbg));
+    std::memcpy(marks + 8, r.amark, sizeof(r.amark)); // [8] / [9]: start / end of the early map pass (batched engine)
     return 0;
 }
 /* profiling aid: host time of the blocking calls since the last reset, microseconds:

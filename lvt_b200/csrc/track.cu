@@ -45,6 +45,7 @@ struct FrameCtl
     // the early part of the map pass (track_a_kernel part 1, batched engine): map points it matched (0: it did not
     // run), their matches, its rounds
     int a1_m, a1_count, a1_rounds;
+    long long amark[4]; // as FrameResult::amark
     // what the motion model predicts for the NEXT frame from this frame's pose (pose_kernel, once per frame, as soon as
     // the pose is known): the next frame's candidate listing and track_a take it from here instead of each running
     // the same slerp again -- lvt_motion_model::predict_next_pose on the state track_a left
@@ -69,6 +70,7 @@ struct TrackArgs
     int *error;         // the context's sticky error flag (the one the host fetches with every result)
     const FrameCtl *ctl_prev; // the previous frame's hand-over block (the early parts read its mode / pose / culled map size)
     int part;                 // track_a_kernel: 0 the whole map pass, 1 its early part, 2 the rest (see there)
+    int wait_seq;             // part 2: TrackState::rest_seq to wait for before anything else (0: nothing)
 };
 
 struct TrackShared
@@ -259,6 +261,8 @@ __device__ void write_result(const TrackArgs &a, TrackState &S, const PoseD &pos
         a.result->cycles[k] = c.cyc[k];
     for (int k = 0; k < 8; k++)
         a.result->rounds[k] = c.rounds[k];
+    for (int k = 0; k < 4; k++)
+        a.result->amark[k] = c.amark[k];
 }
 
 // one thread: world->camera of the pose predicted for the next frame (see TrackState::pred_W)
@@ -320,6 +324,11 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         // ---- the early part (see above); uniform over the cluster
         const bool on = a.ctl_prev->mode == 1;
         const int M1 = on ? S.cand_done : 0; // = the previous frame's map_n_clean, set by the early candidate listing
+        if (threadIdx.x == 0 && rank == 0)
+        {
+            ctl.amark[0] = phase_clock();
+            ctl.amark[1] = ctl.amark[2] = ctl.amark[3] = 0;
+        }
         if (M1 <= 0)
         {
             if (threadIdx.x == 0 && rank == 0)
@@ -340,8 +349,33 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         {
             ctl.a1_m = M1;
             ctl.a1_count = count;
+            ctl.amark[1] = phase_clock();
         }
         return;
+    }
+    if (a.wait_seq != 0)
+    {
+        // the previous frame's map maintenance runs on another stream: wait for its sequence number (signal_kernel).
+        // Everything it depends on was submitted before this kernel, so it cannot be queued behind us; the bound
+        // only keeps a lost signal from hanging the device (the frame then fails loudly).
+        if (threadIdx.x == 0)
+        {
+            const long long t0 = phase_clock();
+            for (;;)
+            {
+                int seen;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(&S.rest_seq) : "memory");
+                if (seen - a.wait_seq >= 0)
+                    break;
+                if (phase_clock() - t0 > 2000000000ll)
+                {
+                    *a.error = S.error = LVTK_ERR_CUDA;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
     }
     const int state0 = S.state;
     const int nl = state0 == 3 ? 0 : min(*fl.n, a.owner_cap);
@@ -971,6 +1005,17 @@ __global__ void reset_state_kernel(TrackState *st)
 
 __global__ void clear_halt_kernel(TrackState *st) { st->halt = 0; }
 
+// last kernel of a frame on the side stream (batched engine): see TrackState::rest_seq
+__global__ void signal_kernel(TrackState *st, int seq)
+{
+    LVT_GRID_DEP_SYNC(); // the kernels in front (track_b, the listing of the appended points) are complete and visible
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(&st->rest_seq), "r"(seq) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // seam kernels
 // ---------------------------------------------------------------------------------------------
@@ -1151,7 +1196,7 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
     const bool early_pass = ov && ov->early;
     const size_t smem = track_smem_bytes(cfg);
     TrackArgs a{st, ctl, result, map, staged, d_feats, tp, sc, row_cand, cfg.owner_cap, cfg.key_cap,
-                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr, d_error, ctl_prev, 0};
+                debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) + 64 : nullptr, d_error, ctl_prev, 0, 0};
     if (parts & 1)
     {
     MapCandArgs mc{st, ctl, early_pass ? 2 : 0, tp.staged_threshold, PoseD{}, 0, map.xyz, map.desc, d_feats, tp.cam, sc.ms.proj, sc.ms.vis,
@@ -1166,11 +1211,15 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
         LVT_TIMED(stream, K_TRACK_A_EARLY,
                   launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a1));
         LVT_LAUNCH_CHECK(stream, "track_a_kernel (early part)");
-        // the previous frame's map maintenance (other stream) has to be through before anything else of this frame
-        LVT_CUDA_TRY(cudaStreamWaitEvent(stream, ov->prev_rest_done, 0));
+        // The previous frame's map maintenance (side stream) has to be through before anything else of this frame:
+        // the rest of track_a -- ONE CTA, resident behind the early part -- waits for its sequence number on the device.
         a.part = 2;
+        a.wait_seq = ov->seq - 1;
+        LVT_TIMED(stream, K_TRACK_A, launch_chained(track_a_kernel, dim3(1), dim3(kTrackThreads), smem, stream, a));
     }
-    LVT_TIMED(stream, K_TRACK_A, launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a));
+    else
+        LVT_TIMED(stream, K_TRACK_A,
+                  launch_chained_cluster(track_a_kernel, dim3(cfg.cluster), dim3(kTrackThreads), smem, stream, cfg.cluster, a));
     LVT_LAUNCH_CHECK(stream, "track_a_kernel");
     PoseArgs pa{ctl, sc.sol_xyz, sc.sol_uv, 0, PoseD{}, tp.cam, sc.level, sc.inlier, sc.e2, nullptr, nullptr,
                 debug_sync_enabled() ? reinterpret_cast<long long *>(sc.tri_xyz) : nullptr, st, early, early_seq,
@@ -1268,7 +1317,12 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
         LVT_LAUNCH_CHECK(stream, "mapcand_kernel (appended points)");
     }
     if (ov)
+    {
+        count_launch();
+        LVT_CUDA_TRY(launch_chained(signal_kernel, dim3(1), dim3(32), 0, stream, st, ov->seq));
+        LVT_LAUNCH_CHECK(stream, "signal_kernel");
         LVT_CUDA_TRY(cudaEventRecord(ov->rest_done, stream));
+    }
     return LVTK_OK;
 }
 

@@ -54,6 +54,11 @@ struct TrackState
     // ... and for [cand_done, tail_done): the points track_b appended, listed behind it on its own stream for the
     // coming frame (mapcand_kernel, which == 3) while that frame's early map pass is running
     int tail_done;
+    // sequence number of the last frame whose map maintenance (track_b and what follows it on the side stream) is
+    // through -- written by signal_kernel; the rest of the next frame's track_a waits for it ON THE DEVICE
+    // (TrackArgs::wait_seq): its CTA is resident behind the early part already, so it starts within a microsecond
+    // instead of competing for an empty SM with the extraction kernels after a stream-level wait
+    int rest_seq;
 };
 
 struct FrameResult
@@ -65,7 +70,8 @@ struct FrameResult
                          // pose solver (passes over the correspondences: linearisations + LM trials), [5] = clock cycles of
                          // the map culling next to the solver, [6] / [7] = ns into track_b when the staged points / the
                          // row matching were done (profiling aids)
-    long long dbg[8];    // clock64() marks inside the map pass (profiling aid)
+    long long dbg[8];    // nanosecond marks inside track_b (profiling aid, lvt_debug_frame_marks)
+    long long amark[4];  // nanosecond marks of the early map pass (track_a_kernel part 1): start, end; [2..3] spare
 };
 
 // what a blocking caller waits for: available as soon as the pose solver is through, while the map
@@ -105,6 +111,7 @@ struct TrackOverlap
     cudaEvent_t rest_done;      // recorded behind this frame's track_b_kernel
     cudaEvent_t prev_rest_done; // the previous frame's rest_done (early only)
     bool early;                 // the previous frame was launched with an overlap too: list / match early
+    int seq;                    // this frame's sequence number (TrackState::rest_seq once its rest is through)
     const FeatDev *next_feats;  // device: the left features of the frame behind this one when they are extracted (the
                                 // points track_b appends are listed for it right behind track_b), else nullptr
 };

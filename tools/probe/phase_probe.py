@@ -35,7 +35,21 @@ for i in range(NN):
     clean += list(rnd)[5]
     if i < 12:
         print(i, "rounds", list(rnd), "tri", infos[i]["triangulated"], "staged", infos[i]["staged_before"], " ".join("%s=%.0fus" % (nm, v / 1e3) for nm, v in zip(names, d)))
-bm = (C.c_longlong * 8)()
+bm = (C.c_longlong * 12)()
+# timeline of the overlapped chain, relative to the previous frame's pose (us): early map pass start / end, the previous
+# frame's track_b end, this frame's track_a (rest) start
+cy = (C.c_longlong * 8)(); rn = (C.c_int * 8)()
+prev = None
+print("overlap timeline (us after the previous frame's pose was written): early pass start, end | previous track_b start, end | rest of track_a start")
+for i in range(NN):
+    lib.lib.lvt_debug_phase_cycles(C.c_void_p(vo.h), i, cy, rn)
+    lib.lib.lvt_debug_frame_marks(C.c_void_p(vo.h), i, bm)
+    cur = (list(cy), list(bm))
+    if prev is not None and i < 14 and bm[8] > 0:
+        p4 = prev[0][4]
+        print("  %2d  early %.1f .. %.1f | track_b %.1f .. %.1f | rest %.1f" % (i, (bm[8] - p4) / 1e3, (bm[9] - p4) / 1e3,
+              (prev[0][5] - p4) / 1e3, (prev[0][7] - p4) / 1e3, (cy[0] - p4) / 1e3))
+    prev = cur
 bn = ["staged rounds", "promotion", "staged compaction", "row matching", "triangulation", "append", "state+prediction"]
 print("track_b phases (us since the previous mark; - = not run):")
 for i in range(12):
