@@ -124,3 +124,43 @@ def test_bad_arguments(cuda):
     assert vo.last_status() == -1 and vo.get_state() == 1
     p, i = vo.track_batch(a, b)
     assert i[1]["state"] == 2 and i[1]["frame_number"] == 2
+
+
+def test_batch_with_lost_frames_and_reset(cuda, oracle):
+    """State changes INSIDE a batch: the engine launches a frame's early map pass before the previous frame's map
+    maintenance is through, so every transition (first frame -> tracking, tracking -> lost on a blank frame, lost
+    frames, reset -> first frame again) has to fall back to the plain order on the device.  Against the oracle and
+    the blocking calls, frame by frame."""
+    name, n = "kitti_synth", 18
+    a, b = _frames(name, n, seed=5)
+    blank = np.full_like(a[0], 128)
+    a[9], b[9] = blank, blank                      # no corners: lost (lvt_system.cpp:267-272), and stays lost
+    ref_p, ref_i, ref = _per_frame(cuda, name, a, b)
+    orc_p, orc_i, _ = _per_frame(oracle, name, a, b)
+    vo = cuda.create(configs.make_params(name), 1)
+    poses, infos = vo.track_batch(a, b)
+    assert infos == ref_i == orc_i
+    assert [i["state"] for i in infos[8:11]] == [capi.STATE_TRACKING, capi.STATE_LOST, capi.STATE_LOST]
+    assert np.array_equal(poses, ref_p) and np.abs(poses - orc_p).max() < 1e-6
+    # reset between two batches: the next batch starts with a first frame again
+    for v in (vo, ref):
+        v.reset()
+    p2, i2 = vo.track_batch(a[:6], b[:6])
+    r2 = [np.concatenate([x.ravel(), y]) for x, y in (track(ref, 1, l, r) for l, r in zip(a[:6], b[:6]))]
+    assert np.array_equal(p2, np.array(r2)) and i2[-1]["state"] == capi.STATE_TRACKING
+    assert i2 == ref_i[:6]
+
+
+def test_batch_retry_pass_with_few_matches(cuda, oracle):
+    """fewer than 50 matches in the map pass: the radius x2 retry (lvt_local_map.cpp:173-199) fires inside the rest of
+    track_a, after the early part; a tiny map (max_keypoints_per_cell = 6) gets there"""
+    name, n = "kitti_synth", 10
+    a, b = _frames(name, n, seed=7)
+    over = dict(max_keypoints_per_cell=6)
+    ref_p, ref_i, _ = _per_frame(cuda, name, a, b, **over)
+    orc_p, orc_i, _ = _per_frame(oracle, name, a, b, **over)
+    vo = cuda.create(configs.make_params(name, **over), 1)
+    poses, infos = vo.track_batch(a, b)
+    assert infos == ref_i == orc_i
+    assert any(i["retried_matching"] for i in infos) and not all(i["retried_matching"] for i in infos[1:])
+    assert np.array_equal(poses, ref_p) and np.abs(poses - orc_p).max() < 1e-6
