@@ -175,8 +175,10 @@ LVT_API int lvt_set_rectification(lvt_handle vo_system, const lvt_rectify_c *lef
  * The reference processes one frame per call and blocks (lvt/src/lvt_c.cpp:63-88).  When the
  * frames are already in device memory the same per-frame pipeline can run back to back with the
  * feature extraction of frame t+1 overlapped with the tracking of frame t (compute_features is
- * state-free, lvt/src/lvt_image_features_handler.cpp:196-209).  Results are identical to calling
- * lvt_track (lvt_track_rgbd) on the same frames in the same order. */
+ * state-free, lvt/src/lvt_image_features_handler.cpp:196-209), and with the map maintenance of frame
+ * t (staged points, triangulation: it only appends to the map) overlapped with the projection
+ * matching of frame t+1 over the points that were there before.  Results are
+ * identical to calling lvt_track (lvt_track_rgbd) on the same frames in the same order. */
 LVT_API int lvt_pool_reserve(lvt_handle vo_system, int n_frames);
 /* copy one stereo pair (tightly packed u8) into pool slot `frame` */
 LVT_API int lvt_pool_upload(lvt_handle vo_system, int frame, const unsigned char *left, const unsigned char *right);

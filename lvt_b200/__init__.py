@@ -8,7 +8,8 @@ import os
 from .capi import (KP_DTYPE, SENSOR_RGBD, SENSOR_STEREO, STATE_LOST, STATE_NOT_INITIALIZED, STATE_TRACKING, Context,
                    FrameInfo, Library, LvtError, Params, System)
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "liblvt_b200.so")
+# LVT_B200_LIB: another build of the same library (A/B runs of the probes against an older build)
+LIB_PATH = os.environ.get("LVT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "liblvt_b200.so")
 _lib = None
 
 

@@ -1213,9 +1213,13 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
         LVT_LAUNCH_CHECK(stream, "track_a_kernel (early part)");
         // The previous frame's map maintenance (side stream) has to be through before anything else of this frame:
         // the rest of track_a -- ONE CTA, resident behind the early part -- waits for its sequence number on the device.
+        // (Parameter sets that send every new point straight to the map -- no staging, RGB-D -- append hundreds to
+        // thousands of points per frame: there the rest keeps the cluster for their rounds.)
         a.part = 2;
         a.wait_seq = ov->seq - 1;
-        LVT_TIMED(stream, K_TRACK_A, launch_chained(track_a_kernel, dim3(1), dim3(kTrackThreads), smem, stream, a));
+        const int rest_ctas = (tp.staged_threshold == 0 || tp.sensor == 2) ? cfg.cluster : 1;
+        LVT_TIMED(stream, K_TRACK_A,
+                  launch_chained_cluster(track_a_kernel, dim3(rest_ctas), dim3(kTrackThreads), smem, stream, rest_ctas, a));
     }
     else
         LVT_TIMED(stream, K_TRACK_A,
