@@ -91,6 +91,39 @@ def test_distinct_handles_on_distinct_threads(cuda, oracle):
         _same(g, r)
 
 
+def test_batched_engine_on_distinct_threads(cuda, oracle):
+    """the batched engine of several handles at once (each with its own tracking / side / extraction streams, a CTA of
+    every handle waiting on the device for that handle's map maintenance): every handle reproduces the oracle and its
+    own blocking calls, whatever the others are doing"""
+    jobs = [("kitti_synth", 36, 4), ("kitti_synth", 36, 5), ("euroc_synth", 18, 3), ("tum_synth", 24, 2), ("kitti_synth", 36, 6)]
+    ref = [_trajectory(oracle, *j)[0] for j in jobs]
+    got, errs = [None] * len(jobs), []
+
+    def work(i):
+        try:
+            name, n, seed = jobs[i]
+            cfg = configs.CONFIGS[name]
+            st = make_stream(name, n, seed)
+            fr = [st.frame(t) for t in range(n)]
+            vo = cuda.create(configs.make_params(name), cfg["sensor"])
+            out = []
+            for lo in range(0, n, 12):  # three calls per handle
+                a, b = [f[0] for f in fr[lo:lo + 12]], [f[1] for f in fr[lo:lo + 12]]
+                poses, infos = vo.track_batch(a, b)  # (depth images select lvt_track_batch_rgbd)
+                out += [(poses[k, :9].reshape(3, 3), poses[k, 9:], infos[k]) for k in range(len(infos))]
+            got[i] = out
+            vo.destroy()
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for g, r in zip(got, ref):
+        _same(g, r)
+
+
 def test_second_brief_table_through_set_brief_pairs(cuda, oracle):
     """the only way a user gets OpenCV-exact descriptor bits is to inject opencv_contrib's table: the
     injection route itself is tested with a second table (other seed) in both libraries, with a handle that
