@@ -414,7 +414,7 @@ struct lvtk_ctx
                               // that a frame's early parts read the previous frame's block while that frame's map
                               // maintenance is still using it (ctl_idx: the block of the frame launched last)
     int ctl_idx = 0;
-    int frame_seq = 0; // frames launched with an overlap so far (TrackState::rest_seq)
+    unsigned frame_seq = 0; // frames launched with an overlap so far (TrackState::rest_seq; wraps)
     cudaEvent_t ev_pose_done[2] = {}, ev_rest_done[2] = {}; // batched engine: TrackOverlap events, by frame parity
     FrameResult *d_result = nullptr, *h_result = nullptr;
     int *h_error = nullptr; // pinned copy of ws.error, fetched together with the result
@@ -492,7 +492,7 @@ static int ctx_launch_track(lvtk_ctx *c, FrameResult *result, const FeatDev *fea
     if (overlap)
         c->frame_seq++;
     TrackOverlap ov{c->xs[3], c->ev_pose_done[c->ctl_idx], c->ev_rest_done[c->ctl_idx], c->ev_rest_done[c->ctl_idx ^ 1], overlap == 2,
-                    c->frame_seq, next_feats};
+                    (int)c->frame_seq, next_feats};
     return launch_track_frame(c->d_state, ctl, result, c->map, c->staged, feats, c->tp, c->sc, row_cand, c->tcfg, c->ws.error, st,
                               right_ready, parts, early, early_seq, overlap ? &ov : nullptr, ctl_prev);
 }

@@ -70,7 +70,7 @@ struct TrackArgs
     int *error;         // the context's sticky error flag (the one the host fetches with every result)
     const FrameCtl *ctl_prev; // the previous frame's hand-over block (the early parts read its mode / pose / culled map size)
     int part;                 // track_a_kernel: 0 the whole map pass, 1 its early part, 2 the rest (see there)
-    int wait_seq;             // part 2: TrackState::rest_seq to wait for before anything else (0: nothing)
+    int wait_seq;             // part 2: TrackState::rest_seq to wait for before anything else
 };
 
 struct TrackShared
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
         }
         return;
     }
-    if (a.wait_seq != 0)
+    if (a.part == 2)
     {
         // the previous frame's map maintenance runs on another stream: wait for its sequence number (signal_kernel).
         // Everything it depends on was submitted before this kernel, so it cannot be queued behind us; the bound
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_a_kernel(TrackArgs a)
             {
                 int seen;
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(&S.rest_seq) : "memory");
-                if (seen - a.wait_seq >= 0)
+                if ((int)((unsigned)seen - (unsigned)a.wait_seq) >= 0) // sequence numbers wrap
                     break;
                 if (phase_clock() - t0 > 2000000000ll)
                 {
@@ -1216,7 +1216,7 @@ int launch_track_frame(TrackState *st, void *ctl_v, FrameResult *result, const P
         // (Parameter sets that send every new point straight to the map -- no staging, RGB-D -- append hundreds to
         // thousands of points per frame: there the rest keeps the cluster for their rounds.)
         a.part = 2;
-        a.wait_seq = ov->seq - 1;
+        a.wait_seq = (int)((unsigned)ov->seq - 1u);
         const int rest_ctas = (tp.staged_threshold == 0 || tp.sensor == 2) ? cfg.cluster : 1;
         LVT_TIMED(stream, K_TRACK_A,
                   launch_chained_cluster(track_a_kernel, dim3(rest_ctas), dim3(kTrackThreads), smem, stream, rest_ctas, a));
