@@ -301,100 +301,6 @@ __device__ int replay_component(const uint32_t *pts, const uint8_t *sc, int n)
     return 0;
 }
 
-// a local maximum: flood its component, decide whether it is the component's survivor.
-// score_at(x, y) = corner score at the current threshold, 0 outside the image / below it.
-template <class ScoreAt>
-__device__ bool nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, int y, int s)
-{
-    // flood the component; give up as soon as anything larger shows up.  Visited test: linear
-    // search while the component is small, then a 64x32-pixel bitmap around the start pixel
-    // (pixels outside that window keep the linear search).
-    uint32_t pts[kCompCap];
-    uint8_t sc[kCompCap];
-    uint32_t bm[64];
-    bool use_bm = false;
-    const int wx0 = x - 32, wy0 = y - 16;
-    auto in_win = [&](int qx, int qy) { return (unsigned)(qx - wx0) < 64u && (unsigned)(qy - wy0) < 32u; };
-    auto bm_set = [&](int qx, int qy) { bm[(qy - wy0) * 2 + ((qx - wx0) >> 5)] |= 1u << ((qx - wx0) & 31); };
-    int n = 1, head = 0;
-    bool tie = false;
-    pts[0] = ((uint32_t)y << 16) | (uint32_t)x;
-    sc[0] = (uint8_t)s;
-    while (head < n)
-    {
-        const uint32_t p = pts[head++];
-        const int px = (int)(p & 0xFFFFu), py = (int)(p >> 16);
-        // the four neighbour loads are independent: issue them together
-        int vv[4];
-#pragma unroll
-        for (int d = 0; d < 4; d++)
-            vv[d] = score_at(px + (d == 0) - (d == 1), py + (d == 2) - (d == 3));
-        if (max(max(vv[0], vv[1]), max(vv[2], vv[3])) > s)
-            return false;
-#pragma unroll
-        for (int d = 0; d < 4; d++)
-        {
-            const int qx = px + (d == 0) - (d == 1), qy = py + (d == 2) - (d == 3);
-            const int v = vv[d];
-            if (v == 0)
-                continue;
-            const uint32_t q = ((uint32_t)qy << 16) | (uint32_t)qx;
-            bool seen = false;
-            if (use_bm && in_win(qx, qy))
-                seen = (bm[(qy - wy0) * 2 + ((qx - wx0) >> 5)] >> ((qx - wx0) & 31)) & 1u;
-            else
-                for (int j = 0; j < n; j++)
-                    seen |= (pts[j] == q);
-            if (seen)
-                continue;
-            if (n == kCompCap)
-            {
-                queue_big_candidate(a, b, x, y, s); // tile_kernel floods it with the whole CTA
-                return false;
-            }
-            tie |= (v == s);
-            pts[n] = q;
-            sc[n] = (uint8_t)v;
-            n++;
-            if (use_bm && in_win(qx, qy))
-                bm_set(qx, qy);
-            if (!use_bm && n == 16)
-            {
-                for (int k = 0; k < 64; k++)
-                    bm[k] = 0;
-                for (int j = 0; j < n; j++)
-                {
-                    const int jx = (int)(pts[j] & 0xFFFFu), jy = (int)(pts[j] >> 16);
-                    if (in_win(jx, jy))
-                        bm_set(jx, jy);
-                }
-                use_bm = true;
-            }
-        }
-    }
-    if (!tie)
-        return true; // unique maximum of its component
-    // several pixels share the maximum: OpenCV's merge order decides.  Insertion sort to
-    // raster order, replay, and emit only if this pixel is the root.
-    const uint32_t self = pts[0];
-    for (int i = 1; i < n; i++)
-    {
-        const uint32_t p = pts[i];
-        const uint8_t v = sc[i];
-        int j = i - 1;
-        while (j >= 0 && pts[j] > p)
-        {
-            pts[j + 1] = pts[j];
-            sc[j + 1] = sc[j];
-            j--;
-        }
-        pts[j + 1] = p;
-        sc[j + 1] = v;
-    }
-    const int root = replay_component(pts, sc, n);
-    return pts[root] == self;
-}
-
 // Fused NMS.  A CTA stages a 64x64 window of the score map (its 32x32 pixels + 16 px halo) in shared
 // memory and labels the 4-connected corner components inside it by max-propagation: every corner
 // starts with (score << 12 | local index) and repeatedly takes the maximum over itself and its four
@@ -402,10 +308,10 @@ __device__ bool nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, in
 // component's maximum.  Then, per pixel of the interior:
 //   * score below the component maximum             -> suppressed
 //   * the only pixel carrying the maximum           -> survivor          (the common case)
-//   * one of several pixels carrying the maximum    -> OpenCV's merge order decides: nms_resolve
-//   * component reaches the window's outer ring     -> labels may be incomplete: nms_resolve
+//   * one of several pixels carrying the maximum    -> OpenCV's merge order decides (warp_replay_component)
+//   * component reaches the window's outer ring     -> labels may be incomplete: warp_nms_resolve
 // The propagation is a few dozen shared-memory sweeps over the corner list; the sequential flood
-// of nms_resolve is left for ties and for components that leave the window.
+// of warp_nms_resolve is left for components that leave the window.
 constexpr int kNmsTile = 48, kNmsHalo = 8, kNmsWin = kNmsTile + 2 * kNmsHalo;
 constexpr uint32_t kNmsOpen = 0xFFFFFFFFu; // label of a corner on the window's ring
 constexpr int kNmsSlowCap = 256;           // per CTA: components with a shared maximum / open-label candidates;
@@ -417,12 +323,131 @@ constexpr int kNmsSlowCap = 256;           // per CTA: components with a shared 
 // raster order and link each to the member directly above; lane 0 then replays OpenCV's merge
 // sequence (same decisions as replay_component) on shared-memory arrays.  Returns the local index of
 // the surviving root, or -1 if the component has more than kCompCap pixels.
-struct WarpComp
+struct alignas(4) WarpComp
 {
     uint16_t mem[kCompCap];
     uint8_t above[kCompCap], sc[kCompCap];
     int8_t par[kCompCap];
 };
+// the same per-warp shared memory while a warp floods a component that leaves the window (warp_nms_resolve: behind the
+// warp's last warp_replay_component job, so the two uses never overlap)
+struct WarpFlood
+{
+    uint32_t pts[kCompCap]; // y << 16 | x, image coordinates
+    uint8_t sc[kCompCap];
+};
+static_assert(sizeof(WarpFlood) <= sizeof(WarpComp), "the flood's member list lives in the warp's WarpComp");
+
+// A local maximum (x, y, s) whose component reaches the window's ring: one WARP floods the component through the
+// score map, breadth first -- every step takes eight members of the current layer and their four neighbours each,
+// one neighbour per lane, so the trips to the score map outside the window (L2) are paid per layer, not per pixel
+// (the one-thread flood this replaces took up to 120 us for a single candidate on densely cornered images).  The
+// outcome does not depend on the order of the walk: a stronger pixel anywhere in the component suppresses the
+// candidate; more than kCompCap members send it to tile_kernel (which floods it with a whole CTA); a unique maximum
+// survives; with several pixels at the maximum the members are sorted to raster order and lane 0 replays OpenCV's
+// merge sequence (replay_component).  All lanes call; returns the verdict in every lane.
+template <class ScoreAt>
+__device__ bool warp_nms_resolve(const NmsArgs &a, int b, ScoreAt score_at, int x, int y, int s, WarpFlood &w)
+{
+    const int lane = threadIdx.x & 31;
+    int n = 1, head = 0;
+    bool tie = false;
+    if (lane == 0)
+    {
+        w.pts[0] = ((uint32_t)y << 16) | (uint32_t)x;
+        w.sc[0] = (uint8_t)s;
+    }
+    __syncwarp();
+    while (head < n)
+    {
+        const int end = n; // the layer [head, end); members found on the way are appended behind it
+        for (int base = head; base < end; base += 8)
+        {
+            const int j = base + (lane >> 2), d = lane & 3;
+            bool cand = false;
+            uint32_t q = 0;
+            int v = 0;
+            if (j < end)
+            {
+                const uint32_t p = w.pts[j];
+                const int qx = (int)(p & 0xFFFFu) + (d == 0) - (d == 1), qy = (int)(p >> 16) + (d == 2) - (d == 3);
+                v = score_at(qx, qy);
+                q = ((uint32_t)qy << 16) | (uint32_t)qx;
+                cand = v != 0;
+            }
+            if (__any_sync(0xFFFFFFFFu, cand && v > s))
+                return false; // beaten inside its own component
+            if (cand) // a member already?
+                for (int k = 0; k < n; k++)
+                    if (w.pts[k] == q)
+                    {
+                        cand = false;
+                        break;
+                    }
+            // the same pixel reached from two members in this step: the lowest lane keeps it
+            const unsigned active = __ballot_sync(0xFFFFFFFFu, cand);
+            if (cand)
+            {
+                const unsigned peers = __match_any_sync(active, q);
+                cand = lane == __ffs(peers) - 1;
+            }
+            const unsigned add = __ballot_sync(0xFFFFFFFFu, cand);
+            const int cnt = __popc(add);
+            if (n + cnt > kCompCap)
+            {
+                if (lane == 0)
+                    queue_big_candidate(a, b, x, y, s); // tile_kernel floods it with the whole CTA
+                return false;
+            }
+            if (cand)
+            {
+                const int pos = n + __popc(add & ((1u << lane) - 1u));
+                w.pts[pos] = q;
+                w.sc[pos] = (uint8_t)v;
+            }
+            tie |= __any_sync(0xFFFFFFFFu, cand && v == s);
+            n += cnt;
+            __syncwarp();
+        }
+        head = end;
+    }
+    if (!tie)
+        return true; // unique maximum of its component
+    // several pixels share the maximum: raster order (rank sort through registers: the keys are unique), then the replay
+    const uint32_t self = ((uint32_t)y << 16) | (uint32_t)x;
+    uint32_t mp[3];
+    uint8_t ms[3];
+    int rank[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++)
+    {
+        const int i = lane + 32 * u;
+        mp[u] = i < n ? w.pts[i] : 0xFFFFFFFFu;
+        ms[u] = i < n ? w.sc[i] : (uint8_t)0;
+        rank[u] = 0;
+    }
+    for (int k = 0; k < n; k++)
+    {
+        const uint32_t o = w.pts[k];
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+            rank[u] += o < mp[u];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 3; u++)
+        if (lane + 32 * u < n)
+        {
+            w.pts[rank[u]] = mp[u];
+            w.sc[rank[u]] = ms[u];
+        }
+    __syncwarp();
+    int root = 0;
+    if (lane == 0)
+        root = replay_component(w.pts, w.sc, n);
+    root = __shfl_sync(0xFFFFFFFFu, root, 0);
+    return w.pts[root] == self;
+}
 
 __device__ int warp_replay_component(const uint32_t *lab, const uint8_t *win, int n_win, int row_w, uint32_t L, WarpComp &w)
 {
@@ -741,17 +766,21 @@ __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
         }
     }
     const int n = min(s_ncand, kNmsSlowCap);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = threadIdx.x >> 5; i < n; i += 8) // a warp per candidate
     {
         const uint32_t c = s_cand[i];
 #ifdef LVT_NMS_STATS
         const long long r0 = clock64();
 #endif
-        if (nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24)))
+        const bool keep = warp_nms_resolve(a, b, score_at, (int)(c & 0xFFFu), (int)((c >> 12) & 0xFFFu), (int)(c >> 24),
+                                           *reinterpret_cast<WarpFlood *>(&s_comp[threadIdx.x >> 5]));
+        if (keep && (threadIdx.x & 31) == 0)
             s_surv[atomicAdd(&s_nsurv, 1)] = c;
 #ifdef LVT_NMS_STATS
-        atomicMax(&s_longest, (unsigned long long)(clock64() - r0));
+        if ((threadIdx.x & 31) == 0)
+            atomicMax(&s_longest, (unsigned long long)(clock64() - r0));
 #endif
+        __syncwarp();
     }
     __syncthreads();
     NMS_PHASE(5);
@@ -766,7 +795,7 @@ __global__ void __launch_bounds__(256) nms_tile_kernel(NmsArgs a)
 #endif
 }
 
-// K2b: sequential fallback for a tile flagged by nms_resolve (pathological inputs only); run by
+// K2b: sequential fallback for a tile flagged by the NMS kernel (pathological inputs only); run by
 // one thread of the tile's tile_kernel CTA before it reads the list
 __device__ void nms_fallback_tile(const NmsArgs &a, int *parent_all, int t, int b)
 {
