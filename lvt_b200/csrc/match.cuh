@@ -12,12 +12,13 @@
 //      search window, each with its 256-bit Hamming distance (8 x __popc), packed as
 //      (distance << 20 | index) keys == knnMatch's (distance, index) order, sorted per query by a
 //      warp rank-sort and stored as a fixed-capacity list.  Nothing here depends on the order.
-//   2. rounds (one CTA, one thread per query): every query takes the first two keys of its list
-//      whose feature is not owned by an earlier query, applies the ratio test, and publishes its
-//      choice with atomicMin(owner[f], q); rounds repeat until one changes nothing.  Round r fixes
-//      at least queries 0..r; in practice 2-4 rounds suffice.
-// Queries whose window holds more candidates than the list capacity, the radius x2 retry pass and
-// the (small) staged set take the list-free path: one warp re-scans the window each round.
+//   2. rounds (one thread per query; one CTA, or the CTAs of a cluster for the map pass: RoundsTeam):
+//      every query takes the first two keys of its list whose feature is not owned by an earlier
+//      query, applies the ratio test, and publishes its choice (atomicMin(owner[f], q), or a store
+//      into every CTA's replica of the choices); rounds repeat until one changes nothing.  Round r
+//      fixes at least queries 0..r; 6-7 rounds on the benchmark stream.
+// Queries whose window holds more candidates than the list capacity and the radius x2 retry pass
+// take the list-free path: one warp re-scans the window each round.
 #pragma once
 #include "extract.cuh"
 #include <cooperative_groups.h>

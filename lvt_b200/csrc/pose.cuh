@@ -1,4 +1,4 @@
-// Block-level motion-only bundle adjustment (one CTA), header-only device code.
+// Motion-only bundle adjustment on a thread-block cluster, header-only device code.
 //
 // Replaces the g2o graph built and solved per frame at lvt/src/lvt_pnp_solver.cpp:60-128:
 // one free SBACam vertex, M fixed points, M EdgeProjectP2MC with a Cauchy kernel
@@ -6,11 +6,13 @@
 // LinearSolverPCG == one preconditioned-CG step == one exact solve), two passes of optimize(5),
 // edges with chi2 > 5.991 demoted to level 1 after each pass.
 //
-// Per evaluation every thread takes correspondences i = tid, tid + T, ...: fp64 projection,
-// residual, robust weight and (for the linearisation pass) the 2x6 Jacobian; the 21 + 6 + 1
-// partial sums of H = sum w J^T J, b = -sum w J^T e and the robust cost are reduced with warp
-// shuffles, then across warps through shared memory in a fixed order (deterministic).  Thread 0
-// runs the 6x6 solve and the LM accept / reject logic between evaluations.
+// Per evaluation every thread takes its correspondences (kept in registers across the evaluations):
+// fp64 projection, residual, robust weight and the 2x6 Jacobian; the 21 + 6 + 1 + 1 partial sums of
+// H = sum w J^T J, b = -sum w J^T e, the robust cost and the edge count are reduced inside the warp
+// (transposed butterfly), across the warps of a CTA through shared memory, and across the CTAs of
+// the cluster by counted st.async pushes into every CTA's gather buffer -- always in the same order
+// (deterministic, identical in every CTA).  Warp 0 of EVERY CTA then runs the same 6x6 solve and LM
+// accept / reject logic in registers, so nothing but the sums travels (cluster_solve_pose below).
 #pragma once
 #include "common.cuh"
 #include <cooperative_groups.h>

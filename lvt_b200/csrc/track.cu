@@ -3,17 +3,22 @@
 // of match.cuh, pose.cuh, track.cuh.
 //
 // lvt_system::perform_tracking (lvt/src/lvt_system.cpp:252-306) per frame, all on the device:
-//   mapcand_kernel    whole GPU   predict pose, project the map, candidate keys per map point
-//   track_a_kernel    1 CTA       greedy rounds over the key lists (+ radius x2 retry), marks,
-//                                 map bookkeeping, solver inputs, LOST decision
-//   pose_kernel       8-CTA cluster  motion-only BA (fp64 LM, Cauchy), reductions through DSMEM
-//   stagedcand        whole GPU   project the staged points with the new pose, candidate keys
-//   track_b_kernel    1 CTA       cull, staged rounds + promotion, triangulation policy,
-//                                 row-matching rounds, triangulation, state + result
-// The serial parts are instruction-latency bound, so the single-CTA kernels run 1024 threads and
-// keep fp64-heavy, register-hungry work out (pose has its own kernel); every data-parallel part
-// (candidate generation, projection, Jacobians) is spread over many SMs.  No host round trip:
-// all control flow (first frame, lost, retry, policy) is decided on the device through FrameCtl.
+//   mapcand_kernel    whole GPU      project the map with the predicted pose, sorted candidate keys per map point
+//   track_a_kernel    8-CTA cluster  greedy rounds over the key lists (+ radius x2 retry); rank 0: marks, map
+//                                    bookkeeping, solver inputs, LOST decision
+//   pose_kernel       2 x 8 CTAs     cluster 0: motion-only BA (fp64 LM, Cauchy), sums exchanged through DSMEM, then
+//                                    the motion model's prediction for the next frame; cluster 1: map culling
+//   mapcand_kernel    whole GPU      ("stagedcand") the staged points under the new pose, candidate keys
+//   track_b_kernel    1 CTA          staged rounds + promotion, triangulation policy, row-matching rounds,
+//                                    triangulation, state + result
+// The serial parts are instruction-latency bound, so the 1024-thread kernels keep fp64-heavy, register-hungry work
+// out (pose has its own kernel); every data-parallel part (candidate generation, projection, Jacobians) is spread
+// over many SMs.  No host round trip: all control flow (first frame, lost, retry, policy, refusal for growth) is
+// decided on the device through FrameCtl.
+//
+// The batched engine (context.cu, run_frames) runs stagedcand + track_b of frame t on a side stream next to frame
+// t+1's candidate listing and the early part of its map pass (TrackOverlap, track_a_kernel's parts, signal_kernel):
+// track_b only appends to the map, and appended points come last in the greedy order.
 #include "track.cuh"
 #include <algorithm>
 #include <cstdio>

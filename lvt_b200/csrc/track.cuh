@@ -3,9 +3,9 @@
 //
 // The reference keeps the local map in host vectors (lvt/src/lvt_local_map.h:64-85) and walks
 // them with scalar loops.  Here the map lives in HBM as structure-of-arrays and the whole of
-// lvt_system::perform_tracking (lvt/src/lvt_system.cpp:252-306) runs as ONE persistent CTA per
-// frame: projection matching, pose solve, culling, staging, triangulation -- no host round trip
-// between the stages, only the pose and the per-frame counters leave the GPU.
+// lvt_system::perform_tracking (lvt/src/lvt_system.cpp:252-306) runs as a chain of kernels per
+// frame (track.cu): projection matching, pose solve, culling, staging, triangulation -- no host
+// round trip between the stages, only the pose and the per-frame counters leave the GPU.
 #pragma once
 #include "match.cuh"
 #include "pose.cuh"
