@@ -377,6 +377,14 @@ class System:
         self.lib.lvt_debug_phase_cycles(C.c_void_p(self.h), i, cyc, rnd)
         return {"rounds": list(rnd)[:4], "lm_evaluations": rnd[4]}
 
+    def frame_marks(self, i=-1):
+        """profiling aid (CUDA library): nanosecond marks of pool frame i of the last batch (i < 0: of the last blocking
+        call): [0..7] inside track_b (start, staged rounds, promotion, staged compaction, row matching, triangulation,
+        append, state), [8], [9] start / end of the frame's early map pass in the batched engine; 0 = phase not run"""
+        m = (C.c_longlong * 12)()
+        self.lib.lvt_debug_frame_marks(C.c_void_p(self.h), i, m)
+        return list(m)
+
     def last_batch_ms(self):
         return float(self.lib.lvt_last_batch_ms(self.h))
 
